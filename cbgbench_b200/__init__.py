@@ -1,0 +1,16 @@
+"""cbgbench_b200 - B200-native implementation of CBGBench's diffusion-sampling hot path.
+
+Only what the path needs:
+  csrc/         hand-written sm_100a CUDA kernels + the C-ABI (include/cbg_b200.h)
+  modules.py    nn.Module mirror of the reference denoiser (same signatures / state-dict keys)
+  targetdiff.py TargetDiff.sample drop-in (outer diffusion loop in Python, one C call per step)
+  schedulers.py noise-schedule tables (checkpoint-compatible parameter containers)
+  sharding.py   pocket sharding over GPUs + the single gather of final coordinates
+  synthetic.py  synthetic pockets / seeded weights for tests and benchmarks
+
+There is no CPU or PyTorch fallback: compute entry points raise if libcbg_b200.so is missing.
+"""
+from .modules import UniTransformerB200, get_e3_gnn  # noqa: F401
+from .targetdiff import TargetDiffB200, get_model, register_model  # noqa: F401
+
+__version__ = '0.1.0'

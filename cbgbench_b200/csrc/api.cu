@@ -1,0 +1,345 @@
+// C-ABI of libcbg_b200.so (declared in include/cbg_b200.h) and the per-forward orchestration.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/cbg_b200.h"
+#include "cbg_kernels.cuh"
+
+long long g_cbg_launches = 0;
+
+static thread_local char g_err[1024] = "";
+
+void cbg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+struct FieldInfo { const char* name; long long size; };
+const FieldInfo kGlobalFields[] = {
+#define X(name, n) {#name, (long long)(n)},
+    CBG_GLOBAL_FIELDS(X)
+#undef X
+};
+const FieldInfo kLayerFields[] = {
+#define X(name, n) {#name, (long long)(n)},
+    CBG_LAYER_FIELDS(X)
+#undef X
+};
+
+inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// workspace carve-up
+struct Workspace {
+  float4* x4;
+  float* h;
+  float* plane[CBG_NPLANES];   // pj_k, pj_v, pi_k, pi_v, q
+  float* w;
+  int* nbr;
+  float* ew;
+  float* dx;
+  size_t bytes;
+};
+
+Workspace carve(void* base, long long n_nodes, long long n_gen) {
+  Workspace ws;
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t nbytes) { char* p = b ? b + off : nullptr; off += align256(nbytes); return p; };
+  ws.x4 = (float4*)take((size_t)n_nodes * sizeof(float4));
+  ws.h = (float*)take((size_t)n_nodes * CBG_H * 4);
+  for (int p = 0; p < CBG_NPLANES; ++p) ws.plane[p] = (float*)take((size_t)n_nodes * CBG_H * 4);
+  ws.w = (float*)take((size_t)n_nodes * CBG_KMAX * CBG_HEADS * 4);
+  ws.nbr = (int*)take((size_t)n_nodes * CBG_KMAX * 4);
+  ws.ew = (float*)take((size_t)n_nodes * CBG_KMAX * 4);
+  ws.dx = (float*)take((size_t)(n_gen > 0 ? n_gen : 1) * 16);
+  ws.bytes = off;
+  return ws;
+}
+
+int check_ws(const void* workspace, size_t have, long long n_nodes, long long n_gen, Workspace* out) {
+  if (n_nodes < 0 || n_gen < 0) { cbg_set_error("negative size"); return 1; }
+  Workspace ws = carve(const_cast<void*>(workspace), n_nodes, n_gen);
+  if (!workspace || have < ws.bytes) {
+    cbg_set_error("workspace too small: have %zu bytes, need %zu (cbg_workspace_bytes)", have, ws.bytes);
+    return 1;
+  }
+  if (((uintptr_t)workspace & 255) != 0) { cbg_set_error("workspace must be 256-byte aligned"); return 1; }
+  *out = ws;
+  return 0;
+}
+
+// graph build + gate + layers on an initialised workspace (x4, h valid)
+int run_core(const float* blob, int num_layers, const Workspace& ws, const int* graph_ptr, int n_graphs,
+             int max_graph_nodes, long long n_nodes, const int* gen_idx, int n_gen, int mode, int k,
+             float r_max, cudaStream_t st) {
+  if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
+  if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, ws.nbr, st)) return rc;
+  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, ws.ew, st)) return rc;
+  const float* layers = blob + cbg_layout::kGlobalFloats;
+  for (int l = 0; l < num_layers; ++l) {
+    const float* L = layers + (size_t)l * cbg_layout::kLayerFloats;
+    // ---- X2H: node planes (all nodes), attention weights, aggregation (h updated in place)
+    NodeGemmArgs g{};
+    g.a = ws.h; g.row_idx = nullptr; g.n_rows = (int)n_nodes;
+    g.wt = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_WT);
+    g.bias = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_B);
+    g.ldw = 640; g.n_planes = 5; g.has_q = 1;
+    for (int p = 0; p < 4; ++p) g.out[p] = ws.plane[p];
+    g.out[4] = nullptr;
+    g.q_ln = L + cbg_layout::layer_offset(CBG_LF_X2H_Q_LN);
+    g.q_w1t = L + cbg_layout::layer_offset(CBG_LF_X2H_Q_W1T);
+    g.q_b1 = L + cbg_layout::layer_offset(CBG_LF_X2H_Q_B1);
+    g.out_q = ws.plane[4];
+    if (int rc = cbg_launch_node_gemm(g, st)) return rc;
+    EdgeArgs e{};
+    e.x4 = ws.x4; e.nbr = ws.nbr; e.ew = ws.ew;
+    e.pj_k = ws.plane[0]; e.pj_v = ws.plane[1]; e.pi_k = ws.plane[2]; e.pi_v = ws.plane[3]; e.q = ws.plane[4];
+    e.layer = L; e.w = ws.w; e.h = ws.h; e.node_idx = nullptr; e.n_nodes = (int)n_nodes; e.dx = nullptr;
+    if (int rc = cbg_launch_x2h(e, st)) return rc;
+    if (n_gen <= 0) continue;   // nothing moves: H2X output is multiplied by gen_flag == 0
+    // ---- H2X (uses the NEW h and the layer-input x): Pj planes for all nodes, Pi/q for generated nodes
+    NodeGemmArgs gj{};
+    gj.a = ws.h; gj.row_idx = nullptr; gj.n_rows = (int)n_nodes;
+    gj.wt = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_WT);
+    gj.bias = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_B);
+    gj.ldw = 640; gj.n_planes = 2; gj.has_q = 0;
+    gj.out[0] = ws.plane[0]; gj.out[1] = ws.plane[1];
+    if (int rc = cbg_launch_node_gemm(gj, st)) return rc;
+    NodeGemmArgs gi{};
+    gi.a = ws.h; gi.row_idx = gen_idx; gi.n_rows = n_gen;
+    gi.wt = gj.wt + 256; gi.bias = gj.bias + 256;
+    gi.ldw = 640; gi.n_planes = 3; gi.has_q = 1;
+    gi.out[0] = ws.plane[2]; gi.out[1] = ws.plane[3]; gi.out[2] = nullptr;
+    gi.q_ln = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_LN);
+    gi.q_w1t = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_W1T);
+    gi.q_b1 = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_B1);
+    gi.out_q = ws.plane[4];
+    if (int rc = cbg_launch_node_gemm(gi, st)) return rc;
+    EdgeArgs x = e;
+    x.node_idx = gen_idx; x.n_nodes = n_gen; x.dx = ws.dx;
+    if (int rc = cbg_launch_h2x(x, st)) return rc;
+    if (int rc = cbg_launch_apply_dx(ws.x4, gen_idx, ws.dx, n_gen, st)) return rc;
+  }
+  return 0;
+}
+
+// cached device scratch for the *_host entry points
+struct HostCache {
+  void* dev = nullptr;
+  size_t bytes = 0;
+  float* blob = nullptr;
+  long long blob_floats = 0;
+  long long blob_version = -1;
+} g_cache;
+
+int cache_reserve(size_t bytes) {
+  if (g_cache.bytes >= bytes) return 0;
+  if (g_cache.dev) CBG_CUDA_OK(cudaFree(g_cache.dev));
+  g_cache.dev = nullptr; g_cache.bytes = 0;
+  CBG_CUDA_OK(cudaMalloc(&g_cache.dev, bytes));
+  g_cache.bytes = bytes;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t cbg_version(void) { return 100; }
+const char* cbg_last_error(void) { return g_err; }
+int64_t cbg_launch_count(void) { return g_cbg_launches; }
+
+int64_t cbg_blob_global_floats(void) { return cbg_layout::kGlobalFloats; }
+int64_t cbg_blob_layer_floats(void) { return cbg_layout::kLayerFloats; }
+int32_t cbg_blob_num_fields(int32_t section) { return section == 0 ? (int)CBG_GF_COUNT : (section == 1 ? (int)CBG_LF_COUNT : -1); }
+const char* cbg_blob_field_name(int32_t section, int32_t idx) {
+  if (section == 0 && idx >= 0 && idx < CBG_GF_COUNT) return kGlobalFields[idx].name;
+  if (section == 1 && idx >= 0 && idx < CBG_LF_COUNT) return kLayerFields[idx].name;
+  return nullptr;
+}
+int64_t cbg_blob_field_size(int32_t section, int32_t idx) {
+  if (section == 0 && idx >= 0 && idx < CBG_GF_COUNT) return kGlobalFields[idx].size;
+  if (section == 1 && idx >= 0 && idx < CBG_LF_COUNT) return kLayerFields[idx].size;
+  return -1;
+}
+int64_t cbg_blob_field_offset(int32_t section, int32_t idx) {
+  if (section == 0 && idx >= 0 && idx < CBG_GF_COUNT) return cbg_layout::global_offset(idx);
+  if (section == 1 && idx >= 0 && idx < CBG_LF_COUNT) return cbg_layout::layer_offset(idx);
+  return -1;
+}
+
+int64_t cbg_workspace_bytes(int64_t n_nodes, int64_t n_gen) {
+  if (n_nodes < 0 || n_gen < 0) return -1;
+  return (int64_t)carve(nullptr, n_nodes, n_gen).bytes;
+}
+
+int32_t cbg_build_neighbors_f32(const float* x, const int32_t* graph_ptr, int32_t n_graphs, int64_t n_nodes,
+                                int32_t max_graph_nodes, int32_t mode, int32_t k, float r_max, int32_t* nbr,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  if (int rc = check_ws(workspace, workspace_bytes, n_nodes, 0, &ws)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  // flags are irrelevant for the neighbour search: pack with zeros
+  CBG_CUDA_OK(cudaMemsetAsync(ws.nbr, 0, (size_t)n_nodes, st));   // reuse as a zero flag array
+  if (int rc = cbg_launch_pack_x4(x, (const unsigned char*)ws.nbr, (const unsigned char*)ws.nbr, n_nodes, ws.x4, st)) return rc;
+  return cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, nbr, st);
+}
+
+int32_t cbg_edge_gate_f32(const float* blob, const float* x, const int32_t* nbr, int64_t n_nodes, float* ew,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  if (int rc = check_ws(workspace, workspace_bytes, n_nodes, 0, &ws)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CBG_CUDA_OK(cudaMemsetAsync(ws.nbr, 0, (size_t)n_nodes, st));
+  if (int rc = cbg_launch_pack_x4(x, (const unsigned char*)ws.nbr, (const unsigned char*)ws.nbr, n_nodes, ws.x4, st)) return rc;
+  return cbg_launch_edge_gate(blob, ws.x4, nbr, n_nodes, ew, st);
+}
+
+int32_t cbg_denoiser_forward_f32(const float* blob, int32_t num_layers, int32_t num_classes, const float* x,
+                                 const float* h, const int32_t* graph_ptr, int32_t n_graphs,
+                                 int32_t max_graph_nodes, const uint8_t* lig_flag, const uint8_t* gen_flag,
+                                 const int32_t* gen_idx, int32_t n_gen, const int32_t* cls_idx, int32_t n_cls,
+                                 int64_t n_nodes, int32_t mode, int32_t k, float r_max, int32_t stop_after_layers,
+                                 float* x_out, float* h_out, float* logits_out, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  Workspace ws;
+  if (int rc = check_ws(workspace, workspace_bytes, n_nodes, n_gen, &ws)) return rc;
+  if (num_layers < 0) { cbg_set_error("num_layers < 0"); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = cbg_launch_pack_x4(x, lig_flag, gen_flag, n_nodes, ws.x4, st)) return rc;
+  CBG_CUDA_OK(cudaMemcpyAsync(ws.h, h, (size_t)n_nodes * CBG_H * 4, cudaMemcpyDeviceToDevice, st));
+  const int L = (stop_after_layers >= 0 && stop_after_layers < num_layers) ? stop_after_layers : num_layers;
+  if (int rc = run_core(blob, L, ws, graph_ptr, n_graphs, max_graph_nodes, n_nodes, gen_idx, n_gen, mode, k, r_max, st)) return rc;
+  if (x_out) { if (int rc = cbg_launch_unpack_x(ws.x4, n_nodes, x_out, st)) return rc; }
+  if (h_out) CBG_CUDA_OK(cudaMemcpyAsync(h_out, ws.h, (size_t)n_nodes * CBG_H * 4, cudaMemcpyDeviceToDevice, st));
+  if (logits_out) {
+    const int rows = cls_idx ? n_cls : (int)n_nodes;
+    if (int rc = cbg_launch_classifier(blob, ws.h, cls_idx, rows, num_classes, logits_out, st)) return rc;
+  }
+  return 0;
+}
+
+int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_floats, int64_t blob_version,
+                                      int32_t num_layers, int32_t num_classes, const float* x_host,
+                                      const float* h_host, const int32_t* graph_ptr_host, int32_t n_graphs,
+                                      const uint8_t* lig_flag_host, const uint8_t* gen_flag_host, int64_t n_nodes,
+                                      int32_t mode, int32_t k, float r_max, float* x_out_host, float* h_out_host,
+                                      float* logits_out_host) {
+  if (n_nodes <= 0 || n_graphs <= 0) { cbg_set_error("empty batch"); return 1; }
+  if (num_classes < 1 || num_classes > CBG_MAXCLS) { cbg_set_error("num_classes=%d outside [1,%d]", num_classes, CBG_MAXCLS); return 1; }
+  if (blob_floats != cbg_layout::kGlobalFloats + (long long)num_layers * cbg_layout::kLayerFloats) {
+    cbg_set_error("blob has %lld floats, expected %lld", (long long)blob_floats,
+                  cbg_layout::kGlobalFloats + (long long)num_layers * cbg_layout::kLayerFloats);
+    return 1;
+  }
+  // host-side graph statistics and the generated-node list
+  int max_graph_nodes = 0;
+  for (int g = 0; g < n_graphs; ++g) {
+    const int n = graph_ptr_host[g + 1] - graph_ptr_host[g];
+    if (n < 0) { cbg_set_error("graph_ptr not monotone"); return 1; }
+    if (n > max_graph_nodes) max_graph_nodes = n;
+  }
+  if (graph_ptr_host[0] != 0 || graph_ptr_host[n_graphs] != n_nodes) { cbg_set_error("graph_ptr must span [0, n_nodes]"); return 1; }
+  std::vector<int> gen_idx;
+  for (long long i = 0; i < n_nodes; ++i) if (gen_flag_host[i]) gen_idx.push_back((int)i);
+  const int n_gen = (int)gen_idx.size();
+
+  if (g_cache.blob_version != blob_version || g_cache.blob_floats != blob_floats) {
+    if (g_cache.blob) CBG_CUDA_OK(cudaFree(g_cache.blob));
+    g_cache.blob = nullptr;
+    CBG_CUDA_OK(cudaMalloc((void**)&g_cache.blob, (size_t)blob_floats * 4));
+    CBG_CUDA_OK(cudaMemcpy(g_cache.blob, blob_host, (size_t)blob_floats * 4, cudaMemcpyHostToDevice));
+    g_cache.blob_floats = blob_floats;
+    g_cache.blob_version = blob_version;
+  }
+  const size_t ws_bytes = carve(nullptr, n_nodes, n_gen).bytes;
+  size_t off = ws_bytes;
+  auto region = [&](size_t nbytes) { size_t o = off; off += align256(nbytes); return o; };
+  const size_t o_x = region((size_t)n_nodes * 12), o_h = region((size_t)n_nodes * CBG_H * 4);
+  const size_t o_gp = region((size_t)(n_graphs + 1) * 4), o_lf = region((size_t)n_nodes), o_gf = region((size_t)n_nodes);
+  const size_t o_gi = region((size_t)(n_gen > 0 ? n_gen : 1) * 4);
+  const size_t o_xo = region((size_t)n_nodes * 12), o_ho = region((size_t)n_nodes * CBG_H * 4);
+  const size_t o_lo = region((size_t)n_nodes * num_classes * 4);
+  if (int rc = cache_reserve(off)) return rc;
+  char* d = (char*)g_cache.dev;
+  cudaStream_t st = 0;
+  CBG_CUDA_OK(cudaMemcpyAsync(d + o_x, x_host, (size_t)n_nodes * 12, cudaMemcpyHostToDevice, st));
+  CBG_CUDA_OK(cudaMemcpyAsync(d + o_h, h_host, (size_t)n_nodes * CBG_H * 4, cudaMemcpyHostToDevice, st));
+  CBG_CUDA_OK(cudaMemcpyAsync(d + o_gp, graph_ptr_host, (size_t)(n_graphs + 1) * 4, cudaMemcpyHostToDevice, st));
+  CBG_CUDA_OK(cudaMemcpyAsync(d + o_lf, lig_flag_host, (size_t)n_nodes, cudaMemcpyHostToDevice, st));
+  CBG_CUDA_OK(cudaMemcpyAsync(d + o_gf, gen_flag_host, (size_t)n_nodes, cudaMemcpyHostToDevice, st));
+  if (n_gen) CBG_CUDA_OK(cudaMemcpyAsync(d + o_gi, gen_idx.data(), (size_t)n_gen * 4, cudaMemcpyHostToDevice, st));
+  if (int rc = cbg_denoiser_forward_f32(g_cache.blob, num_layers, num_classes, (const float*)(d + o_x),
+                                        (const float*)(d + o_h), (const int32_t*)(d + o_gp), n_graphs,
+                                        max_graph_nodes, (const uint8_t*)(d + o_lf), (const uint8_t*)(d + o_gf),
+                                        (const int32_t*)(d + o_gi), n_gen, nullptr, 0, n_nodes, mode, k, r_max, -1,
+                                        (float*)(d + o_xo), (float*)(d + o_ho), (float*)(d + o_lo), d, ws_bytes, st))
+    return rc;
+  if (x_out_host) CBG_CUDA_OK(cudaMemcpyAsync(x_out_host, d + o_xo, (size_t)n_nodes * 12, cudaMemcpyDeviceToHost, st));
+  if (h_out_host) CBG_CUDA_OK(cudaMemcpyAsync(h_out_host, d + o_ho, (size_t)n_nodes * CBG_H * 4, cudaMemcpyDeviceToHost, st));
+  if (logits_out_host) CBG_CUDA_OK(cudaMemcpyAsync(logits_out_host, d + o_lo, (size_t)n_nodes * num_classes * 4, cudaMemcpyDeviceToHost, st));
+  CBG_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, const uint8_t* lig_flag,
+                             const uint8_t* gen_flag, void* stream) {
+  if (!plan) { cbg_set_error("null plan"); return 1; }
+  Workspace ws;
+  if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
+  return cbg_launch_pack_x4(x_nodes, lig_flag, gen_flag, plan->n_nodes, ws.x4, (cudaStream_t)stream);
+}
+
+int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* coef, const float* x_t,
+                            const float* c_t, const float* pos_noise, const float* type_uniform, float* x_next,
+                            float* c_next, int64_t* v_next, float* x0_pred, float* logits, void* stream) {
+  if (!plan || !coef) { cbg_set_error("null plan/coef"); return 1; }
+  Workspace ws;
+  if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = plan->num_classes;
+  if (K < 1 || K > CBG_MAXCLS) { cbg_set_error("num_classes=%d outside [1,%d]", K, CBG_MAXCLS); return 1; }
+  if (int rc = cbg_launch_step_init(x_t, c_t, plan->lig_node, plan->n_lig, K, plan->emb_wt, plan->h_lig_bias,
+                                    plan->h_static, plan->n_nodes, ws.x4, ws.h, st)) return rc;
+  if (int rc = run_core(plan->blob, plan->num_layers, ws, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes,
+                        plan->n_nodes, plan->gen_node, plan->n_gen, plan->mode, plan->k, plan->r_max, st)) return rc;
+  // classifier on ligand rows only; logits scratch lives in the w buffer (free after the layers)
+  float* lg = logits ? logits : ws.w;
+  if (int rc = cbg_launch_classifier(plan->blob, ws.h, plan->lig_node, plan->n_lig, K, lg, st)) return rc;
+  ReverseArgs r{};
+  r.x0 = (const float*)ws.x4; r.x0_stride = 4; r.x0_idx = plan->lig_node;
+  r.logits = lg; r.x_t = x_t; r.c_t = c_t; r.gen = plan->gen_lig; r.pos_noise = pos_noise; r.type_u = type_uniform;
+  r.c0 = coef->pos_c0; r.ct = coef->pos_ct;
+  r.lac_prev = coef->log_alphas_cumprod_prev; r.l1mac_prev = coef->log_one_minus_alphas_cumprod_prev;
+  r.la = coef->log_alpha; r.l1ma = coef->log_one_minus_alpha;
+  r.n_lig = plan->n_lig; r.num_classes = K; r.x_next = x_next; r.c_next = c_next; r.v_next = (long long*)v_next;
+  if (int rc = cbg_launch_reverse(r, coef->pos_logvar, coef->pos_nonzero, st)) return rc;
+  if (x0_pred) {   // predicted ligand coordinates (testing / trajectory inspection)
+    if (int rc = cbg_launch_gather_x(ws.x4, plan->lig_node, plan->n_lig, x0_pred, st)) return rc;
+  }
+  return 0;
+}
+
+int32_t cbg_reverse_step_f32(const cbg_step_coef* coef, const float* x0_pred, const float* logits, const float* x_t,
+                             const float* c_t, const uint8_t* gen, const float* pos_noise, const float* type_uniform,
+                             int32_t n, int32_t num_classes, float* x_next, float* c_next, int64_t* v_next,
+                             void* stream) {
+  if (!coef) { cbg_set_error("null coef"); return 1; }
+  if (num_classes < 1 || num_classes > CBG_MAXCLS) { cbg_set_error("num_classes=%d outside [1,%d]", num_classes, CBG_MAXCLS); return 1; }
+  ReverseArgs r{};
+  r.x0 = x0_pred; r.x0_stride = 3; r.x0_idx = nullptr;
+  r.logits = logits; r.x_t = x_t; r.c_t = c_t; r.gen = gen; r.pos_noise = pos_noise; r.type_u = type_uniform;
+  r.c0 = coef->pos_c0; r.ct = coef->pos_ct;
+  r.lac_prev = coef->log_alphas_cumprod_prev; r.l1mac_prev = coef->log_one_minus_alphas_cumprod_prev;
+  r.la = coef->log_alpha; r.l1ma = coef->log_one_minus_alpha;
+  r.n_lig = n; r.num_classes = num_classes; r.x_next = x_next; r.c_next = c_next; r.v_next = (long long*)v_next;
+  return cbg_launch_reverse(r, coef->pos_logvar, coef->pos_nonzero, (cudaStream_t)stream);
+}
+
+}  // extern "C"

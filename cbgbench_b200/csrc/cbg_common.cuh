@@ -1,0 +1,71 @@
+// Shared device helpers for the cbg_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "cbg_layout.h"
+
+#define CBG_FULL 0xffffffffu
+
+// error plumbing (api.cu owns the storage)
+void cbg_set_error(const char* fmt, ...);
+#define CBG_CUDA_OK(expr)                                                        \
+  do {                                                                           \
+    cudaError_t _e = (expr);                                                     \
+    if (_e != cudaSuccess) {                                                     \
+      cbg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return 2;                                                                  \
+    }                                                                            \
+  } while (0)
+
+extern long long g_cbg_launches;
+// after a kernel launch: surface launch errors and count the launch
+#define CBG_LAUNCHED(n)                \
+  do {                                 \
+    CBG_CUDA_OK(cudaGetLastError());   \
+    g_cbg_launches += (n);             \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(CBG_FULL, v, m);
+  return v;
+}
+
+// Reduce NV per-lane values across the 32 lanes of a warp with a halving butterfly.
+// On return lane l holds in v[0 .. NV/32) the full (all-lane) sums of the original
+// indices l*(NV/32) + i.  NV must be a power of two >= 32; 2*NV-64 shuffles... (NV-NV/32).
+template <int NV>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[NV], int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int mask = 16 >> s;
+    const int n = NV >> (s + 1);
+    const bool upper = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? v[i] : v[i + n];
+      const float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(CBG_FULL, send, mask);
+    }
+  }
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ void fma4(float4& acc, const float4 w, const float s) {
+  acc.x = fmaf(w.x, s, acc.x);
+  acc.y = fmaf(w.y, s, acc.y);
+  acc.z = fmaf(w.z, s, acc.z);
+  acc.w = fmaf(w.w, s, acc.w);
+}
+
+// cooperative contiguous copy global -> shared, n floats (multiple of 4), both 16B aligned
+__device__ __forceinline__ void block_copy_f4(float* dst, const float* __restrict__ src, int n_floats) {
+  const int n4 = n_floats >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) st4(dst + 4 * i, ldg4(src + 4 * i));
+}
+
+// node flags are stored as a float in x4.w: 0/1 = ligand bit, +2 = generate bit
+__device__ __forceinline__ int node_flags(const float4 x) { return (int)x.w; }

@@ -1,0 +1,82 @@
+// Internal launcher declarations (one per kernel family).  Not part of the C-ABI.
+#pragma once
+#include "cbg_common.cuh"
+
+#define CBG_MODE_KNN 0
+#define CBG_MODE_RADIUS 1
+
+// graph.cu
+int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max_graph_nodes, int mode,
+                   int k, float r_max, int* nbr, cudaStream_t st);
+int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
+                         float* ew, cudaStream_t st);
+
+// node_gemm.cu
+struct NodeGemmArgs {
+  const float* a;        // [*,128] input rows (h)
+  const int* row_idx;    // optional gather list (node ids); nullptr = identity
+  int n_rows;            // rows to process
+  const float* wt;       // Wt[k][ldw] (k-major), already offset to the first plane's column
+  const float* bias;     // [n_planes*128], already offset
+  int ldw;               // row stride of wt in floats
+  int n_planes;          // planes computed by this launch (the last one is q_hidden if has_q)
+  float* out[CBG_NPLANES];  // destination plane per computed plane ([N,128], indexed by node id)
+  int has_q;             // 1: last plane goes LN->ReLU->W1T GEMM -> out_q instead of global
+  const float* q_ln;     // gamma[128], beta[128]
+  const float* q_w1t;    // [128][128] k-major
+  const float* q_b1;     // [128]
+  float* out_q;          // [N,128]
+};
+int cbg_launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st);
+
+// edge.cu
+struct EdgeArgs {
+  const float4* x4;      // [N] xyz + flags
+  const int* nbr;        // [N,32]
+  const float* ew;       // [N,32]
+  const float* pj_k;     // planes [N,128]
+  const float* pj_v;
+  const float* pi_k;
+  const float* pi_v;
+  const float* q;        // [N,128] (already scaled by 1/sqrt(8))
+  const float* layer;    // base of this layer's weight block
+  float* w;              // [N,32,16] scratch: alpha * e_w
+  float* h;              // [N,128] in/out (x2h_v residual update)
+  const int* node_idx;   // h2x: list of generated nodes
+  int n_nodes;           // x2h: N ; h2x: number of generated nodes
+  float* dx;             // h2x: [n_nodes,4] coordinate deltas (compact, same order as node_idx)
+};
+int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st);
+int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st);
+int cbg_edge_init(void);  // sets max-dynamic-smem attributes once
+
+// misc.cu
+int cbg_launch_pack_x4(const float* x, const unsigned char* lig_flag, const unsigned char* gen_flag,
+                       long long n, float4* x4, cudaStream_t st);
+int cbg_launch_unpack_x(const float4* x4, long long n, float* x, cudaStream_t st);
+int cbg_launch_gather_x(const float4* x4, const int* idx, int n, float* out /*[n,3]*/, cudaStream_t st);
+int cbg_launch_apply_dx(float4* x4, const int* node_idx, const float* dx, int n, cudaStream_t st);
+int cbg_launch_classifier(const float* blob_global, const float* h, const int* row_idx, int n_rows,
+                          int num_classes, float* logits, cudaStream_t st);
+int cbg_launch_step_init(const float* x_lig, const float* c_lig, const int* lig_node, int n_lig,
+                         int num_classes, const float* emb_wt, const float* h_lig_bias,
+                         const float* h_static, long long n_nodes, float4* x4, float* h, cudaStream_t st);
+struct ReverseArgs {
+  const float* x0;         // denoiser output coordinates (x0 prediction), row stride x0_stride floats
+  int x0_stride;           // 4 when reading the packed node array, 3 for a plain [n,3] tensor
+  const int* x0_idx;       // optional row index per ligand atom (lig_node); nullptr = identity
+  const float* logits;     // [n_lig, K]
+  const float* x_t;        // [n_lig,3]
+  const float* c_t;        // [n_lig,K]
+  const unsigned char* gen;  // [n_lig]
+  const float* pos_noise;  // [n_lig,3]
+  const float* type_u;     // [n_lig,K]
+  float c0, ct;            // posterior_mean_c0_coef[t], posterior_mean_ct_coef[t]
+  float lac_prev, l1mac_prev, la, l1ma;  // type tables at t-1 (clamped) and t
+  int n_lig, num_classes;
+  float* x_next;           // [n_lig,3]
+  float* c_next;           // [n_lig,K]
+  long long* v_next;       // [n_lig]
+};
+// logvar = posterior_logvar[t]; nonzero = 0 at t == 0 else 1
+int cbg_launch_reverse(const ReverseArgs& a, float logvar, float nonzero, cudaStream_t st);

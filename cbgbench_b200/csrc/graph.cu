@@ -1,0 +1,171 @@
+// Neighbour-list construction and the global edge gate.
+//
+// Replaces, on the hot path:
+//   [3P] torch_geometric.nn.knn_graph   (call site /root/reference repo/modules/e3nn/unitransformer.py:79-80)
+//   UniTransformer edge gate e_w         (unitransformer.py:109-112, embs/dist_emb.py:6-14,
+//                                         common.py:114-133 GaussianSmearing, :151-171 MLP)
+#include "cbg_kernels.cuh"
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr u64 kInfKey = ~0ull;
+
+__device__ __forceinline__ u64 bitonic_sort32(u64 v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const u64 o = __shfl_xor_sync(CBG_FULL, v, j);
+      const bool up = (lane & k) == 0;     // k == 32 -> always ascending
+      const bool lower = (lane & j) == 0;
+      const u64 mn = v < o ? v : o, mx = v < o ? o : v;
+      v = (lower == up) ? mn : mx;
+    }
+  }
+  return v;
+}
+
+__device__ __forceinline__ u64 bitonic_merge32(u64 v, int lane) {
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const u64 o = __shfl_xor_sync(CBG_FULL, v, j);
+    const u64 mn = v < o ? v : o, mx = v < o ? o : v;
+    v = ((lane & j) == 0) ? mn : mx;
+  }
+  return v;
+}
+
+// One CTA = one (graph, chunk of 64 centres).  The whole graph's coordinates sit in shared
+// memory; a warp owns one centre at a time and keeps the running 32 best (key = d2 bits:idx)
+// sorted across its lanes; candidate batches of 32 are bitonic-sorted and merged.
+// Squared distance uses individually rounded mul/add (no FMA) so the selection is
+// bit-identical to the oracle (oracle/graph_ops.py).
+__global__ void __launch_bounds__(256) knn_kernel(const float4* __restrict__ x4,
+                                                  const int* __restrict__ graph_ptr, int k, int mode,
+                                                  float r2max, int* __restrict__ nbr) {
+  extern __shared__ float4 xs[];
+  const int g = blockIdx.y;
+  const int s = graph_ptr[g];
+  const int n = graph_ptr[g + 1] - s;
+  const int c0 = blockIdx.x * 64;
+  if (c0 >= n) return;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = x4[s + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c1 = min(n, c0 + 64);
+  for (int c = c0 + warp; c < c1; c += 8) {
+    const float4 xc = xs[c];
+    u64 best = kInfKey;
+    for (int base = 0; base < n; base += 32) {
+      const int j = base + lane;
+      u64 key = kInfKey;
+      if (j < n && j != c) {
+        const float4 xj = xs[j];
+        const float dx = xc.x - xj.x, dy = xc.y - xj.y, dz = xc.z - xj.z;
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        key = ((u64)__float_as_uint(d2) << 32) | (u64)(unsigned)j;
+      }
+      const u64 worst = __shfl_sync(CBG_FULL, best, 31);
+      if (!__any_sync(CBG_FULL, key < worst)) continue;
+      key = bitonic_sort32(key, lane);
+      const u64 rev = __shfl_sync(CBG_FULL, key, 31 - lane);
+      best = best < rev ? best : rev;
+      best = bitonic_merge32(best, lane);
+    }
+    int out = -1;
+    if (best != kInfKey && lane < k) {
+      const float d2 = __uint_as_float((unsigned)(best >> 32));
+      if (mode == CBG_MODE_KNN || d2 <= r2max) out = s + (int)(unsigned)(best & 0xffffffffull);
+    }
+    nbr[(size_t)(s + c) * CBG_KMAX + lane] = out;
+  }
+}
+
+// Edge gate: one thread per (node, slot).  e_w = sigmoid(W1 . relu(LN(W0 g(d) + b0)) + b1).
+constexpr int kGateSmemFloats = 20 * 160 + 160 + 320 + 160 + 32;
+
+__global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict__ gw,  // GATE_W0T..GATE_RBF
+                                                        const float4* __restrict__ x4,
+                                                        const int* __restrict__ nbr, long long n_slots,
+                                                        float* __restrict__ ew) {
+  __shared__ __align__(16) float sm[kGateSmemFloats];
+  block_copy_f4(sm, gw, kGateSmemFloats);
+  __syncthreads();
+  const float* w0t = sm;                 // [20][160]
+  const float* b0 = sm + 3200;
+  const float* gamma = b0 + 160;
+  const float* beta = gamma + 160;
+  const float* w1 = beta + 160;
+  const float* rbf = w1 + 160;           // offsets[20], coeff, b1
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_slots) return;
+  const int j = nbr[idx];
+  if (j < 0) { ew[idx] = 0.f; return; }
+  const int i = (int)(idx / CBG_KMAX);
+  const float4 xi = x4[i], xj = x4[j];
+  const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+  const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+  float g[CBG_NRBF];
+  const float coeff = rbf[20];
+#pragma unroll
+  for (int m = 0; m < CBG_NRBF; ++m) { const float u = d - rbf[m]; g[m] = expf(coeff * u * u); }
+  float4 hid[40];
+#pragma unroll
+  for (int u = 0; u < 40; ++u) hid[u] = ld4(b0 + 4 * u);
+#pragma unroll
+  for (int m = 0; m < CBG_NRBF; ++m) {
+#pragma unroll
+    for (int u = 0; u < 40; ++u) fma4(hid[u], ld4(w0t + m * 160 + 4 * u), g[m]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int u = 0; u < 40; ++u) s += (hid[u].x + hid[u].y) + (hid[u].z + hid[u].w);
+  const float mean = s * (1.f / 160.f);
+  float q = 0.f;
+#pragma unroll
+  for (int u = 0; u < 40; ++u) {
+    hid[u].x -= mean; hid[u].y -= mean; hid[u].z -= mean; hid[u].w -= mean;
+    q += (hid[u].x * hid[u].x + hid[u].y * hid[u].y) + (hid[u].z * hid[u].z + hid[u].w * hid[u].w);
+  }
+  const float rstd = 1.f / sqrtf(q * (1.f / 160.f) + 1e-5f);
+  float o = rbf[21];
+#pragma unroll
+  for (int u = 0; u < 40; ++u) {
+    const float4 ga = ld4(gamma + 4 * u), be = ld4(beta + 4 * u), ww = ld4(w1 + 4 * u);
+    o = fmaf(ww.x, fmaxf(fmaf(hid[u].x * rstd, ga.x, be.x), 0.f), o);
+    o = fmaf(ww.y, fmaxf(fmaf(hid[u].y * rstd, ga.y, be.y), 0.f), o);
+    o = fmaf(ww.z, fmaxf(fmaf(hid[u].z * rstd, ga.z, be.z), 0.f), o);
+    o = fmaf(ww.w, fmaxf(fmaf(hid[u].w * rstd, ga.w, be.w), 0.f), o);
+  }
+  ew[idx] = 1.f / (1.f + expf(-o));
+}
+
+}  // namespace
+
+int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max_graph_nodes, int mode,
+                   int k, float r_max, int* nbr, cudaStream_t st) {
+  if (n_graphs <= 0) return 0;
+  if (k < 1 || k > CBG_KMAX) { cbg_set_error("k=%d outside [1,%d]", k, CBG_KMAX); return 1; }
+  const size_t smem = (size_t)max_graph_nodes * sizeof(float4);
+  if (smem > 200 * 1024) {
+    cbg_set_error("graph with %d atoms exceeds the %d-atom shared-memory limit of the neighbour search",
+                  max_graph_nodes, 200 * 1024 / 16);
+    return 1;
+  }
+  CBG_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((max_graph_nodes + 63) / 64, n_graphs);
+  knn_kernel<<<grid, 256, smem, st>>>(x4, graph_ptr, k, mode, r_max * r_max, nbr);
+  CBG_LAUNCHED(1);
+  return 0;
+}
+
+int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
+                         float* ew, cudaStream_t st) {
+  const long long n_slots = n_nodes * CBG_KMAX;
+  if (n_slots == 0) return 0;
+  const float* gw = blob_global + cbg_layout::global_offset(CBG_GF_GATE_W0T);
+  edge_gate_kernel<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(gw, x4, nbr, n_slots, ew);
+  CBG_LAUNCHED(1);
+  return 0;
+}

@@ -1,0 +1,259 @@
+"""B200 drop-in for the reference's ``TargetDiff`` model (sampling path).
+
+Mirrors /root/reference repo/models/diffusion/targetdiff.py:14-38 (constructor, sub-module
+names => state-dict keys) and :127-184 (``sample(batch) -> traj``).  The Python loop over the
+T diffusion steps stays here (north-star: host code keeps the outer schedule); each iteration
+is ONE C-ABI call (``cbg_sample_step_f32``) that enqueues: ligand embedding -> device kNN ->
+edge gate -> 9 x (node GEMMs, fused X2H, fused H2X) -> classifier -> fused reverse step.
+Step-invariant work is hoisted out of the loop: protein embedding,
+the compose_context permutation, graph offsets, flag arrays.
+
+Random numbers are drawn with torch on the model device in the reference's order
+(positions ``randn_like`` then types ``rand_like``, diffusion_scheduler.py:158-163 /
+categorical.py:27), or injected for parity tests.
+"""
+import ctypes as C
+
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from . import _lib
+from .modules import cfg_get, get_e3_gnn, graph_ptr_from_batch, _Workspace
+from .schedulers import CTNVPTables, TypeVPTables
+
+N_AA_TYPES = 20        # repo/utils/protein/constants.py:39-41
+N_PROTEIN_ATOM_FEAT = 7  # 6 elements + backbone flag, repo/utils/protein/constants.py:37
+
+_MODEL_DICT = {}
+
+
+def register_model(name):
+    def deco(cls):
+        _MODEL_DICT[name] = cls
+        return cls
+    return deco
+
+
+def get_model(config):
+    """Mirror of repo/models/_base.py:10-12."""
+    return _MODEL_DICT[config.type](config)
+
+
+class PLContextEmbedderB200(nn.Module):
+    """Parameter container for PLContextEmbedder (context_emb.py:137-177), 'linear' embeddings,
+    no time embedding (the only shipped configuration)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.num_classes = cfg_get(cfg, 'num_atomtype', 14)
+        emb_dim = cfg_get(cfg, 'emb_dim', 128)
+        self.emb_dim = emb_dim
+        if cfg_get(cfg, 'time', None) is not None or cfg_get(cfg, 'vec', None) is not None:
+            raise NotImplementedError('time / vec embeddings are not used by any shipped CBGBench config '
+                                      'and are not implemented on the B200 path')
+        atom = cfg_get(cfg, 'atom', None)
+        res = cfg_get(cfg, 'residue', None)
+        if atom is None or res is None or cfg_get(atom, 'type') != 'linear' or cfg_get(res, 'type') != 'linear':
+            raise NotImplementedError("embedder needs atom.type == residue.type == 'linear'")
+        if emb_dim != 128:
+            raise NotImplementedError('emb_dim must be 128')
+        self.ligand_atom_emb = nn.Linear(self.num_classes, emb_dim)
+        self.protein_atom_emb = nn.Linear(N_PROTEIN_ATOM_FEAT, emb_dim)
+        self.residue_emb = nn.Linear(N_AA_TYPES, emb_dim)
+        self.ligand_indicator = nn.Linear(1, emb_dim)
+
+    @torch.no_grad()
+    def static_features(self, v_rec, aa_rec, lig_flag, rec_flag):
+        """Step-invariant pieces (tensor plumbing, executed once per batch):
+        h_rec (context_emb.py:210-222) and the c_lig-independent part of h_lig."""
+        if aa_rec.dim() == 1:
+            aa_rec = F.one_hot(aa_rec, num_classes=N_AA_TYPES).float()
+        if v_rec.dim() == 1:
+            v_rec = F.one_hot(v_rec.long(), num_classes=N_PROTEIN_ATOM_FEAT).float()
+        h_rec = self.protein_atom_emb(v_rec.float()) + self.residue_emb(aa_rec) \
+            + self.ligand_indicator(rec_flag.float().unsqueeze(-1))
+        h_lig_bias = self.ligand_atom_emb.bias.unsqueeze(0) + self.ligand_indicator(lig_flag.float().unsqueeze(-1))
+        return h_rec, h_lig_bias.contiguous()
+
+
+@register_model('targetdiff')
+class TargetDiffB200(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        gen = cfg.generator
+        self.num_diffusion_timesteps = gen.num_diffusion_timesteps
+        self.denoise_structure = cfg_get(gen, 'denoise_structure', True)
+        self.denoise_atom = cfg_get(gen, 'denoise_atom', True)
+        self.time_sampler = cfg_get(gen, 'time_sampler', 'symmetric')
+        if not (self.denoise_structure and self.denoise_atom):
+            raise NotImplementedError('denoise_structure / denoise_atom = False is not implemented')
+        self.num_classes = cfg.num_atomtype
+        ps = gen.pos_schedule
+        self.pos_scheduler = CTNVPTables(self.num_diffusion_timesteps, beta_start=ps.beta_start,
+                                         beta_end=ps.beta_end, type=ps.type)
+        at = gen.atom_schedule
+        self.type_scheduler = TypeVPTables(self.num_diffusion_timesteps, num_classes=self.num_classes,
+                                           type=at.type, cosine_s=at.cosine_s)
+        cfg.embedder.num_atomtype = cfg.num_atomtype
+        self.context_embedder = PLContextEmbedderB200(cfg.embedder)
+        self.denoiser = get_e3_gnn(cfg.encoder, num_classes=self.num_classes)
+        self._ws = _Workspace()
+        self.last_launches = 0
+
+    def forward(self, batch):
+        raise NotImplementedError('TargetDiffB200 is a forward-only sampling build: the training / '
+                                  'validation loss (targetdiff.py:41-124) is out of scope (DESIGN.md)')
+
+    # ---- setup of the step-invariant state ------------------------------------------------
+    @torch.no_grad()
+    def prepare(self, batch, device=None):
+        """Move the batch to the device and hoist everything that does not change over the
+        T steps.  Returns a dict holding device tensors (kept alive) and the ctypes plan."""
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != 'cuda':
+            raise RuntimeError('TargetDiffB200.sample needs the model on a CUDA device (no CPU fallback)')
+        g = lambda k, d=None: batch.get(k, d) if hasattr(batch, 'get') else (batch[k] if k in batch else d)
+        to = lambda t: t.to(dev, non_blocking=True)
+        x_lig = to(batch['ligand_pos']).float().contiguous()
+        v_lig = to(batch['ligand_atom_type'])
+        x_rec = to(batch['protein_pos']).float()
+        v_rec = to(batch['protein_atom_feature'])
+        aa_rec = to(batch['protein_aa_type'])
+        lig_flag = to(batch['ligand_lig_flag']).bool()
+        rec_flag = to(batch['protein_lig_flag']).bool()
+        gl = g('ligand_gen_flag', None)
+        gen_lig = to(gl).bool() if gl is not None else lig_flag
+        gr = g('protein_gen_flag', None)
+        gen_rec = to(gr).bool() if gr is not None else torch.zeros_like(rec_flag)
+        bl = to(batch['ligand_element_batch']).long()
+        br = to(batch['protein_element_batch']).long()
+        n_lig, n_rec = x_lig.shape[0], x_rec.shape[0]
+        N = n_lig + n_rec
+
+        # compose_context (common.py:189-214): stable sort of [rec | lig] by graph id
+        batch_ctx = torch.cat([br, bl], 0)
+        sort_idx = torch.sort(batch_ctx, stable=True).indices
+        batch_sorted = batch_ctx[sort_idx]
+        inv = torch.empty_like(sort_idx)
+        inv[sort_idx] = torch.arange(N, device=dev)
+        lig_node = inv[n_rec:].to(torch.int32).contiguous()
+        if n_lig > 1 and not bool((lig_node[1:] > lig_node[:-1]).all()):
+            raise ValueError('ligand_element_batch must be sorted')
+        gptr, B, max_n = graph_ptr_from_batch(batch_sorted)
+
+        h_rec, h_lig_bias = self.context_embedder.static_features(v_rec, aa_rec, lig_flag, rec_flag)
+        h_static = torch.cat([h_rec, torch.zeros(n_lig, 128, device=dev)], 0)[sort_idx].contiguous()
+        x_nodes = torch.cat([x_rec, x_lig], 0)[sort_idx].contiguous()
+        lig_nodes = torch.cat([rec_flag, lig_flag], 0)[sort_idx].to(torch.uint8).contiguous()
+        gen_nodes_flag = torch.cat([gen_rec, gen_lig], 0)[sort_idx].to(torch.uint8).contiguous()
+        gen_node = torch.nonzero(gen_nodes_flag, as_tuple=False).flatten().to(torch.int32).contiguous()
+        n_gen = int(gen_node.numel())
+        gen_lig8 = gen_lig.to(torch.uint8).contiguous()
+        emb_wt = self.context_embedder.ligand_atom_emb.weight.detach().t().contiguous().float()
+        blob = self.denoiser.packed_blob(dev)
+
+        L = _lib.lib()
+        ws_bytes = L.cbg_workspace_bytes(N, n_gen)
+        ws_ptr, ws_have = self._ws.get(ws_bytes, dev)
+        den = self.denoiser
+        plan = _lib.SamplePlan(
+            blob=blob.data_ptr(), num_layers=den.num_layers, num_classes=self.num_classes,
+            emb_wt=emb_wt.data_ptr(), h_lig_bias=h_lig_bias.data_ptr(), h_static=h_static.data_ptr(),
+            graph_ptr=gptr.data_ptr(), n_graphs=B, max_graph_nodes=max_n, n_nodes=N,
+            lig_node=lig_node.data_ptr(), n_lig=n_lig, gen_lig=gen_lig8.data_ptr(),
+            gen_node=gen_node.data_ptr() if n_gen else None, n_gen=n_gen,
+            mode=den.mode_id, k=den.cut_off, r_max=den.r_max, workspace=ws_ptr, workspace_bytes=ws_have)
+        with torch.cuda.device(dev):
+            _lib.check(L.cbg_sample_begin_f32(C.byref(plan), x_nodes.data_ptr(), lig_nodes.data_ptr(),
+                                              gen_nodes_flag.data_ptr(), _lib.stream_ptr(dev)))
+        keep = dict(blob=blob, emb_wt=emb_wt, h_lig_bias=h_lig_bias, h_static=h_static, gptr=gptr,
+                    lig_node=lig_node, gen_lig8=gen_lig8, gen_node=gen_node, x_nodes=x_nodes,
+                    lig_nodes=lig_nodes, gen_nodes_flag=gen_nodes_flag)
+        c_lig = F.one_hot(v_lig, num_classes=self.num_classes).float().contiguous()
+        return dict(plan=plan, keep=keep, device=dev, x_lig=x_lig, c_lig=c_lig, batch_idx_lig=bl,
+                    n_lig=n_lig, n_nodes=N)
+
+    def step_coef(self, t_idx):
+        ps, ts = self.pos_scheduler, self.type_scheduler
+        tm1 = max(t_idx - 1, 0)
+        return _lib.StepCoef(
+            pos_c0=float(ps.host_table('posterior_mean_c0_coef')[t_idx]),
+            pos_ct=float(ps.host_table('posterior_mean_ct_coef')[t_idx]),
+            pos_logvar=float(ps.host_table('posterior_logvar')[t_idx]),
+            pos_nonzero=0.0 if t_idx == 0 else 1.0,
+            log_alphas_cumprod_prev=float(ts.host_table('log_alphas_cumprod_v')[tm1]),
+            log_one_minus_alphas_cumprod_prev=float(ts.host_table('log_one_minus_alphas_cumprod_v')[tm1]),
+            log_alpha=float(ts.host_table('log_alphas_v')[t_idx]),
+            log_one_minus_alpha=float(ts.host_table('log_one_minus_alphas_v')[t_idx]))
+
+    @torch.no_grad()
+    def run_steps(self, state, t_seq, X, Cc, V=None, pos_noise=None, type_uniform=None,
+                  x0_out=None, logits_out=None):
+        """Enqueue the denoise steps ``t_seq`` (descending t).  X [T+1,n_lig,3] / Cc [T+1,n_lig,K]
+        hold the trajectory on the device: slot t+1 is the state ENTERING step t, slot t its
+        result (slot 0 = traj[-1])."""
+        L = _lib.lib()
+        dev = state['device']
+        plan = state['plan']
+        n_lig, K = state['n_lig'], self.num_classes
+        st = _lib.stream_ptr(dev)
+        v_scratch = V if V is not None else torch.empty(n_lig, dtype=torch.int64, device=dev)
+        launches0 = L.cbg_launch_count()
+        with torch.cuda.device(dev):
+            for t_idx in t_seq:
+                x_t, c_t = X[t_idx + 1], Cc[t_idx + 1]
+                if pos_noise is None:
+                    eps = torch.randn_like(x_t)
+                else:
+                    eps = pos_noise[t_idx].to(dev, torch.float32).contiguous()
+                if type_uniform is None:
+                    uni = torch.rand_like(c_t)
+                else:
+                    uni = type_uniform[t_idx].to(dev, torch.float32).contiguous()
+                coef = self.step_coef(t_idx)
+                _lib.check(L.cbg_sample_step_f32(
+                    C.byref(plan), C.byref(coef), x_t.data_ptr(), c_t.data_ptr(), eps.data_ptr(), uni.data_ptr(),
+                    X[t_idx].data_ptr(), Cc[t_idx].data_ptr(), v_scratch.data_ptr(),
+                    x0_out[t_idx].data_ptr() if x0_out is not None else None,
+                    logits_out[t_idx].data_ptr() if logits_out is not None else None, st))
+        self.last_launches = L.cbg_launch_count() - launches0
+
+    @torch.no_grad()
+    def sample(self, batch, pos_noise=None, type_uniform=None, num_steps=None, traj_mode='full'):
+        """TargetDiff.sample (targetdiff.py:127-184).
+
+        Returns ``traj``: {t: (x_lig [n_lig,3], c_lig [n_lig,K] one-hot, batch_idx_lig)} with keys
+        T-1 ... -1; entries >= 0 live on the CPU and key -1 on the device, exactly like the
+        reference (whose consumer, sample.py:194-201, reads traj[0]).  The per-step D2H +
+        sync of the reference (targetdiff.py:182) is replaced by one device-side trajectory
+        buffer and a single copy at the end.
+
+        Extras (default = reference behaviour): ``pos_noise`` / ``type_uniform`` inject the noise
+        (indexable by t); ``num_steps`` stops after that many steps (testing);
+        ``traj_mode='final'`` keeps only traj[0] and traj[-1]."""
+        T = self.num_diffusion_timesteps
+        state = self.prepare(batch)
+        dev, n_lig, K = state['device'], state['n_lig'], self.num_classes
+        X = torch.empty((T + 1, n_lig, 3), dtype=torch.float32, device=dev)
+        Cc = torch.empty((T + 1, n_lig, K), dtype=torch.float32, device=dev)
+        X[T].copy_(state['x_lig'])
+        Cc[T].copy_(state['c_lig'])
+        t_seq = list(reversed(range(T)))
+        if num_steps is not None:
+            t_seq = t_seq[:num_steps]
+        self.run_steps(state, t_seq, X, Cc, pos_noise=pos_noise, type_uniform=type_uniform)
+        bl = state['batch_idx_lig']
+        t_last = t_seq[-1]
+        traj = {}
+        if traj_mode == 'full':
+            Xh = X[t_last + 1:].cpu()
+            Ch = Cc[t_last + 1:].cpu()
+            bl_cpu = bl.cpu()
+            for t in range(t_last, T):
+                traj[t] = (Xh[t - t_last], Ch[t - t_last], bl_cpu)
+        else:
+            traj[t_last] = (X[t_last + 1].cpu(), Cc[t_last + 1].cpu(), bl.cpu())
+        traj[t_last - 1] = (X[t_last].clone(), Cc[t_last].clone(), bl)
+        return traj

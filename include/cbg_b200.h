@@ -1,0 +1,167 @@
+/* cbg_b200 - C-ABI of the B200-native CBGBench diffusion-sampling hot path.
+ *
+ * The reference (EDAPINENUT/CBGBench @ 983fca2, /root/reference) is 100 % Python/PyTorch and
+ * has NO FFI / plugin / operator boundary of its own: its seam is the Python
+ * factory get_e3_gnn() (repo/modules/e3nn/__init__.py:5-18) returning an nn.Module whose
+ * forward(x, h, batch_idx, lig_flag, gen_flag) -> (x, h, c) is repo/modules/e3nn/unitransformer.py:102-123,
+ * iterated by TargetDiff.sample (repo/models/diffusion/targetdiff.py:127-184).  The entry points
+ * below are what a ctypes binding for that seam needs; each one cites the reference code it
+ * replaces.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - plain C, no C++ types or exceptions across the boundary;
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in _host;
+ *   - fp32 data, int32 indices, uint8 flags; row-major contiguous;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only
+ *     enqueue work (no host synchronisation) unless the name ends in _host;
+ *   - return 0 on success; non-zero = error, message from cbg_last_error() (thread-local);
+ *   - graphs are contiguous node ranges: graph g owns nodes graph_ptr[g] .. graph_ptr[g+1]-1
+ *     (the reference's sorted PyG `batch` vector, repo/modules/common.py:189-214);
+ *   - neighbour tables have fixed width CBG_NBR_WIDTH = 32 (k <= 32), nearest first,
+ *     padded with -1 (graphs with fewer than k+1 atoms, radius mode).
+ */
+#ifndef CBG_B200_H_
+#define CBG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBG_NBR_WIDTH 32
+#define CBG_HIDDEN 128
+#define CBG_N_HEADS 16
+#define CBG_MAX_CLASSES 16
+
+#define CBG_CUTOFF_KNN 0     /* reference default, unitransformer.py:27-28,78-80 */
+#define CBG_CUTOFF_RADIUS 1  /* defined in SURVEY.md section 8c (reference branch is dead code, unitransformer.py:76-77) */
+
+int32_t cbg_version(void);
+const char* cbg_last_error(void);
+/* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
+int64_t cbg_launch_count(void);
+
+/* ---- packed weight blob layout (single source of truth: csrc/cbg_layout.h) -------------------
+ * blob = [global section][layer 0][layer 1]...; section 0 = global, 1 = per-layer.
+ * Replaces the nn.Module parameter tree of UniTransformer (state-dict keys in SURVEY.md section 8b). */
+int64_t cbg_blob_global_floats(void);
+int64_t cbg_blob_layer_floats(void);
+int32_t cbg_blob_num_fields(int32_t section);
+const char* cbg_blob_field_name(int32_t section, int32_t idx);
+int64_t cbg_blob_field_offset(int32_t section, int32_t idx);
+int64_t cbg_blob_field_size(int32_t section, int32_t idx);
+
+/* scratch bytes needed by the calls below for n_nodes nodes of which n_gen carry gen_flag */
+int64_t cbg_workspace_bytes(int64_t n_nodes, int64_t n_gen);
+
+/* Neighbour lists on device.
+ * Replaces torch_geometric.nn.knn_graph(x, k, batch, flow='source_to_target')
+ * (call site unitransformer.py:79-80; third-party torch_cluster kernel).  nbr[i, s] = global index
+ * of the s-th nearest j != i of i's graph (ties -> lower index), -1 padded.  The reference's
+ * edge_index is [nbr[i,s] ; i] for all valid slots, grouped by i. */
+int32_t cbg_build_neighbors_f32(const float* x /*[N,3]*/, const int32_t* graph_ptr /*[B+1]*/,
+                                int32_t n_graphs, int64_t n_nodes, int32_t max_graph_nodes,
+                                int32_t mode, int32_t k, float r_max,
+                                int32_t* nbr /*[N,32] out*/,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Global edge gate e_w = sigmoid(dist_emb(|x_i - x_j|)) (unitransformer.py:109-112,
+ * embs/dist_emb.py:6-14).  ew[i, s] for slot s of node i (0 for padded slots). */
+int32_t cbg_edge_gate_f32(const float* blob, const float* x /*[N,3]*/, const int32_t* nbr /*[N,32]*/,
+                          int64_t n_nodes, float* ew /*[N,32] out*/,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* One full denoiser forward = UniTransformer.forward (unitransformer.py:102-123): graph build,
+ * edge gate, num_layers x (X2HAttention, H2XAttention, masked coordinate update), classifier.
+ * Inputs are not modified.  gen_idx lists the nodes with gen_flag set (any order);
+ * cls_idx = NULL computes logits for all nodes (logits_out [N,K]) else only for the listed
+ * rows (logits_out [n_cls,K]).  stop_after_layers < 0 runs all layers (testing hook: run
+ * only the first stop_after_layers layers, then the classifier). */
+int32_t cbg_denoiser_forward_f32(const float* blob, int32_t num_layers, int32_t num_classes,
+                                 const float* x /*[N,3]*/, const float* h /*[N,128]*/,
+                                 const int32_t* graph_ptr, int32_t n_graphs, int32_t max_graph_nodes,
+                                 const uint8_t* lig_flag /*[N]*/, const uint8_t* gen_flag /*[N]*/,
+                                 const int32_t* gen_idx, int32_t n_gen,
+                                 const int32_t* cls_idx, int32_t n_cls,
+                                 int64_t n_nodes, int32_t mode, int32_t k, float r_max,
+                                 int32_t stop_after_layers,
+                                 float* x_out /*[N,3]*/, float* h_out /*[N,128]*/, float* logits_out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies inputs to the device, runs the
+ * forward, copies x_out/h_out/logits_out back and synchronises.  Device scratch is cached
+ * inside the library.  blob_host holds the packed weights; it is re-uploaded when
+ * blob_version changes. */
+int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_floats, int64_t blob_version,
+                                      int32_t num_layers, int32_t num_classes,
+                                      const float* x_host, const float* h_host,
+                                      const int32_t* graph_ptr_host, int32_t n_graphs,
+                                      const uint8_t* lig_flag_host, const uint8_t* gen_flag_host,
+                                      int64_t n_nodes, int32_t mode, int32_t k, float r_max,
+                                      float* x_out_host, float* h_out_host, float* logits_out_host);
+
+/* ---- fused sampling step: embed -> denoiser -> reverse diffusion step -------------------------
+ * One iteration of the loop body of TargetDiff.sample (targetdiff.py:150-182):
+ *   PLContextEmbedder.forward (context_emb.py:179-231), compose_context (common.py:189-214,
+ *   hoisted: the permutation is step-invariant), denoiser, then
+ *   CTNVPScheduler.backward_remove_noise(type='denoise') (diffusion_scheduler.py:144-165) and
+ *   TypeVPScheduler.backward_remove_noise (diffusion_scheduler.py:367-378).
+ * Random numbers stay with the caller (torch.randn_like / rand_like order of the reference). */
+typedef struct cbg_sample_plan {
+  const float* blob;            /* packed denoiser weights */
+  int32_t num_layers;
+  int32_t num_classes;
+  const float* emb_wt;          /* [K,128] context_embedder.ligand_atom_emb.weight^T */
+  const float* h_lig_bias;      /* [n_lig,128] ligand_atom_emb.bias + ligand_indicator(lig_flag) */
+  const float* h_static;        /* [N,128] step-invariant node features (protein rows) */
+  const int32_t* graph_ptr;     /* [B+1] over composed nodes ([protein | ligand] per graph) */
+  int32_t n_graphs;
+  int32_t max_graph_nodes;
+  int64_t n_nodes;
+  const int32_t* lig_node;      /* [n_lig] composed node index of every ligand atom */
+  int32_t n_lig;
+  const uint8_t* gen_lig;       /* [n_lig] ligand_gen_flag */
+  const int32_t* gen_node;      /* [n_gen] composed node indices with gen_flag */
+  int32_t n_gen;
+  int32_t mode;                 /* CBG_CUTOFF_* */
+  int32_t k;
+  float r_max;
+  void* workspace;
+  size_t workspace_bytes;
+} cbg_sample_plan;
+
+typedef struct cbg_step_coef {  /* scheduler table entries of the current step (host scalars) */
+  float pos_c0;                 /* pos_scheduler.posterior_mean_c0_coef[t] */
+  float pos_ct;                 /* pos_scheduler.posterior_mean_ct_coef[t] */
+  float pos_logvar;             /* pos_scheduler.posterior_logvar[t] */
+  float pos_nonzero;            /* 0 if t == 0 else 1 */
+  float log_alphas_cumprod_prev;          /* type_scheduler.log_alphas_cumprod_v[max(t-1,0)] */
+  float log_one_minus_alphas_cumprod_prev;/* type_scheduler.log_one_minus_alphas_cumprod_v[max(t-1,0)] */
+  float log_alpha;              /* type_scheduler.log_alphas_v[t] */
+  float log_one_minus_alpha;    /* type_scheduler.log_one_minus_alphas_v[t] */
+} cbg_step_coef;
+
+/* writes the static part of the node state (all coordinates + flags) into the plan workspace */
+int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes /*[N,3]*/,
+                             const uint8_t* lig_flag /*[N]*/, const uint8_t* gen_flag /*[N]*/, void* stream);
+
+int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* coef,
+                            const float* x_t /*[n_lig,3]*/, const float* c_t /*[n_lig,K]*/,
+                            const float* pos_noise /*[n_lig,3]*/, const float* type_uniform /*[n_lig,K]*/,
+                            float* x_next /*[n_lig,3]*/, float* c_next /*[n_lig,K]*/, int64_t* v_next /*[n_lig]*/,
+                            float* x0_pred /*[n_lig,3] or NULL*/, float* logits /*[n_lig,K] or NULL*/,
+                            void* stream);
+
+/* the reverse step alone (testing / integration hook) */
+int32_t cbg_reverse_step_f32(const cbg_step_coef* coef, const float* x0_pred /*[n,3]*/, const float* logits /*[n,K]*/,
+                             const float* x_t, const float* c_t, const uint8_t* gen /*[n]*/,
+                             const float* pos_noise, const float* type_uniform,
+                             int32_t n, int32_t num_classes,
+                             float* x_next, float* c_next, int64_t* v_next, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBG_B200_H_ */
