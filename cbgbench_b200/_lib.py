@@ -39,6 +39,10 @@ SIGNATURES = {
     'cbg_version': (_I32, []),
     'cbg_last_error': (C.c_char_p, []),
     'cbg_launch_count': (_I64, []),
+    'cbg_profile_num_families': (_I32, []),
+    'cbg_profile_family_name': (C.c_char_p, [_I32]),
+    'cbg_profile_enable': (_I32, [_I32]),
+    'cbg_profile_collect': (_I32, [_P, _P]),
     'cbg_blob_global_floats': (_I64, []),
     'cbg_blob_layer_floats': (_I64, []),
     'cbg_blob_num_fields': (_I32, [_I32]),
@@ -91,6 +95,16 @@ def blob_layout():
             d[L.cbg_blob_field_name(sec, i).decode()] = (L.cbg_blob_field_offset(sec, i), L.cbg_blob_field_size(sec, i))
         out[key] = d
     return out
+
+
+def profile_collect():
+    """{family: (total_ms, launches)} since cbg_profile_enable(1); clears the recorded events."""
+    L = lib()
+    n = L.cbg_profile_num_families()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(L.cbg_profile_collect(ms, cnt))
+    return {L.cbg_profile_family_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
 
 
 def ptr(t):

@@ -8,6 +8,21 @@
 #include "cbg_kernels.cuh"
 
 long long g_cbg_launches = 0;
+int g_cbg_prof_on = 0;
+
+namespace {
+struct ProfMark { int family; int is_end; cudaEvent_t ev; };
+std::vector<ProfMark> g_prof_marks;
+const char* const kFamilyNames[CBG_K_COUNT] = {"knn", "edge_gate", "node_gemm", "x2h_k", "x2h_v", "h2x",
+                                               "classifier", "step_init", "reverse", "misc"};
+}  // namespace
+
+void cbg_prof_mark(int family, int is_end, cudaStream_t st) {
+  cudaEvent_t ev;
+  if (cudaEventCreate(&ev) != cudaSuccess) return;
+  cudaEventRecord(ev, st);
+  g_prof_marks.push_back({family, is_end, ev});
+}
 
 static thread_local char g_err[1024] = "";
 
@@ -154,6 +169,30 @@ extern "C" {
 int32_t cbg_version(void) { return 100; }
 const char* cbg_last_error(void) { return g_err; }
 int64_t cbg_launch_count(void) { return g_cbg_launches; }
+
+int32_t cbg_profile_num_families(void) { return CBG_K_COUNT; }
+const char* cbg_profile_family_name(int32_t i) { return (i >= 0 && i < CBG_K_COUNT) ? kFamilyNames[i] : nullptr; }
+int32_t cbg_profile_enable(int32_t on) {
+  g_cbg_prof_on = on ? 1 : 0;
+  return 0;
+}
+int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family) {
+  for (int i = 0; i < CBG_K_COUNT; ++i) { ms_per_family[i] = 0.0; launches_per_family[i] = 0; }
+  CBG_CUDA_OK(cudaDeviceSynchronize());
+  for (size_t i = 0; i + 1 < g_prof_marks.size(); i += 2) {
+    const ProfMark& a = g_prof_marks[i];
+    const ProfMark& b = g_prof_marks[i + 1];
+    if (a.is_end || !b.is_end || a.family != b.family) continue;   // unmatched bracket (error path)
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, a.ev, b.ev) == cudaSuccess) {
+      ms_per_family[a.family] += ms;
+      launches_per_family[a.family] += 1;
+    }
+  }
+  for (auto& m : g_prof_marks) cudaEventDestroy(m.ev);
+  g_prof_marks.clear();
+  return 0;
+}
 
 int64_t cbg_blob_global_floats(void) { return cbg_layout::kGlobalFloats; }
 int64_t cbg_blob_layer_floats(void) { return cbg_layout::kLayerFloats; }

@@ -18,11 +18,22 @@ void cbg_set_error(const char* fmt, ...);
   } while (0)
 
 extern long long g_cbg_launches;
-// after a kernel launch: surface launch errors and count the launch
-#define CBG_LAUNCHED(n)                \
-  do {                                 \
-    CBG_CUDA_OK(cudaGetLastError());   \
-    g_cbg_launches += (n);             \
+extern int g_cbg_prof_on;
+// kernel families for the optional per-kernel CUDA-event profile (bench.py roofline)
+enum CbgKernelFamily {
+  CBG_K_KNN = 0, CBG_K_GATE, CBG_K_NODE_GEMM, CBG_K_X2H_K, CBG_K_X2H_V, CBG_K_H2X, CBG_K_CLASSIFIER,
+  CBG_K_STEP_INIT, CBG_K_REVERSE, CBG_K_MISC, CBG_K_COUNT
+};
+void cbg_prof_mark(int family, int is_end, cudaStream_t st);
+// bracket a kernel launch: PROF_BEGIN before it, LAUNCHED after it (surfaces launch errors,
+// counts the launch, closes the profile bracket)
+#define CBG_PROF_BEGIN(family, st) \
+  do { if (g_cbg_prof_on) cbg_prof_mark((family), 0, (st)); } while (0)
+#define CBG_LAUNCHED(family, st)                              \
+  do {                                                        \
+    CBG_CUDA_OK(cudaGetLastError());                          \
+    g_cbg_launches += 1;                                      \
+    if (g_cbg_prof_on) cbg_prof_mark((family), 1, (st));      \
   } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -420,17 +420,20 @@ int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
   const int grid = edge_grid(a.n_nodes);
+  CBG_PROF_BEGIN(CBG_K_X2H_K, st);
   x2h_k_kernel<<<grid, kThreads, kX2hKSmem, st>>>(a);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_X2H_K, st);
+  CBG_PROF_BEGIN(CBG_K_X2H_V, st);
   x2h_v_kernel<<<grid, kThreads, kX2hVSmem, st>>>(a);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_X2H_V, st);
   return 0;
 }
 
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
+  CBG_PROF_BEGIN(CBG_K_H2X, st);
   h2x_kernel<<<edge_grid(a.n_nodes), kThreads, kH2xSmem, st>>>(a);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_H2X, st);
   return 0;
 }

@@ -153,10 +153,15 @@ int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max
                   max_graph_nodes, 200 * 1024 / 16);
     return 1;
   }
-  CBG_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static size_t smem_attr = 0;
+  if (smem > 48 * 1024 && smem > smem_attr) {
+    CBG_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
   dim3 grid((max_graph_nodes + 63) / 64, n_graphs);
+  CBG_PROF_BEGIN(CBG_K_KNN, st);
   knn_kernel<<<grid, 256, smem, st>>>(x4, graph_ptr, k, mode, r_max * r_max, nbr);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_KNN, st);
   return 0;
 }
 
@@ -165,7 +170,8 @@ int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* 
   const long long n_slots = n_nodes * CBG_KMAX;
   if (n_slots == 0) return 0;
   const float* gw = blob_global + cbg_layout::global_offset(CBG_GF_GATE_W0T);
+  CBG_PROF_BEGIN(CBG_K_GATE, st);
   edge_gate_kernel<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(gw, x4, nbr, n_slots, ew);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_GATE, st);
   return 0;
 }

@@ -176,29 +176,33 @@ __global__ void __launch_bounds__(128) reverse_kernel(ReverseArgs p, float logva
 int cbg_launch_pack_x4(const float* x, const unsigned char* lig_flag, const unsigned char* gen_flag,
                        long long n, float4* x4, cudaStream_t st) {
   if (n <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
   pack_x4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, lig_flag, gen_flag, n, x4);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_MISC, st);
   return 0;
 }
 
 int cbg_launch_unpack_x(const float4* x4, long long n, float* x, cudaStream_t st) {
   if (n <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
   unpack_x_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x4, n, x);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_MISC, st);
   return 0;
 }
 
 int cbg_launch_gather_x(const float4* x4, const int* idx, int n, float* out, cudaStream_t st) {
   if (n <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
   gather_x_kernel<<<(n + 255) / 256, 256, 0, st>>>(x4, idx, n, out);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_MISC, st);
   return 0;
 }
 
 int cbg_launch_apply_dx(float4* x4, const int* node_idx, const float* dx, int n, cudaStream_t st) {
   if (n <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
   apply_dx_kernel<<<(n + 255) / 256, 256, 0, st>>>(x4, node_idx, dx, n);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_MISC, st);
   return 0;
 }
 
@@ -213,9 +217,10 @@ int cbg_launch_classifier(const float* blob_global, const float* h, const int* r
   }
   int grid = (n_rows + 7) / 8;
   if (grid > 2 * 148) grid = 2 * 148;
+  CBG_PROF_BEGIN(CBG_K_CLASSIFIER, st);
   classifier_kernel<<<grid, 256, kClsFloats * 4, st>>>(blob_global + cbg_layout::global_offset(CBG_GF_CLS_W0T), h,
                                                        row_idx, n_rows, num_classes, logits);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_CLASSIFIER, st);
   return 0;
 }
 
@@ -224,15 +229,17 @@ int cbg_launch_step_init(const float* x_lig, const float* c_lig, const int* lig_
                          const float* h_static, long long n_nodes, float4* x4, float* h, cudaStream_t st) {
   CBG_CUDA_OK(cudaMemcpyAsync(h, h_static, (size_t)n_nodes * CBG_H * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (n_lig <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_STEP_INIT, st);
   step_init_kernel<<<(n_lig + 7) / 8, 256, 0, st>>>(x_lig, c_lig, lig_node, n_lig, num_classes, emb_wt,
                                                     h_lig_bias, x4, h);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_STEP_INIT, st);
   return 0;
 }
 
 int cbg_launch_reverse(const ReverseArgs& a, float logvar, float nonzero, cudaStream_t st) {
   if (a.n_lig <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_REVERSE, st);
   reverse_kernel<<<(a.n_lig + 127) / 128, 128, 0, st>>>(a, logvar, nonzero);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_REVERSE, st);
   return 0;
 }

@@ -149,7 +149,8 @@ int cbg_launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st) {
     CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;
   }
+  CBG_PROF_BEGIN(CBG_K_NODE_GEMM, st);
   node_gemm_kernel<<<(a.n_rows + BM - 1) / BM, 256, kSmemBytes, st>>>(a);
-  CBG_LAUNCHED(1);
+  CBG_LAUNCHED(CBG_K_NODE_GEMM, st);
   return 0;
 }

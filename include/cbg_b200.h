@@ -43,6 +43,14 @@ const char* cbg_last_error(void);
 /* number of CUDA kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t cbg_launch_count(void);
 
+/* Optional per-kernel profile: while enabled every kernel launch of the library is bracketed by
+ * CUDA events on the launching stream; cbg_profile_collect synchronises and returns the summed
+ * device time (ms) and launch count per kernel family (bench.py roofline block). */
+int32_t cbg_profile_num_families(void);
+const char* cbg_profile_family_name(int32_t i);
+int32_t cbg_profile_enable(int32_t on);
+int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family);
+
 /* ---- packed weight blob layout (single source of truth: csrc/cbg_layout.h) -------------------
  * blob = [global section][layer 0][layer 1]...; section 0 = global, 1 = per-layer.
  * Replaces the nn.Module parameter tree of UniTransformer (state-dict keys in SURVEY.md section 8b). */

@@ -1,0 +1,315 @@
+"""Parity of the CUDA path (through the C-ABI) against the oracle and the reference goldens.
+
+Bars (BASELINE.json north_star): coordinates / logits within 1e-4 relative fp32
+(max|a-b| / max|b|), integer outputs (neighbour lists, atom-type argmax) bit-exact.
+Run on the B200 box:  python -m pytest tests -m gpu
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cbgbench_b200 import _lib, synthetic
+from helpers import FORWARD_CASES, composed_inputs, golden, make_model, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4          # relative fp32 tolerance of the parity bar
+torch.set_grad_enabled(False)
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def _ws(n_nodes, n_gen=0):
+    L = _lib.lib()
+    nbytes = L.cbg_workspace_bytes(n_nodes, n_gen)
+    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev())
+    off = (-buf.data_ptr()) % 256
+    return buf, buf.data_ptr() + off, nbytes
+
+
+def _gptr(batch_idx):
+    counts = torch.bincount(batch_idx)
+    ptr = torch.zeros(counts.numel() + 1, dtype=torch.int32)
+    ptr[1:] = torch.cumsum(counts, 0)
+    return ptr.to(dev()), int(counts.numel()), int(counts.max())
+
+
+def cuda_neighbors(x, batch_idx, k=32, mode=0, r_max=10.0):
+    L = _lib.lib()
+    N = x.shape[0]
+    gptr, B, max_n = _gptr(batch_idx)
+    xd = x.to(dev()).contiguous()
+    nbr = torch.empty((N, 32), dtype=torch.int32, device=dev())
+    buf, wsp, wsb = _ws(N)
+    _lib.check(L.cbg_build_neighbors_f32(xd.data_ptr(), gptr.data_ptr(), B, N, max_n, mode, k, r_max,
+                                         nbr.data_ptr(), wsp, wsb, None))
+    torch.cuda.synchronize()
+    return nbr.cpu().long()
+
+
+# ---------------------------------------------------------------------------------------------
+# stage: neighbour lists (bit-exact)
+@pytest.mark.parametrize('sizes', [[224], [299, 25, 1, 2, 33, 32], [850, 100, 450]])
+@pytest.mark.parametrize('k', [32, 8])
+def test_knn_bit_exact(sizes, k):
+    from oracle import graph_ops as G
+    rs = np.random.RandomState(sum(sizes) + k)
+    x = torch.from_numpy((4.0 * rs.normal(size=(sum(sizes), 3))).astype(np.float32))
+    x[5] = x[3]                                  # exact duplicate -> distance ties
+    bidx = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    ptr = [0] + list(np.cumsum(sizes))
+    want = G.neighbor_table(x, ptr, k=k)
+    got = cuda_neighbors(x, bidx, k=k)
+    assert torch.equal(got, want)
+
+
+def test_radius_graph_bit_exact():
+    from oracle import graph_ops as G
+    rs = np.random.RandomState(9)
+    sizes = [300, 120]
+    x = torch.from_numpy((6.0 * rs.normal(size=(sum(sizes), 3))).astype(np.float32))
+    bidx = torch.repeat_interleave(torch.arange(2), torch.tensor(sizes))
+    want = G.neighbor_table(x, [0, 300, 420], k=32, r_max=6.0)
+    got = cuda_neighbors(x, bidx, k=32, mode=1, r_max=6.0)
+    assert torch.equal(got, want)
+    assert (want == -1).any() and (want[:, 0] >= 0).any()
+
+
+# ---------------------------------------------------------------------------------------------
+# stage: edge gate
+def test_edge_gate_matches_oracle():
+    from oracle import denoiser as ODn, graph_ops as G
+    model, sd = make_model(10)
+    batch = synthetic.make_batch([200, 40], [24, 10], seed=3)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    ptr = G.graph_ptr_from_batch(bidx)
+    nbr = G.neighbor_table(x, ptr, k=32)
+    ei = G.table_to_edge_index(nbr)
+    want = torch.zeros(nbr.shape, dtype=torch.float32)
+    want[nbr >= 0] = ODn.edge_gate(sd, 'denoiser.', x, ei[0], ei[1]).flatten()
+    L = _lib.lib()
+    blob = model.denoiser.packed_blob(dev())
+    N = x.shape[0]
+    ew = torch.empty((N, 32), dtype=torch.float32, device=dev())
+    buf, wsp, wsb = _ws(N)
+    _lib.check(L.cbg_edge_gate_f32(blob.data_ptr(), x.to(dev()).contiguous().data_ptr(),
+                                   nbr.to(dev(), torch.int32).contiguous().data_ptr(), N, ew.data_ptr(), wsp, wsb, None))
+    torch.cuda.synchronize()
+    assert rel_err(ew.cpu(), want) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# full forward: per-layer trace against the oracle, then the reference goldens
+def test_forward_layer_by_layer_vs_oracle():
+    from oracle import denoiser as ODn
+    model, sd = make_model(10, device=dev())
+    batch = synthetic.make_batch([200, 40, 20], [24, 10, 5], seed=11)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    xo, ho, co, trace = ODn.unitransformer_forward(sd, x, h, bidx, lig, gen, return_trace=True)
+    args = [t.to(dev()) for t in (x, h, bidx, lig, gen)]
+    for L_ in range(1, 10):
+        xg, hg, cg = model.denoiser(*args, stop_after_layers=L_)
+        ex, eh = rel_err(xg.cpu(), trace['x'][L_ - 1]), rel_err(hg.cpu(), trace['h'][L_ - 1])
+        assert ex < TOL and eh < TOL, f'layer {L_}: x {ex:.2e} h {eh:.2e}'
+    xg, hg, cg = model.denoiser(*args)
+    assert rel_err(xg.cpu(), xo) < TOL and rel_err(hg.cpu(), ho) < TOL and rel_err(cg.cpu(), co) < TOL
+    # the inputs must not be modified (reference clones x, unitransformer.py:178)
+    assert torch.equal(args[0].cpu(), x) and torch.equal(args[1].cpu(), h)
+
+
+@pytest.mark.parametrize('case', FORWARD_CASES, ids=[c[0] for c in FORWARD_CASES])
+def test_forward_matches_reference_golden(case):
+    name, n_prot, n_lig, seed, gen_mode, enc = case
+    gold = golden('forward_cases.npz')
+    model, sd = make_model(10, device=dev(), **enc)
+    batch = synthetic.make_batch(n_prot, n_lig, seed=seed, gen_mode=gen_mode)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    xg, hg, cg = model.denoiser(x.to(dev()), h.to(dev()), bidx.to(dev()), lig.to(dev()), gen.to(dev()))
+    ex, eh, ec = (rel_err(a.cpu(), gold[f'{name}/{k}']) for a, k in ((xg, 'x'), (hg, 'h'), (cg, 'c')))
+    assert ex < TOL and eh < TOL and ec < TOL, f'{name}: x {ex:.2e} h {eh:.2e} c {ec:.2e}'
+    # atoms with gen_flag == False never move (unitransformer.py:182)
+    assert torch.equal(xg.cpu()[~gen], x[~gen])
+    # element-wise closeness of the moved coordinates as well
+    assert torch.allclose(xg.cpu(), torch.from_numpy(gold[f'{name}/x']), rtol=1e-4, atol=1e-4)
+
+
+def test_forward_radius_mode_vs_oracle():
+    from oracle import denoiser as ODn
+    model, sd = make_model(10, device=dev(), cutoff_mode='radius', r_max=9.0)
+    batch = synthetic.make_batch([150, 80], [20, 12], seed=31)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    xo, ho, co = ODn.unitransformer_forward(sd, x, h, bidx, lig, gen, cutoff_mode='radius', r_max=9.0)
+    xg, hg, cg = model.denoiser(x.to(dev()), h.to(dev()), bidx.to(dev()), lig.to(dev()), gen.to(dev()))
+    assert rel_err(xg.cpu(), xo) < TOL and rel_err(hg.cpu(), ho) < TOL and rel_err(cg.cpu(), co) < TOL
+
+
+def test_forward_host_buffers_equals_device_path():
+    model, sd = make_model(10, device=dev())
+    batch = synthetic.make_batch([120, 60], [16, 8], seed=41)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    xd, hd, cd = model.denoiser(x.to(dev()), h.to(dev()), bidx.to(dev()), lig.to(dev()), gen.to(dev()))
+    xh, hh, ch = model.denoiser.forward_host(x, h, bidx, lig, gen)
+    assert not xh.is_cuda
+    assert torch.equal(xh, xd.cpu()) and torch.equal(hh, hd.cpu()) and torch.equal(ch, cd.cpu())
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    model, sd = make_model(10)
+    batch = synthetic.make_batch([30], [6], seed=1)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    with pytest.raises(RuntimeError):
+        model.denoiser(x, h, bidx, lig, gen)
+
+
+# ---------------------------------------------------------------------------------------------
+# properties (size independent)
+def _rand_rotation(rs):
+    q, _ = np.linalg.qr(rs.normal(size=(3, 3)))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return torch.from_numpy(q.astype(np.float32))
+
+
+def test_e3_equivariance_and_batch_independence():
+    model, sd = make_model(10, device=dev())
+    batch = synthetic.make_batch([180, 90, 60], [20, 12, 7], seed=51)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    d = dev()
+    x1, h1, c1 = model.denoiser(x.to(d), h.to(d), bidx.to(d), lig.to(d), gen.to(d))
+    rs = np.random.RandomState(4)
+    R, tvec = _rand_rotation(rs), torch.tensor([3.0, -2.0, 5.0])
+    xr = x @ R.T + tvec
+    x2, h2, c2 = model.denoiser(xr.to(d), h.to(d), bidx.to(d), lig.to(d), gen.to(d))
+    # rotated/translated input -> rotated/translated coordinates, invariant features/logits
+    # (kNN selection may flip on near-ties after rotation, hence 1e-3 rather than 1e-4)
+    assert rel_err(x2.cpu(), x1.cpu() @ R.T + tvec) < 1e-3
+    assert rel_err(h2.cpu(), h1.cpu()) < 1e-3 and rel_err(c2.cpu(), c1.cpu()) < 1e-3
+    # graphs are independent: running graph 1 alone reproduces its rows bit-for-bit
+    m = bidx == 1
+    xa, ha, ca = model.denoiser(x[m].to(d), h[m].to(d), torch.zeros(int(m.sum()), dtype=torch.long, device=d),
+                                lig[m].to(d), gen[m].to(d))
+    assert torch.equal(xa.cpu(), x1.cpu()[m]) and torch.equal(ha.cpu(), h1.cpu()[m]) and torch.equal(ca.cpu(), c1.cpu()[m])
+
+
+def test_forward_is_deterministic():
+    model, sd = make_model(10, device=dev())
+    batch = synthetic.make_batch([300] * 4, [24] * 4, seed=61)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    d = dev()
+    a = model.denoiser(x.to(d), h.to(d), bidx.to(d), lig.to(d), gen.to(d))
+    b = model.denoiser(x.to(d), h.to(d), bidx.to(d), lig.to(d), gen.to(d))
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+
+
+# ---------------------------------------------------------------------------------------------
+# reverse step and sampling loop
+def test_reverse_step_matches_reference_golden():
+    g = golden('reverse_step.npz')
+    model, sd = make_model(1000, device=dev())
+    L = _lib.lib()
+    d = dev()
+    n, K = g['x0'].shape[0], 13
+    td = lambda k, dt=torch.float32: torch.from_numpy(g[k]).to(d, dt).contiguous()
+    x0, xt, logits, ct, noise, uni = td('x0'), td('xt'), td('logits'), td('ct'), td('noise'), td('uni')
+    gen = td('gen', torch.uint8)
+    for t in (0, 1, 500, 999):
+        coef = model.step_coef(t)
+        xn = torch.empty((n, 3), device=d)
+        cn = torch.empty((n, K), device=d)
+        vn = torch.empty(n, dtype=torch.int64, device=d)
+        _lib.check(L.cbg_reverse_step_f32(C.byref(coef), x0.data_ptr(), logits.data_ptr(), xt.data_ptr(), ct.data_ptr(),
+                                          gen.data_ptr(), noise.data_ptr(), uni.data_ptr(), n, K,
+                                          xn.data_ptr(), cn.data_ptr(), vn.data_ptr(), None))
+        torch.cuda.synchronize()
+        assert np.array_equal(vn.cpu().numpy(), g[f't{t}/v_next']), t        # integer: bit-exact
+        assert np.array_equal(cn.cpu().numpy(), g[f't{t}/c_next']), t
+        assert rel_err(xn.cpu(), g[f't{t}/x_next']) < 1e-6, t
+
+
+def test_short_trajectory_matches_reference_golden():
+    """TargetDiff.sample over T=10 steps with the reference's injected noise: every step's
+    atom types bit-exact, coordinates within tolerance."""
+    g = golden('trajectory.npz')
+    T = 10
+    model, sd = make_model(T, device=dev())
+    batch = synthetic.make_batch([150, 60], [20, 9], seed=21)
+    pn, tu = synthetic.make_noise(T, 29, 13, seed=7)
+    traj = model.sample(batch, pos_noise=pn, type_uniform=tu)
+    assert sorted(traj.keys()) == list(range(-1, T))
+    for t in range(-1, T):
+        x, c, b = traj[t]
+        assert (x.is_cuda, c.is_cuda) == ((t == -1), (t == -1))          # reference contract: >=0 on CPU
+        assert np.array_equal(c.cpu().argmax(-1).numpy(), g[f'v{t}']), f't={t}'
+        assert rel_err(x.cpu(), g[f'x{t}']) < TOL, f't={t}'
+        assert torch.equal(b.cpu(), batch['ligand_element_batch'])
+    assert model.last_launches > 0
+
+
+def test_sample_partial_generation_keeps_context_fixed():
+    from oracle import diffusion as OD
+    T = 6
+    model, sd = make_model(T, device=dev())
+    batch = synthetic.make_batch([100, 70], [18, 12], seed=71, gen_mode='partial')
+    pn, tu = synthetic.make_noise(T, 30, 13, seed=8)
+    traj = model.sample(batch, pos_noise=pn, type_uniform=tu)
+    want = OD.sample(sd, batch, T, pn, tu)
+    fixed = ~batch['ligand_gen_flag']
+    for t in range(-1, T):
+        assert torch.equal(traj[t][0].cpu()[fixed], batch['ligand_pos'][fixed])
+        assert torch.equal(traj[t][1].cpu().argmax(-1)[fixed], batch['ligand_atom_type'][fixed])
+        assert torch.equal(traj[t][1].cpu().argmax(-1), want[t][1].argmax(-1)), t
+        assert rel_err(traj[t][0].cpu(), want[t][0]) < TOL, t
+
+
+def test_sample_with_torch_rng_is_seed_reproducible():
+    T = 4
+    model, sd = make_model(T, device=dev())
+    batch = synthetic.make_batch([80], [10], seed=81)
+    torch.manual_seed(2024)
+    a = model.sample(batch)
+    torch.manual_seed(2024)
+    b = model.sample(batch, traj_mode='final')
+    assert torch.equal(a[0][0], b[0][0]) and torch.equal(a[0][1], b[0][1])
+    assert torch.equal(a[-1][0], b[-1][0])
+    assert set(b.keys()) == {0, -1}
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full-size shapes: size-independent properties
+def test_full_size_config2_properties():
+    """config 2 shape (64 pockets x (300 + 24) atoms): finite outputs, fixed atoms never move,
+    per-graph results identical to running one of the graphs alone (bit-for-bit)."""
+    model, sd = make_model(10, device=dev())
+    batch = synthetic.make_batch([300] * 64, [24] * 64, seed=2024)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    d = dev()
+    xg, hg, cg = model.denoiser(x.to(d), h.to(d), bidx.to(d), lig.to(d), gen.to(d))
+    assert torch.isfinite(xg).all() and torch.isfinite(hg).all() and torch.isfinite(cg).all()
+    assert torch.equal(xg.cpu()[~gen], x[~gen])
+    for gsel in (0, 37, 63):
+        m = bidx == gsel
+        xa, ha, ca = model.denoiser(x[m].to(d), h[m].to(d), torch.zeros(int(m.sum()), dtype=torch.long, device=d),
+                                    lig[m].to(d), gen[m].to(d))
+        assert torch.equal(xa.cpu(), xg.cpu()[m]) and torch.equal(ca.cpu(), cg.cpu()[m])
+
+
+def test_ragged_config5_shape_vs_oracle_subset():
+    """config 5 style ragged pockets (100..800 atoms): compare two of the graphs with the oracle."""
+    from oracle import denoiser as ODn
+    rs = np.random.RandomState(5)
+    n_prot = [int(v) for v in rs.randint(100, 801, size=12)]
+    n_prot[0], n_prot[1] = 800, 100
+    model, sd = make_model(10, device=dev())
+    batch = synthetic.make_batch(n_prot, [24] * 12, seed=91, gen_mode='partial')
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    d = dev()
+    xg, hg, cg = model.denoiser(x.to(d), h.to(d), bidx.to(d), lig.to(d), gen.to(d))
+    for gsel in (0, 1):
+        m = bidx == gsel
+        xo, ho, co = ODn.unitransformer_forward(sd, x[m], h[m], torch.zeros(int(m.sum()), dtype=torch.long), lig[m], gen[m])
+        assert rel_err(xg.cpu()[m], xo) < TOL and rel_err(hg.cpu()[m], ho) < TOL and rel_err(cg.cpu()[m], co) < TOL
