@@ -96,8 +96,9 @@ def test_edge_gate_matches_oracle():
     N = x.shape[0]
     ew = torch.empty((N, 32), dtype=torch.float32, device=dev())
     buf, wsp, wsb = _ws(N)
-    _lib.check(L.cbg_edge_gate_f32(blob.data_ptr(), x.to(dev()).contiguous().data_ptr(),
-                                   nbr.to(dev(), torch.int32).contiguous().data_ptr(), N, ew.data_ptr(), wsp, wsb, None))
+    xd = x.to(dev()).contiguous()                       # keep references alive across the call
+    nd = nbr.to(dev(), torch.int32).contiguous()
+    _lib.check(L.cbg_edge_gate_f32(blob.data_ptr(), xd.data_ptr(), nd.data_ptr(), N, ew.data_ptr(), wsp, wsb, None))
     torch.cuda.synchronize()
     assert rel_err(ew.cpu(), want) < 1e-5
 
