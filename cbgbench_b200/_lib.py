@@ -56,6 +56,7 @@ SIGNATURES = {
                                         _I64, _I32, _I32, _F, _I32, _P, _P, _P, _P, _SZ, _P]),
     'cbg_denoiser_forward_host_f32': (_I32, [_P, _I64, _I64, _I32, _I32, _P, _P, _P, _I32, _P, _P, _I64,
                                              _I32, _I32, _F, _P, _P, _P]),
+    'cbg_node_proj_f32': (_I32, [_P, _I32, _I32, _P, _P, _I32, _I64, _P, _P]),
     'cbg_sample_begin_f32': (_I32, [C.POINTER(SamplePlan), _P, _P, _P, _P]),
     'cbg_sample_step_f32': (_I32, [C.POINTER(SamplePlan), C.POINTER(StepCoef), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cbg_reverse_step_f32': (_I32, [C.POINTER(StepCoef), _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P]),

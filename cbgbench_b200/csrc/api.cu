@@ -1,6 +1,7 @@
 // C-ABI of libcbg_b200.so (declared in include/cbg_b200.h) and the per-forward orchestration.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -89,6 +90,19 @@ int check_ws(const void* workspace, size_t have, long long n_nodes, long long n_
   return 0;
 }
 
+// node GEMM implementation: tcgen05 (3xTF32) unless CBG_NODE_GEMM=simt
+int node_gemm_impl() {
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("CBG_NODE_GEMM");
+    impl = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return impl;
+}
+int launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st) {
+  return node_gemm_impl() ? cbg_launch_node_gemm_tc(a, st) : cbg_launch_node_gemm(a, st);
+}
+
 // graph build + gate + layers on an initialised workspace (x4, h valid)
 int run_core(const float* blob, int num_layers, const Workspace& ws, const int* graph_ptr, int n_graphs,
              int max_graph_nodes, long long n_nodes, const int* gen_idx, int n_gen, int mode, int k,
@@ -111,7 +125,8 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     g.q_w1t = L + cbg_layout::layer_offset(CBG_LF_X2H_Q_W1T);
     g.q_b1 = L + cbg_layout::layer_offset(CBG_LF_X2H_Q_B1);
     g.out_q = ws.plane[4];
-    if (int rc = cbg_launch_node_gemm(g, st)) return rc;
+    g.tc_planes = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_TC); g.tc_first_plane = 0;
+    if (int rc = launch_node_gemm(g, st)) return rc;
     EdgeArgs e{};
     e.x4 = ws.x4; e.nbr = ws.nbr; e.ew = ws.ew;
     e.pj_k = ws.plane[0]; e.pj_v = ws.plane[1]; e.pi_k = ws.plane[2]; e.pi_v = ws.plane[3]; e.q = ws.plane[4];
@@ -125,7 +140,8 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     gj.bias = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_B);
     gj.ldw = 640; gj.n_planes = 2; gj.has_q = 0;
     gj.out[0] = ws.plane[0]; gj.out[1] = ws.plane[1];
-    if (int rc = cbg_launch_node_gemm(gj, st)) return rc;
+    gj.tc_planes = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_TC); gj.tc_first_plane = 0;
+    if (int rc = launch_node_gemm(gj, st)) return rc;
     NodeGemmArgs gi{};
     gi.a = ws.h; gi.row_idx = gen_idx; gi.n_rows = n_gen;
     gi.wt = gj.wt + 256; gi.bias = gj.bias + 256;
@@ -135,7 +151,8 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     gi.q_w1t = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_W1T);
     gi.q_b1 = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_B1);
     gi.out_q = ws.plane[4];
-    if (int rc = cbg_launch_node_gemm(gi, st)) return rc;
+    gi.tc_planes = gj.tc_planes; gi.tc_first_plane = 2;
+    if (int rc = launch_node_gemm(gi, st)) return rc;
     EdgeArgs x = e;
     x.node_idx = gen_idx; x.n_nodes = n_gen; x.dx = ws.dx;
     if (int rc = cbg_launch_h2x(x, st)) return rc;
@@ -325,6 +342,26 @@ int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_float
   if (logits_out_host) CBG_CUDA_OK(cudaMemcpyAsync(logits_out_host, d + o_lo, (size_t)n_nodes * num_classes * 4, cudaMemcpyDeviceToHost, st));
   CBG_CUDA_OK(cudaStreamSynchronize(st));
   return 0;
+}
+
+int32_t cbg_node_proj_f32(const float* blob_layer, int32_t sublayer, int32_t impl, const float* h,
+                          const int32_t* row_idx, int32_t n_rows, int64_t n_nodes, float* planes, void* stream) {
+  if (sublayer < 0 || sublayer > 1 || impl < 0 || impl > 1) { cbg_set_error("bad sublayer/impl"); return 1; }
+  const float* L = blob_layer;
+  NodeGemmArgs g{};
+  g.a = h; g.row_idx = row_idx; g.n_rows = n_rows;
+  g.wt = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_NODE_WT : CBG_LF_X2H_NODE_WT);
+  g.bias = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_NODE_B : CBG_LF_X2H_NODE_B);
+  g.ldw = 640; g.n_planes = 5; g.has_q = 1;
+  for (int p = 0; p < 4; ++p) g.out[p] = planes + (size_t)p * n_nodes * CBG_H;
+  g.out[4] = nullptr;
+  g.q_ln = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_Q_LN : CBG_LF_X2H_Q_LN);
+  g.q_w1t = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_Q_W1T : CBG_LF_X2H_Q_W1T);
+  g.q_b1 = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_Q_B1 : CBG_LF_X2H_Q_B1);
+  g.out_q = planes + (size_t)4 * n_nodes * CBG_H;
+  g.tc_planes = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_NODE_TC : CBG_LF_X2H_NODE_TC);
+  g.tc_first_plane = 0;
+  return impl ? cbg_launch_node_gemm_tc(g, (cudaStream_t)stream) : cbg_launch_node_gemm(g, (cudaStream_t)stream);
 }
 
 int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, const uint8_t* lig_flag,

@@ -26,8 +26,12 @@ struct NodeGemmArgs {
   const float* q_w1t;    // [128][128] k-major
   const float* q_b1;     // [128]
   float* out_q;          // [N,128]
+  // tensor-core path only: pre-split weight planes of the sub-layer (layout: cbg_layout.h *_NODE_TC)
+  const float* tc_planes;  // plane 0 of the sub-layer
+  int tc_first_plane;      // index of this launch's first plane (q second Linear is always plane 5)
 };
-int cbg_launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st);
+int cbg_launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st);      // fp32 SIMT
+int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st);   // tcgen05 3xTF32
 
 // edge.cu
 struct EdgeArgs {

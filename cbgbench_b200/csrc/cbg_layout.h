@@ -44,12 +44,16 @@
   X(X2H_V_W1, 128 * 128)     /* hv_func.net.3.weight natural [f_out][f_in] */            \
   X(X2H_V_B1, 128)           /* hv_func.net.3.bias */                                    \
   X(X2H_V_RBF, 32)                                                                       \
+  /* X2H node GEMM weights for the tcgen05 path: 6 planes [Pj_k,Pj_v,Pi_k,Pi_v,q_hidden,q_out],   \
+     each = 4 K-chunks x (hi | lo) x [128 n][32 k] tf32 in UMMA canonical K-major layout */       \
+  X(X2H_NODE_TC, 6 * 32768)                                                              \
   /* H2X node GEMM */                                                                    \
   X(H2X_NODE_WT, 128 * 640)                                                              \
   X(H2X_NODE_B, 640)                                                                     \
   X(H2X_Q_LN, 256)                                                                       \
   X(H2X_Q_W1T, 128 * 128)                                                                \
   X(H2X_Q_B1, 128)                                                                       \
+  X(H2X_NODE_TC, 6 * 32768)                                                              \
   /* h2x edge kernel working set (contiguous) */                                         \
   X(H2X_K_WRF, 4 * 20 * 128)                                                             \
   X(H2X_K_C, 4 * 128)                                                                    \

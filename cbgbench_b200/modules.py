@@ -99,6 +99,31 @@ def _t(w):
     return w.detach().to('cpu', torch.float64)
 
 
+def _round_tf32(x):
+    """cvt.rna.tf32.f32 on the host: round-to-nearest (ties away) to a 10-bit mantissa, fp32 container."""
+    import numpy as np
+    b = x.astype(np.float32).view(np.uint32).astype(np.uint64)
+    b = ((b + 0x1000) & 0xFFFFE000).astype(np.uint32)
+    return b.view(np.float32)
+
+
+def tc_weight_plane(w):
+    """[128 n][128 k] weight (natural nn.Linear layout) -> the tcgen05 operand image:
+    4 K-chunks x (hi | lo) x [128 n][32 k] tf32, each in the UMMA canonical K-major / no-swizzle layout
+    (8-row x 16-byte core matrices, 128 B apart along K, 1024 B between 8-row groups)."""
+    import numpy as np
+    w = w.detach().cpu().to(torch.float32).numpy()
+    assert w.shape == (128, 128)
+    hi = _round_tf32(w)
+    lo = _round_tf32(w - hi)
+    out = np.zeros((4, 2, 16, 8, 8, 4), dtype=np.float32)      # [chunk][hi/lo][n/8][k_local/4][n%8][k%4]
+    for c in range(4):
+        for part, src in enumerate((hi, lo)):
+            blk = src[:, 32 * c: 32 * c + 32].reshape(16, 8, 8, 4)   # [n/8][n%8][kl/4][kl%4]
+            out[c, part] = blk.transpose(0, 2, 1, 3)
+    return torch.from_numpy(out.reshape(-1)).to(torch.float64)
+
+
 def pack_denoiser_blob(sd, prefix, num_layers, num_classes):
     """Pack a (reference-keyed) state dict into the flat fp32 blob of csrc/cbg_layout.h."""
     lay = _lib.blob_layout()
@@ -158,6 +183,10 @@ def pack_denoiser_blob(sd, prefix, num_layers, num_classes):
             node_b = torch.cat([torch.zeros(256, dtype=torch.float64), _t(sd[sp + kname + '.net.0.bias']),
                                 _t(sd[sp + vname + '.net.0.bias']), _t(sd[sp + qname + '.net.0.bias'])])
             put(base, lf, f'{tag}_NODE_WT', node_wt)
+            w0k, w0v = _t(sd[sp + kname + '.net.0.weight']), _t(sd[sp + vname + '.net.0.weight'])
+            tc = [w0k[:, 212:340], w0v[:, 212:340], w0k[:, 84:212], w0v[:, 84:212],
+                  _t(sd[sp + qname + '.net.0.weight']), _t(sd[sp + qname + '.net.3.weight']) * inv_sqrt_dh]
+            put(base, lf, f'{tag}_NODE_TC', torch.cat([tc_weight_plane(m.to(torch.float32)) for m in tc]))
             put(base, lf, f'{tag}_NODE_B', node_b)
             put(base, lf, f'{tag}_Q_LN', torch.cat([_t(sd[sp + qname + '.net.1.weight']), _t(sd[sp + qname + '.net.1.bias'])]))
             put(base, lf, f'{tag}_Q_W1T', (_t(sd[sp + qname + '.net.3.weight']) * inv_sqrt_dh).t().contiguous())

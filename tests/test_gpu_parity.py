@@ -314,3 +314,46 @@ def test_ragged_config5_shape_vs_oracle_subset():
         m = bidx == gsel
         xo, ho, co = ODn.unitransformer_forward(sd, x[m], h[m], torch.zeros(int(m.sum()), dtype=torch.long), lig[m], gen[m])
         assert rel_err(xg.cpu()[m], xo) < TOL and rel_err(hg.cpu()[m], ho) < TOL and rel_err(cg.cpu()[m], co) < TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# node projections: fp32 SIMT kernel and tcgen05 (3xTF32) kernel against a float64 reference
+@pytest.mark.parametrize('impl', [0, 1], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('sublayer', [0, 1], ids=['x2h', 'h2x'])
+def test_node_projections_match_float64(impl, sublayer):
+    model, sd = make_model(10, device=dev())
+    L = _lib.lib()
+    lay = _lib.blob_layout()
+    blob = model.denoiser.packed_blob(dev())
+    layer = 3
+    rs = np.random.RandomState(17)
+    N = 333                                              # not a multiple of the 64/128-row tiles
+    h = torch.from_numpy((1.5 * rs.normal(size=(N, 128))).astype(np.float32))
+    rows = torch.from_numpy(np.sort(rs.choice(N, size=150, replace=False)).astype(np.int32))
+    hd = h.to(dev())
+    base_ptr = blob.data_ptr() + 4 * (lay['global_floats'] + layer * lay['layer_floats'])
+    pre = f'denoiser.blocks.{layer}.' + ('x2h_layers.0.' if sublayer == 0 else 'h2x_layers.0.')
+    kn, vn, qn = ('hk_func', 'hv_func', 'hq_func') if sublayer == 0 else ('xk_func', 'xv_func', 'xq_func')
+    d = lambda k: sd[pre + k].double()
+    h64 = h.double()
+    w0k, w0v = d(kn + '.net.0.weight'), d(vn + '.net.0.weight')
+    want = [h64 @ w0k[:, 212:340].T, h64 @ w0v[:, 212:340].T,
+            h64 @ w0k[:, 84:212].T + d(kn + '.net.0.bias'), h64 @ w0v[:, 84:212].T + d(vn + '.net.0.bias')]
+    qh = F.layer_norm(h64 @ d(qn + '.net.0.weight').T + d(qn + '.net.0.bias'), (128,), d(qn + '.net.1.weight'),
+                      d(qn + '.net.1.bias'), 1e-5).relu()
+    want.append((qh @ d(qn + '.net.3.weight').T + d(qn + '.net.3.bias')) / np.sqrt(8.0))
+    for row_idx in (None, rows):
+        planes = torch.full((5, N, 128), float('nan'), device=dev())
+        ridx = row_idx.to(dev()) if row_idx is not None else None
+        n_rows = N if row_idx is None else int(row_idx.numel())
+        _lib.check(L.cbg_node_proj_f32(base_ptr, sublayer, impl, hd.data_ptr(), ridx.data_ptr() if ridx is not None else None,
+                                       n_rows, N, planes.data_ptr(), None))
+        torch.cuda.synchronize()
+        sel = slice(None) if row_idx is None else row_idx.long()
+        for p in range(5):
+            err = rel_err(planes[p].cpu()[sel], want[p][sel])
+            assert err < 2e-6, f'impl {impl} sublayer {sublayer} plane {p}: rel err {err:.2e}'
+        if row_idx is not None:                                   # rows not listed stay untouched
+            mask = torch.ones(N, dtype=torch.bool)
+            mask[row_idx.long()] = False
+            assert torch.isnan(planes.cpu()[:, mask]).all()
