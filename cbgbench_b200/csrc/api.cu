@@ -54,7 +54,8 @@ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 struct Workspace {
   float4* x4;
   float* h;
-  float* plane[CBG_NPLANES];   // pj_k, pj_v, pi_k, pi_v, q
+  float* plane[CBG_NPLANES];   // X2H: pj_k, pj_v, pi_k, pi_v, q
+  float* hplane[CBG_NPLANES];  // H2X: same five planes (separate so the H2X chain can overlap the next X2H GEMM)
   float* w;
   int* nbr;
   float* ew;
@@ -70,6 +71,7 @@ Workspace carve(void* base, long long n_nodes, long long n_gen) {
   ws.x4 = (float4*)take((size_t)n_nodes * sizeof(float4));
   ws.h = (float*)take((size_t)n_nodes * CBG_H * 4);
   for (int p = 0; p < CBG_NPLANES; ++p) ws.plane[p] = (float*)take((size_t)n_nodes * CBG_H * 4);
+  for (int p = 0; p < CBG_NPLANES; ++p) ws.hplane[p] = (float*)take((size_t)n_nodes * CBG_H * 4);
   ws.w = (float*)take((size_t)n_nodes * CBG_KMAX * CBG_HEADS * 4);
   ws.nbr = (int*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.ew = (float*)take((size_t)n_nodes * CBG_KMAX * 4);
@@ -103,6 +105,28 @@ int launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st) {
   return node_gemm_impl() ? cbg_launch_node_gemm_tc(a, st) : cbg_launch_node_gemm(a, st);
 }
 
+// Second stream for the H2X chain of layer l, which overlaps the X2H node GEMM of layer l+1
+// (that GEMM needs only h).  Fork/join with two events; CBG_OVERLAP=0 keeps everything on one stream.
+struct AuxStream {
+  cudaStream_t s2 = nullptr;
+  cudaEvent_t ev_h = nullptr, ev_x = nullptr;
+  int state = -1;   // -1 unknown, 0 disabled, 1 ready
+} g_aux;
+
+int aux_ready() {
+  if (g_aux.state >= 0) return g_aux.state;
+  const char* e = getenv("CBG_OVERLAP");
+  if (e && strcmp(e, "0") == 0) { g_aux.state = 0; return 0; }
+  if (cudaStreamCreateWithFlags(&g_aux.s2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g_aux.ev_h, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g_aux.ev_x, cudaEventDisableTiming) != cudaSuccess) {
+    g_aux.state = 0;
+    return 0;
+  }
+  g_aux.state = 1;
+  return 1;
+}
+
 // graph build + gate + layers on an initialised workspace (x4, h valid)
 int run_core(const float* blob, int num_layers, const Workspace& ws, const int* graph_ptr, int n_graphs,
              int max_graph_nodes, long long n_nodes, const int* gen_idx, int n_gen, int mode, int k,
@@ -111,6 +135,9 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
   if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, ws.nbr, st)) return rc;
   if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, ws.ew, st)) return rc;
   const float* layers = blob + cbg_layout::kGlobalFloats;
+  const bool overlap = (n_gen > 0) && aux_ready();
+  cudaStream_t sx = overlap ? g_aux.s2 : st;       // stream of the H2X chain
+  bool x_pending = false;                          // an apply_dx on sx has not been joined yet
   for (int l = 0; l < num_layers; ++l) {
     const float* L = layers + (size_t)l * cbg_layout::kLayerFloats;
     // ---- X2H: node planes (all nodes), attention weights, aggregation (h updated in place)
@@ -126,38 +153,46 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     g.q_b1 = L + cbg_layout::layer_offset(CBG_LF_X2H_Q_B1);
     g.out_q = ws.plane[4];
     g.tc_planes = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_TC); g.tc_first_plane = 0;
-    if (int rc = launch_node_gemm(g, st)) return rc;
+    if (int rc = launch_node_gemm(g, st)) return rc;          // reads h only: may overlap the previous H2X chain
+    if (overlap && x_pending) { CBG_CUDA_OK(cudaStreamWaitEvent(st, g_aux.ev_x, 0)); x_pending = false; }
     EdgeArgs e{};
     e.x4 = ws.x4; e.nbr = ws.nbr; e.ew = ws.ew;
     e.pj_k = ws.plane[0]; e.pj_v = ws.plane[1]; e.pi_k = ws.plane[2]; e.pi_v = ws.plane[3]; e.q = ws.plane[4];
     e.layer = L; e.w = ws.w; e.h = ws.h; e.node_idx = nullptr; e.n_nodes = (int)n_nodes; e.dx = nullptr;
     if (int rc = cbg_launch_x2h(e, st)) return rc;
     if (n_gen <= 0) continue;   // nothing moves: H2X output is multiplied by gen_flag == 0
+    if (overlap) {
+      CBG_CUDA_OK(cudaEventRecord(g_aux.ev_h, st));
+      CBG_CUDA_OK(cudaStreamWaitEvent(sx, g_aux.ev_h, 0));
+    }
     // ---- H2X (uses the NEW h and the layer-input x): Pj planes for all nodes, Pi/q for generated nodes
     NodeGemmArgs gj{};
     gj.a = ws.h; gj.row_idx = nullptr; gj.n_rows = (int)n_nodes;
     gj.wt = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_WT);
     gj.bias = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_B);
     gj.ldw = 640; gj.n_planes = 2; gj.has_q = 0;
-    gj.out[0] = ws.plane[0]; gj.out[1] = ws.plane[1];
+    gj.out[0] = ws.hplane[0]; gj.out[1] = ws.hplane[1];
     gj.tc_planes = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_TC); gj.tc_first_plane = 0;
-    if (int rc = launch_node_gemm(gj, st)) return rc;
+    if (int rc = launch_node_gemm(gj, sx)) return rc;
     NodeGemmArgs gi{};
     gi.a = ws.h; gi.row_idx = gen_idx; gi.n_rows = n_gen;
     gi.wt = gj.wt + 256; gi.bias = gj.bias + 256;
     gi.ldw = 640; gi.n_planes = 3; gi.has_q = 1;
-    gi.out[0] = ws.plane[2]; gi.out[1] = ws.plane[3]; gi.out[2] = nullptr;
+    gi.out[0] = ws.hplane[2]; gi.out[1] = ws.hplane[3]; gi.out[2] = nullptr;
     gi.q_ln = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_LN);
     gi.q_w1t = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_W1T);
     gi.q_b1 = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_B1);
-    gi.out_q = ws.plane[4];
+    gi.out_q = ws.hplane[4];
     gi.tc_planes = gj.tc_planes; gi.tc_first_plane = 2;
-    if (int rc = launch_node_gemm(gi, st)) return rc;
+    if (int rc = launch_node_gemm(gi, sx)) return rc;
     EdgeArgs x = e;
+    x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
     x.node_idx = gen_idx; x.n_nodes = n_gen; x.dx = ws.dx;
-    if (int rc = cbg_launch_h2x(x, st)) return rc;
-    if (int rc = cbg_launch_apply_dx(ws.x4, gen_idx, ws.dx, n_gen, st)) return rc;
+    if (int rc = cbg_launch_h2x(x, sx)) return rc;
+    if (int rc = cbg_launch_apply_dx(ws.x4, gen_idx, ws.dx, n_gen, sx)) return rc;
+    if (overlap) { CBG_CUDA_OK(cudaEventRecord(g_aux.ev_x, sx)); x_pending = true; }
   }
+  if (overlap && x_pending) CBG_CUDA_OK(cudaStreamWaitEvent(st, g_aux.ev_x, 0));   // join
   return 0;
 }
 

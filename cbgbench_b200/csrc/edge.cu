@@ -23,12 +23,13 @@
 // groups of 4 edges; per-(edge, head) contractions are finished with a halving butterfly
 // (warp_transpose_reduce) that leaves lane l with edge 4g + l/8 and heads 2*(l%8), 2*(l%8)+1.
 #include <math.h>
+#include <stdlib.h>
 #include "cbg_kernels.cuh"
 
 namespace {
 
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
+// warps per CTA are a template parameter (8 / 12 / 16): more warps = better latency hiding at the
+// price of a tighter register budget (255 / 168 / 128 per thread); picked at run time, see below.
 constexpr long long kOffX2hK = cbg_layout::layer_offset(CBG_LF_X2H_K_WRF);
 constexpr long long kOffX2hV = cbg_layout::layer_offset(CBG_LF_X2H_V_WRF);
 constexpr long long kOffH2x = cbg_layout::layer_offset(CBG_LF_H2X_K_WRF);
@@ -196,9 +197,10 @@ __device__ __forceinline__ void softmax32(float (&lg)[8][2], int lane, unsigned 
 // X2H, part 1: attention weights  w[i][e][hd] = softmax_e(<q_i, k_ie>) * e_w[i][e]
 // smem: K_WRF | K_C | K_LN | K_W1 | K_RBF  (contiguous in the blob) + per-warp EdgeMeta
 constexpr int kX2hKFloats = 4 * 20 * 128 + 4 * 128 + 256 + 128 * 128 + 32;
-constexpr int kX2hKSmem = kX2hKFloats * 4 + kWarps * (int)sizeof(EdgeMeta);
+constexpr int x2hk_smem(int w) { return kX2hKFloats * 4 + w * (int)sizeof(EdgeMeta); }
 
-__global__ void __launch_bounds__(kThreads, 1) x2h_k_kernel(EdgeArgs p) {
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
   extern __shared__ __align__(16) float smem[];
   const float* s_wrf = smem;
   const float* s_c = s_wrf + 4 * 20 * 128;
@@ -244,9 +246,10 @@ __global__ void __launch_bounds__(kThreads, 1) x2h_k_kernel(EdgeArgs p) {
 // X2H, part 2: h_i += W1v (sum_e w_ie a_ie) + b1v sum_e w_ie   (per head)
 // smem: V_WRF | V_C | V_LN | V_W1 | V_B1 | V_RBF + per-warp (EdgeMeta, wbuf[32][16])
 constexpr int kX2hVFloats = 4 * 20 * 128 + 4 * 128 + 256 + 128 * 128 + 128 + 32;
-constexpr int kX2hVSmem = kX2hVFloats * 4 + kWarps * ((int)sizeof(EdgeMeta) + 32 * 16 * 4);
+constexpr int x2hv_smem(int w) { return kX2hVFloats * 4 + w * ((int)sizeof(EdgeMeta) + 32 * 16 * 4); }
 
-__global__ void __launch_bounds__(kThreads, 1) x2h_v_kernel(EdgeArgs p) {
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
   extern __shared__ __align__(16) float smem[];
   const float* s_wrf = smem;
   const float* s_c = s_wrf + 4 * 20 * 128;
@@ -324,9 +327,10 @@ __global__ void __launch_bounds__(kThreads, 1) x2h_v_kernel(EdgeArgs p) {
 //   dx_i = (1/16) sum_hd sum_e alpha_ie^hd e_w (W1xv[hd] . a_v,ie + b1xv[hd]) (x_i - x_j)
 // smem: K_WRF|K_C|K_LN|K_W1 | V_WRF|V_C|V_LN|V_W1(16x128)|V_B1(32) | RBF + per-warp EdgeMeta
 constexpr int kH2xFloats = (4 * 20 * 128 + 4 * 128 + 256 + 128 * 128) + (4 * 20 * 128 + 4 * 128 + 256 + 16 * 128 + 32) + 32;
-constexpr int kH2xSmem = kH2xFloats * 4 + kWarps * (int)sizeof(EdgeMeta);
+constexpr int h2x_smem(int w) { return kH2xFloats * 4 + w * (int)sizeof(EdgeMeta); }
 
-__global__ void __launch_bounds__(kThreads, 1) h2x_kernel(EdgeArgs p) {
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) h2x_kernel(EdgeArgs p) {
   extern __shared__ __align__(16) float smem[];
   const float* k_wrf = smem;
   const float* k_c = k_wrf + 4 * 20 * 128;
@@ -395,6 +399,40 @@ __global__ void __launch_bounds__(kThreads, 1) h2x_kernel(EdgeArgs p) {
 }
 
 int g_num_sms = 0;
+int g_edge_warps = 12;
+
+template <int W>
+int set_attrs() {
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_smem(W)));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_smem(W)));
+  CBG_CUDA_OK(cudaFuncSetAttribute(h2x_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_smem(W)));
+  return 0;
+}
+
+int edge_grid(int n_nodes, int warps) {
+  const int need = (n_nodes + warps - 1) / warps;
+  return need < g_num_sms ? need : g_num_sms;
+}
+
+template <int W>
+int launch_x2h(const EdgeArgs& a, cudaStream_t st) {
+  const int grid = edge_grid(a.n_nodes, W);
+  CBG_PROF_BEGIN(CBG_K_X2H_K, st);
+  x2h_k_kernel<W><<<grid, W * 32, x2hk_smem(W), st>>>(a);
+  CBG_LAUNCHED(CBG_K_X2H_K, st);
+  CBG_PROF_BEGIN(CBG_K_X2H_V, st);
+  x2h_v_kernel<W><<<grid, W * 32, x2hv_smem(W), st>>>(a);
+  CBG_LAUNCHED(CBG_K_X2H_V, st);
+  return 0;
+}
+
+template <int W>
+int launch_h2x(const EdgeArgs& a, cudaStream_t st) {
+  CBG_PROF_BEGIN(CBG_K_H2X, st);
+  h2x_kernel<W><<<edge_grid(a.n_nodes, W), W * 32, h2x_smem(W), st>>>(a);
+  CBG_LAUNCHED(CBG_K_H2X, st);
+  return 0;
+}
 
 }  // namespace
 
@@ -404,36 +442,33 @@ int cbg_edge_init(void) {
   int dev = 0;
   CBG_CUDA_OK(cudaGetDevice(&dev));
   CBG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kX2hKSmem));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kX2hVSmem));
-  CBG_CUDA_OK(cudaFuncSetAttribute(h2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kH2xSmem));
+  if (const char* e = getenv("CBG_EDGE_WARPS")) {
+    const int w = atoi(e);
+    if (w == 8 || w == 12 || w == 16) g_edge_warps = w;
+  }
+  if (int rc = set_attrs<8>()) return rc;
+  if (int rc = set_attrs<12>()) return rc;
+  if (int rc = set_attrs<16>()) return rc;
   done = true;
   return 0;
-}
-
-static int edge_grid(int n_nodes) {
-  const int need = (n_nodes + kWarps - 1) / kWarps;
-  return need < g_num_sms ? need : g_num_sms;
 }
 
 int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
-  const int grid = edge_grid(a.n_nodes);
-  CBG_PROF_BEGIN(CBG_K_X2H_K, st);
-  x2h_k_kernel<<<grid, kThreads, kX2hKSmem, st>>>(a);
-  CBG_LAUNCHED(CBG_K_X2H_K, st);
-  CBG_PROF_BEGIN(CBG_K_X2H_V, st);
-  x2h_v_kernel<<<grid, kThreads, kX2hVSmem, st>>>(a);
-  CBG_LAUNCHED(CBG_K_X2H_V, st);
-  return 0;
+  switch (g_edge_warps) {
+    case 8: return launch_x2h<8>(a, st);
+    case 16: return launch_x2h<16>(a, st);
+    default: return launch_x2h<12>(a, st);
+  }
 }
 
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
-  CBG_PROF_BEGIN(CBG_K_H2X, st);
-  h2x_kernel<<<edge_grid(a.n_nodes), kThreads, kH2xSmem, st>>>(a);
-  CBG_LAUNCHED(CBG_K_H2X, st);
-  return 0;
+  switch (g_edge_warps) {
+    case 8: return launch_h2x<8>(a, st);
+    case 16: return launch_h2x<16>(a, st);
+    default: return launch_h2x<12>(a, st);
+  }
 }
