@@ -21,7 +21,9 @@
 // Thread mapping: a warp owns one destination node at a time.  Geometry is computed with
 // lane = edge; the MLP math with lane = 4 consecutive features (f = 4*lane .. 4*lane+3) for
 // groups of 4 edges; per-(edge, head) contractions are finished with a halving butterfly
-// (warp_transpose_reduce) that leaves lane l with edge 4g + l/8 and heads 2*(l%8), 2*(l%8)+1.
+// that leaves lane l with head l/2 and edges 4g + 2*(l%2), 4g + 2*(l%2) + 1.  The butterfly is
+// select-free for its four head steps because every lane keeps its per-head operand (U, W1xv) in a
+// lane-permuted order (physical slot hp <-> head hp ^ (lane >> 1)).
 #include <math.h>
 #include <stdlib.h>
 #include "cbg_kernels.cuh"
@@ -74,6 +76,27 @@ __device__ __forceinline__ unsigned edge_setup(EdgeMeta& M, int i, int lane, con
   return vmask;
 }
 
+// All-lane sums of 4 per-lane values, result in every lane: transposed butterfly (each step halves
+// the number of live values), three plain steps, four broadcasts: 10 SHFL instead of 20.
+__device__ __forceinline__ void allreduce4(float (&s)[4], int lane) {
+  const bool u1 = (lane & 16) != 0;
+  float k0 = u1 ? s[2] : s[0], k1 = u1 ? s[3] : s[1];
+  const float d0 = u1 ? s[0] : s[2], d1 = u1 ? s[1] : s[3];
+  k0 += __shfl_xor_sync(CBG_FULL, d0, 16);
+  k1 += __shfl_xor_sync(CBG_FULL, d1, 16);
+  const bool u2 = (lane & 8) != 0;
+  float k = u2 ? k1 : k0;
+  const float d = u2 ? k0 : k1;
+  k += __shfl_xor_sync(CBG_FULL, d, 8);
+  k += __shfl_xor_sync(CBG_FULL, k, 4);
+  k += __shfl_xor_sync(CBG_FULL, k, 2);
+  k += __shfl_xor_sync(CBG_FULL, k, 1);
+  s[0] = __shfl_sync(CBG_FULL, k, 0);     // lanes 0-7 hold value 0, 8-15 value 1, 16-23 value 2, 24-31 value 3
+  s[1] = __shfl_sync(CBG_FULL, k, 8);
+  s[2] = __shfl_sync(CBG_FULL, k, 16);
+  s[3] = __shfl_sync(CBG_FULL, k, 24);
+}
+
 // First Linear + LayerNorm + ReLU of one edge MLP for the 4 edges e0..e0+3.
 // a[ee] = relu(LN(Pi + Pj[j] + c[t] + Wrf[t] g)) restricted to this lane's 4 features.
 __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane, const float4 pi,
@@ -111,20 +134,14 @@ __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane
   float s[4];
 #pragma unroll
   for (int ee = 0; ee < 4; ++ee) s[ee] = (a[ee].x + a[ee].y) + (a[ee].z + a[ee].w);
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1)
-#pragma unroll
-    for (int ee = 0; ee < 4; ++ee) s[ee] += __shfl_xor_sync(CBG_FULL, s[ee], m);
+  allreduce4(s, lane);
 #pragma unroll
   for (int ee = 0; ee < 4; ++ee) {
     const float mean = s[ee] * (1.f / 128.f);
     a[ee].x -= mean; a[ee].y -= mean; a[ee].z -= mean; a[ee].w -= mean;
     s[ee] = (a[ee].x * a[ee].x + a[ee].y * a[ee].y) + (a[ee].z * a[ee].z + a[ee].w * a[ee].w);
   }
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1)
-#pragma unroll
-    for (int ee = 0; ee < 4; ++ee) s[ee] += __shfl_xor_sync(CBG_FULL, s[ee], m);
+  allreduce4(s, lane);
 #pragma unroll
   for (int ee = 0; ee < 4; ++ee) {
     const float rstd = 1.f / sqrtf(s[ee] * (1.f / 128.f) + 1e-5f);
@@ -135,62 +152,85 @@ __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane
   }
 }
 
-// U[c][hd] = sum_{d<8} q[hd*8+d] * W1[hd*8+d][4*lane+c]   (W1 natural [f_out][f_in] in smem)
+// Query-folded key matrix, lane-permuted: Up[c][hp] = U[c][hp ^ (lane>>1)] with
+// U[c][hd] = sum_{d<8} q[hd*8+d] * W1[hd*8+d][4*lane+c]   (W1 natural [f_out][f_in] in smem).
 __device__ __forceinline__ void build_u(const float* __restrict__ q_i, const float* s_w1, int lane,
                                         float (&U)[4][CBG_HEADS]) {
+  const int hx = lane >> 1;
 #pragma unroll
-  for (int hd = 0; hd < CBG_HEADS; ++hd) {
+  for (int hp = 0; hp < CBG_HEADS; ++hp) {
+    const int hd = hp ^ hx;
     const float4 q0 = ldg4(q_i + hd * 8), q1 = ldg4(q_i + hd * 8 + 4);
     const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
     float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int d = 0; d < 8; ++d) fma4(u, ld4(s_w1 + (hd * 8 + d) * CBG_H + 4 * lane), qv[d]);
-    U[0][hd] = u.x; U[1][hd] = u.y; U[2][hd] = u.z; U[3][hd] = u.w;
+    U[0][hp] = u.x; U[1][hp] = u.y; U[2][hp] = u.z; U[3][hp] = u.w;
   }
 }
 
-// part[ee*16+hd] = a[ee] . U[:,hd] (this lane's 4 features), then all-lane sums.
-// Afterwards lane l holds, for edge 4g + l/8, heads 2*(l%8) and 2*(l%8)+1 in r0, r1.
+// Reduce part[hp*4 + ee] (hp = lane-permuted head slot, ee = edge in the group) over the warp.
+// Steps 1-4 split on the head bits; because slot hp holds head hp ^ (lane>>1), every lane keeps
+// its lower half and sends its upper half: no selects.  Step 5 splits the high edge bit.
+// Result: r0, r1 = totals for head lane>>1 and edges 2*(lane&1), 2*(lane&1)+1 of the group.
+__device__ __forceinline__ void reduce_heads(float (&part)[64], int lane, float& r0, float& r1) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) part[i] += __shfl_xor_sync(CBG_FULL, part[i + 32], 16);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) part[i] += __shfl_xor_sync(CBG_FULL, part[i + 16], 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) part[i] += __shfl_xor_sync(CBG_FULL, part[i + 8], 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) part[i] += __shfl_xor_sync(CBG_FULL, part[i + 4], 2);
+  const bool up = (lane & 1) != 0;
+  const float s0 = up ? part[0] : part[2], s1 = up ? part[1] : part[3];
+  const float k0 = up ? part[2] : part[0], k1 = up ? part[3] : part[1];
+  r0 = k0 + __shfl_xor_sync(CBG_FULL, s0, 1);
+  r1 = k1 + __shfl_xor_sync(CBG_FULL, s1, 1);
+}
+
+// part[hp*4+ee] = a[ee] . Up[:,hp] (this lane's 4 features), then all-lane sums (see reduce_heads).
 __device__ __forceinline__ void contract_heads(const float4 (&a)[4], const float (&U)[4][CBG_HEADS], int lane,
                                                float& r0, float& r1) {
   float part[64];
 #pragma unroll
-  for (int ee = 0; ee < 4; ++ee)
+  for (int hp = 0; hp < CBG_HEADS; ++hp)
 #pragma unroll
-    for (int hd = 0; hd < CBG_HEADS; ++hd)
-      part[ee * 16 + hd] = fmaf(a[ee].w, U[3][hd], fmaf(a[ee].z, U[2][hd], fmaf(a[ee].y, U[1][hd], a[ee].x * U[0][hd])));
-  warp_transpose_reduce<64>(part, lane);
-  r0 = part[0];
-  r1 = part[1];
+    for (int ee = 0; ee < 4; ++ee)
+      part[hp * 4 + ee] = fmaf(a[ee].w, U[3][hp], fmaf(a[ee].z, U[2][hp], fmaf(a[ee].y, U[1][hp], a[ee].x * U[0][hp])));
+  reduce_heads(part, lane, r0, r1);
 }
 
-// in-warp segment softmax over the 32 edges for this lane's 2 heads; 8 logits per head per lane
-// (groups g = 0..7), lanes with equal (lane % 8) share the heads.  Returns alpha in place.
+// edge handled by this lane for value i (0/1) of group g under the reduce_heads mapping
+__device__ __forceinline__ int lane_edge(int g, int lane, int i) { return 4 * g + 2 * (lane & 1) + i; }
+
+// in-warp segment softmax over the 32 edges of head lane>>1: 16 logits per lane (8 groups x 2
+// edges), the other 16 live in lane^1.  Returns alpha in place.
 __device__ __forceinline__ void softmax32(float (&lg)[8][2], int lane, unsigned vmask) {
+  float mx = -INFINITY;
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const bool valid = (vmask >> (4 * g + (lane >> 3))) & 1u;
-    if (!valid) { lg[g][0] = -INFINITY; lg[g][1] = -INFINITY; }
-  }
+  for (int g = 0; g < 8; ++g)
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float mx = lg[0][i];
+    for (int i = 0; i < 2; ++i) {
+      const bool valid = (vmask >> lane_edge(g, lane, i)) & 1u;
+      if (!valid) lg[g][i] = -INFINITY;
+      mx = fmaxf(mx, lg[g][i]);
+    }
+  mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 1));
+  float sum = 0.f;
 #pragma unroll
-    for (int g = 1; g < 8; ++g) mx = fmaxf(mx, lg[g][i]);
-    mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 8));
-    mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 16));
-    float sum = 0.f;
+  for (int g = 0; g < 8; ++g)
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int i = 0; i < 2; ++i) {
       lg[g][i] = (mx == -INFINITY) ? 0.f : expf(lg[g][i] - mx);
       sum += lg[g][i];
     }
-    sum += __shfl_xor_sync(CBG_FULL, sum, 8);
-    sum += __shfl_xor_sync(CBG_FULL, sum, 16);
-    const float inv = (sum > 0.f) ? sum : 1.f;
+  sum += __shfl_xor_sync(CBG_FULL, sum, 1);
+  const float inv = (sum > 0.f) ? sum : 1.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) lg[g][i] = lg[g][i] / inv;
-  }
+  for (int g = 0; g < 8; ++g)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) lg[g][i] = lg[g][i] / inv;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -233,11 +273,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
     softmax32(lg, lane, vmask);
     float* wout = p.w + (size_t)i * (CBG_KMAX * CBG_HEADS);
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int e = 4 * g + (lane >> 3);
-      const float ew = M.ew[e];
-      *reinterpret_cast<float2*>(wout + e * CBG_HEADS + 2 * (lane & 7)) = make_float2(lg[g][0] * ew, lg[g][1] * ew);
-    }
+    for (int g = 0; g < 8; ++g)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e = lane_edge(g, lane, i);
+        wout[e * CBG_HEADS + (lane >> 1)] = lg[g][i] * M.ew[e];
+      }
     __syncwarp();   // M is rewritten by the next node's setup
   }
 }
@@ -293,30 +334,58 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
         for (int hd = 0; hd < CBG_HEADS; ++hd) fma4(S[hd], a[ee], wv[hd]);
       }
     }
-    // out[f'] = W1v[f'][:] . S[head(f')][:]  -> 128 partials per lane in two halves of 64
+    // out[f'] = W1v[f'][:] . S[head(f')][:]  -> 128 partials per lane in two halves of 64.
+    // Partial index = dp*8 + hh with f' = half*64 + hh*8 + (dp ^ (lane>>2)): the three steps over the
+    // within-head bits are select-free (lane-permuted rows of W1v), the two steps over head bits
+    // use selects.  Lane l ends with hh = 2*(l&3) + {0,1}, d = l>>2.
     const float* hin = p.h + (size_t)i * CBG_H;
+    const int dx3 = lane >> 2;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       float part[64];
 #pragma unroll
-      for (int fo = 0; fo < 64; ++fo) {
-        const int f = half * 64 + fo;
-        const float4 wv = ld4(s_w1 + f * CBG_H + 4 * lane);
-        const float4 sv = S[f >> 3];
-        part[fo] = fmaf(wv.w, sv.w, fmaf(wv.z, sv.z, fmaf(wv.y, sv.y, wv.x * sv.x)));
-      }
-      warp_transpose_reduce<64>(part, lane);
-      const int f0 = half * 64 + 2 * lane;           // this lane's outputs f0, f0+1 (same head)
-      const int hd = f0 >> 3;
-      float sw = 0.f;
+      for (int dp = 0; dp < 8; ++dp)
 #pragma unroll
-      for (int e = 0; e < 32; ++e) sw += wbuf[e * 16 + hd];
-      const float2 hv = *reinterpret_cast<const float2*>(hin + f0);
-      const float2 b1 = *reinterpret_cast<const float2*>(s_b1 + f0);
-      float2 o;
-      o.x = hv.x + (part[0] + b1.x * sw);
-      o.y = hv.y + (part[1] + b1.y * sw);
-      *reinterpret_cast<float2*>(p.h + (size_t)i * CBG_H + f0) = o;
+        for (int hh = 0; hh < 8; ++hh) {
+          const int f = half * 64 + hh * 8 + (dp ^ dx3);
+          const float4 wv = ld4(s_w1 + f * CBG_H + 4 * lane);
+          const float4 sv = S[half * 8 + hh];
+          part[dp * 8 + hh] = fmaf(wv.w, sv.w, fmaf(wv.z, sv.z, fmaf(wv.y, sv.y, wv.x * sv.x)));
+        }
+#pragma unroll
+      for (int k = 0; k < 32; ++k) part[k] += __shfl_xor_sync(CBG_FULL, part[k + 32], 16);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) part[k] += __shfl_xor_sync(CBG_FULL, part[k + 16], 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) part[k] += __shfl_xor_sync(CBG_FULL, part[k + 8], 4);
+      {   // hh bit 2 <-> lane bit 1
+        const bool up = (lane & 2) != 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float send = up ? part[k] : part[k + 4];
+          const float keep = up ? part[k + 4] : part[k];
+          part[k] = keep + __shfl_xor_sync(CBG_FULL, send, 2);
+        }
+      }
+      {   // hh bit 1 <-> lane bit 0
+        const bool up = (lane & 1) != 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float send = up ? part[k] : part[k + 2];
+          const float keep = up ? part[k + 2] : part[k];
+          part[k] = keep + __shfl_xor_sync(CBG_FULL, send, 1);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int hh = 2 * (lane & 3) + k;
+        const int hd = half * 8 + hh;
+        const int f = half * 64 + hh * 8 + dx3;
+        float sw = 0.f;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) sw += wbuf[e * 16 + hd];
+        p.h[(size_t)i * CBG_H + f] = hin[f] + (part[k] + s_b1[f] * sw);
+      }
     }
     __syncwarp();
   }
@@ -350,7 +419,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) h2x_kernel(EdgeArgs p) {
   const MlpSmem WK{k_wrf, k_c}, WV{v_wrf, v_c};
   const float4 kga = ld4(k_ln + 4 * lane), kbe = ld4(k_ln + 128 + 4 * lane);
   const float4 vga = ld4(v_ln + 4 * lane), vbe = ld4(v_ln + 128 + 4 * lane);
-  const float b1_0 = v_b1[2 * (lane & 7)], b1_1 = v_b1[2 * (lane & 7) + 1];
+  const float b1 = v_b1[lane >> 1];      // this lane's head under the reduce_heads mapping
 
   for (int n = blockIdx.x * kWarps + warp; n < p.n_nodes; n += gridDim.x * kWarps) {
     const int i = p.node_idx[n];
@@ -372,26 +441,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) h2x_kernel(EdgeArgs p) {
       first_layer4(M, 4 * g, lane, piv, p.pj_v, WV, vga, vbe, a);
       float part[64];
 #pragma unroll
-      for (int hd = 0; hd < CBG_HEADS; ++hd) {
-        const float4 wv = ld4(v_w1 + hd * CBG_H + 4 * lane);
+      for (int hp = 0; hp < CBG_HEADS; ++hp) {
+        const float4 wv = ld4(v_w1 + (hp ^ (lane >> 1)) * CBG_H + 4 * lane);   // lane-permuted head slot
 #pragma unroll
         for (int ee = 0; ee < 4; ++ee)
-          part[ee * 16 + hd] = fmaf(a[ee].w, wv.w, fmaf(a[ee].z, wv.z, fmaf(a[ee].y, wv.y, a[ee].x * wv.x)));
+          part[hp * 4 + ee] = fmaf(a[ee].w, wv.w, fmaf(a[ee].z, wv.z, fmaf(a[ee].y, wv.y, a[ee].x * wv.x)));
       }
-      warp_transpose_reduce<64>(part, lane);
+      reduce_heads(part, lane, r0, r1);
 #pragma unroll
-      for (int gg = 0; gg < 8; ++gg) if (gg == g) { vx[gg][0] = part[0] + b1_0; vx[gg][1] = part[1] + b1_1; }
+      for (int gg = 0; gg < 8; ++gg) if (gg == g) { vx[gg][0] = r0 + b1; vx[gg][1] = r1 + b1; }
     }
     softmax32(lg, lane, vmask);
     float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const int e = 4 * g + (lane >> 3);
-      const float coef = M.ew[e] * (lg[g][0] * vx[g][0] + lg[g][1] * vx[g][1]);
-      ax = fmaf(coef, M.rel[0][e], ax);
-      ay = fmaf(coef, M.rel[1][e], ay);
-      az = fmaf(coef, M.rel[2][e], az);
-    }
+    for (int g = 0; g < 8; ++g)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e = lane_edge(g, lane, i);
+        const float coef = M.ew[e] * lg[g][i] * vx[g][i];
+        ax = fmaf(coef, M.rel[0][e], ax);
+        ay = fmaf(coef, M.rel[1][e], ay);
+        az = fmaf(coef, M.rel[2][e], az);
+      }
     ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
     if (lane == 0) st4(p.dx + 4 * (size_t)n, make_float4(ax * (1.f / 16.f), ay * (1.f / 16.f), az * (1.f / 16.f), 0.f));
     __syncwarp();
