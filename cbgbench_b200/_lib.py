@@ -21,6 +21,7 @@ class SamplePlan(C.Structure):
         ('gen_lig', C.c_void_p), ('gen_node', C.c_void_p), ('n_gen', C.c_int32),
         ('mode', C.c_int32), ('k', C.c_int32), ('r_max', C.c_float),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
+        ('rcache', C.c_void_p), ('rcache_bytes', C.c_size_t),
     ]
 
 
@@ -49,6 +50,7 @@ SIGNATURES = {
     'cbg_blob_field_name': (C.c_char_p, [_I32, _I32]),
     'cbg_blob_field_offset': (_I64, [_I32, _I32]),
     'cbg_blob_field_size': (_I64, [_I32, _I32]),
+    'cbg_rcache_bytes': (_I64, [_I64, _I32]),
     'cbg_workspace_bytes': (_I64, [_I64, _I64]),
     'cbg_build_neighbors_f32': (_I32, [_P, _P, _I32, _I64, _I32, _I32, _I32, _F, _P, _P, _SZ, _P]),
     'cbg_edge_gate_f32': (_I32, [_P, _P, _P, _I64, _P, _P, _SZ, _P]),

@@ -58,6 +58,7 @@ struct Workspace {
   float* hplane[CBG_NPLANES];  // H2X: same five planes (separate so the H2X chain can overlap the next X2H GEMM)
   float* w;
   int* nbr;
+  int* snbr;                   // static-only neighbour lists (R-cache build)
   float* ew;
   float* dx;
   size_t bytes;
@@ -74,6 +75,7 @@ Workspace carve(void* base, long long n_nodes, long long n_gen) {
   for (int p = 0; p < CBG_NPLANES; ++p) ws.hplane[p] = (float*)take((size_t)n_nodes * CBG_H * 4);
   ws.w = (float*)take((size_t)n_nodes * CBG_KMAX * CBG_HEADS * 4);
   ws.nbr = (int*)take((size_t)n_nodes * CBG_KMAX * 4);
+  ws.snbr = (int*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.ew = (float*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.dx = (float*)take((size_t)(n_gen > 0 ? n_gen : 1) * 16);
   ws.bytes = off;
@@ -130,9 +132,9 @@ int aux_ready() {
 // graph build + gate + layers on an initialised workspace (x4, h valid)
 int run_core(const float* blob, int num_layers, const Workspace& ws, const int* graph_ptr, int n_graphs,
              int max_graph_nodes, long long n_nodes, const int* gen_idx, int n_gen, int mode, int k,
-             float r_max, cudaStream_t st) {
+             float r_max, const float* rcache, cudaStream_t st) {
   if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
-  if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, ws.nbr, st)) return rc;
+  if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, ws.nbr, st)) return rc;
   if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, ws.ew, st)) return rc;
   const float* layers = blob + cbg_layout::kGlobalFloats;
   const bool overlap = (n_gen > 0) && aux_ready();
@@ -159,6 +161,11 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     e.x4 = ws.x4; e.nbr = ws.nbr; e.ew = ws.ew;
     e.pj_k = ws.plane[0]; e.pj_v = ws.plane[1]; e.pi_k = ws.plane[2]; e.pi_v = ws.plane[3]; e.q = ws.plane[4];
     e.layer = L; e.w = ws.w; e.h = ws.h; e.node_idx = nullptr; e.n_nodes = (int)n_nodes; e.dx = nullptr;
+    if (rcache) {
+      const size_t per = (size_t)n_nodes * (CBG_KMAX * CBG_H);
+      e.rc_k = rcache + (size_t)(2 * l) * per;
+      e.rc_v = rcache + (size_t)(2 * l + 1) * per;
+    }
     if (int rc = cbg_launch_x2h(e, st)) return rc;
     if (n_gen <= 0) continue;   // nothing moves: H2X output is multiplied by gen_flag == 0
     if (overlap) {
@@ -187,7 +194,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     if (int rc = launch_node_gemm(gi, sx)) return rc;
     EdgeArgs x = e;
     x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
-    x.node_idx = gen_idx; x.n_nodes = n_gen; x.dx = ws.dx;
+    x.node_idx = gen_idx; x.n_nodes = n_gen; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr;
     if (int rc = cbg_launch_h2x(x, sx)) return rc;
     if (int rc = cbg_launch_apply_dx(ws.x4, gen_idx, ws.dx, n_gen, sx)) return rc;
     if (overlap) { CBG_CUDA_OK(cudaEventRecord(g_aux.ev_x, sx)); x_pending = true; }
@@ -265,6 +272,11 @@ int64_t cbg_blob_field_offset(int32_t section, int32_t idx) {
   return -1;
 }
 
+int64_t cbg_rcache_bytes(int64_t n_nodes, int32_t num_layers) {
+  if (n_nodes < 0 || num_layers < 0) return -1;
+  return (int64_t)2 * num_layers * n_nodes * (CBG_KMAX * CBG_H) * (int64_t)sizeof(float);
+}
+
 int64_t cbg_workspace_bytes(int64_t n_nodes, int64_t n_gen) {
   if (n_nodes < 0 || n_gen < 0) return -1;
   return (int64_t)carve(nullptr, n_nodes, n_gen).bytes;
@@ -279,7 +291,7 @@ int32_t cbg_build_neighbors_f32(const float* x, const int32_t* graph_ptr, int32_
   // flags are irrelevant for the neighbour search: pack with zeros
   CBG_CUDA_OK(cudaMemsetAsync(ws.nbr, 0, (size_t)n_nodes, st));   // reuse as a zero flag array
   if (int rc = cbg_launch_pack_x4(x, (const unsigned char*)ws.nbr, (const unsigned char*)ws.nbr, n_nodes, ws.x4, st)) return rc;
-  return cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, nbr, st);
+  return cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, nbr, st);
 }
 
 int32_t cbg_edge_gate_f32(const float* blob, const float* x, const int32_t* nbr, int64_t n_nodes, float* ew,
@@ -306,7 +318,7 @@ int32_t cbg_denoiser_forward_f32(const float* blob, int32_t num_layers, int32_t 
   if (int rc = cbg_launch_pack_x4(x, lig_flag, gen_flag, n_nodes, ws.x4, st)) return rc;
   CBG_CUDA_OK(cudaMemcpyAsync(ws.h, h, (size_t)n_nodes * CBG_H * 4, cudaMemcpyDeviceToDevice, st));
   const int L = (stop_after_layers >= 0 && stop_after_layers < num_layers) ? stop_after_layers : num_layers;
-  if (int rc = run_core(blob, L, ws, graph_ptr, n_graphs, max_graph_nodes, n_nodes, gen_idx, n_gen, mode, k, r_max, st)) return rc;
+  if (int rc = run_core(blob, L, ws, graph_ptr, n_graphs, max_graph_nodes, n_nodes, gen_idx, n_gen, mode, k, r_max, nullptr, st)) return rc;
   if (x_out) { if (int rc = cbg_launch_unpack_x(ws.x4, n_nodes, x_out, st)) return rc; }
   if (h_out) CBG_CUDA_OK(cudaMemcpyAsync(h_out, ws.h, (size_t)n_nodes * CBG_H * 4, cudaMemcpyDeviceToDevice, st));
   if (logits_out) {
@@ -404,7 +416,18 @@ int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, 
   if (!plan) { cbg_set_error("null plan"); return 1; }
   Workspace ws;
   if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
-  return cbg_launch_pack_x4(x_nodes, lig_flag, gen_flag, plan->n_nodes, ws.x4, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = cbg_launch_pack_x4(x_nodes, lig_flag, gen_flag, plan->n_nodes, ws.x4, st)) return rc;
+  if (plan->rcache) {
+    // step-invariant edge terms of the static (non-generated) part of every graph, SURVEY.md Appendix B
+    const int64_t need = cbg_rcache_bytes(plan->n_nodes, plan->num_layers);
+    if ((int64_t)plan->rcache_bytes < need) { cbg_set_error("rcache too small: have %zu bytes, need %lld", plan->rcache_bytes, (long long)need); return 1; }
+    if (int rc = cbg_launch_knn(ws.x4, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes, CBG_MODE_KNN, CBG_KMAX,
+                                0.f, 1, ws.snbr, st)) return rc;
+    if (int rc = cbg_launch_rcache(plan->blob + cbg_layout::kGlobalFloats, plan->num_layers, ws.x4, ws.snbr,
+                                   (int)plan->n_nodes, plan->rcache, st)) return rc;
+  }
+  return 0;
 }
 
 int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* coef, const float* x_t,
@@ -419,7 +442,7 @@ int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* co
   if (int rc = cbg_launch_step_init(x_t, c_t, plan->lig_node, plan->n_lig, K, plan->emb_wt, plan->h_lig_bias,
                                     plan->h_static, plan->n_nodes, ws.x4, ws.h, st)) return rc;
   if (int rc = run_core(plan->blob, plan->num_layers, ws, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes,
-                        plan->n_nodes, plan->gen_node, plan->n_gen, plan->mode, plan->k, plan->r_max, st)) return rc;
+                        plan->n_nodes, plan->gen_node, plan->n_gen, plan->mode, plan->k, plan->r_max, plan->rcache, st)) return rc;
   // classifier on ligand rows only; logits scratch lives in the w buffer (free after the layers)
   float* lg = logits ? logits : ws.w;
   if (int rc = cbg_launch_classifier(plan->blob, ws.h, plan->lig_node, plan->n_lig, K, lg, st)) return rc;

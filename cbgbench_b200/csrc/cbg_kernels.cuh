@@ -6,8 +6,10 @@
 #define CBG_MODE_RADIUS 1
 
 // graph.cu
+// static_only != 0: neighbour search restricted to nodes without the generate bit (centres with
+// the bit get an empty row) - the static-only kNN lists behind the R-cache
 int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max_graph_nodes, int mode,
-                   int k, float r_max, int* nbr, cudaStream_t st);
+                   int k, float r_max, int static_only, int* nbr, cudaStream_t st);
 int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
                          float* ew, cudaStream_t st);
 
@@ -49,7 +51,11 @@ struct EdgeArgs {
   const int* node_idx;   // h2x: list of generated nodes
   int n_nodes;           // x2h: N ; h2x: number of generated nodes
   float* dx;             // h2x: [n_nodes,4] coordinate deltas (compact, same order as node_idx)
+  const float* rc_k;     // x2h: R-cache of this layer's hk / hv MLP ([N][32][128]) or nullptr
+  const float* rc_v;
 };
+int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, const int* snbr, int n_nodes,
+                      float* rcache, cudaStream_t st);
 int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st);
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st);
 int cbg_edge_init(void);  // sets max-dynamic-smem attributes once

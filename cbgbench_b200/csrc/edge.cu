@@ -35,13 +35,16 @@ namespace {
 constexpr long long kOffX2hK = cbg_layout::layer_offset(CBG_LF_X2H_K_WRF);
 constexpr long long kOffX2hV = cbg_layout::layer_offset(CBG_LF_X2H_V_WRF);
 constexpr long long kOffH2x = cbg_layout::layer_offset(CBG_LF_H2X_K_WRF);
+constexpr long long kOffX2hKRbf = cbg_layout::layer_offset(CBG_LF_X2H_K_RBF);
+constexpr long long kOffX2hVRbf = cbg_layout::layer_offset(CBG_LF_X2H_V_RBF);
 
-struct __align__(16) EdgeMeta {   // per-warp scratch, 3328 B
+struct __align__(16) EdgeMeta {   // per-warp scratch, 3456 B; indexed by the PERMUTED edge position
   float g[CBG_NRBF][32];          // g[m][e]
   float rel[3][32];               // x_i - x_j
   float ew[32];                   // e_w (0 for padded slots)
   int j[32];                      // source node (i itself for padded slots)
   int t[32];                      // edge type 0..3
+  int slot[32];                   // index into the node's static-neighbour list (-1: not a static edge)
 };
 
 struct MlpSmem {                  // first-layer weights of one edge MLP in shared memory
@@ -49,7 +52,13 @@ struct MlpSmem {                  // first-layer weights of one edge MLP in shar
   const float* c;                 // [4][128]
 };
 
-// lane = edge: geometry, RBF, type.  Returns the validity ballot.
+// lane = edge: geometry, RBF, type.  The 32 slots of the node are re-ordered as
+//   [static edges (both endpoints have gen_flag == 0) | other valid edges | padding],
+// each class keeping its nearest-first order; every edge kernel applies the same permutation, so
+// positions agree between x2h_k (writes w) and x2h_v (reads w).  Static edges never change over the
+// diffusion steps (their endpoints never move), which is what the R-cache below exploits; the p-th
+// static edge of the list is the p-th entry of the node's static-only kNN list (prefix property).
+// Returns the validity mask in permuted positions.
 __device__ __forceinline__ unsigned edge_setup(EdgeMeta& M, int i, int lane, const float4* __restrict__ x4,
                                                const int* __restrict__ nbr, const float* __restrict__ ew,
                                                const float* s_rbf) {
@@ -60,20 +69,37 @@ __device__ __forceinline__ unsigned edge_setup(EdgeMeta& M, int i, int lane, con
   const float4 xj = x4[j];
   const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
   const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+  const int fi = node_flags(xi), fj = node_flags(xj);
+  const bool is_static = valid && ((fi | fj) & 2) == 0;
+  const unsigned vm = __ballot_sync(CBG_FULL, valid);
+  const unsigned sm = __ballot_sync(CBG_FULL, is_static);
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_static = __popc(sm), n_valid = __popc(vm);
+  const int rank_s = __popc(sm & lt);
+  const int pos = is_static ? rank_s
+                            : (valid ? n_static + __popc(vm & ~sm & lt) : n_valid + __popc(~vm & lt));
   const float coeff = s_rbf[20];
 #pragma unroll
   for (int m = 0; m < CBG_NRBF; ++m) {
     const float u = d - s_rbf[m];
-    M.g[m][lane] = expf(coeff * u * u);
+    M.g[m][pos] = expf(coeff * u * u);
   }
-  M.rel[0][lane] = rx; M.rel[1][lane] = ry; M.rel[2][lane] = rz;
-  M.ew[lane] = valid ? ew[(size_t)i * CBG_KMAX + lane] : 0.f;
-  M.j[lane] = j;
+  M.rel[0][pos] = rx; M.rel[1][pos] = ry; M.rel[2][pos] = rz;
+  M.ew[pos] = valid ? ew[(size_t)i * CBG_KMAX + lane] : 0.f;
+  M.j[pos] = j;
   // unitransformer.py:88-99: 0 lig->lig, 1 lig src/prot dst, 2 prot src/lig dst, 3 prot->prot
-  M.t[lane] = ((node_flags(xj) & 1) ? 0 : 2) + ((node_flags(xi) & 1) ? 0 : 1);
-  const unsigned vmask = __ballot_sync(CBG_FULL, valid);
+  M.t[pos] = ((fj & 1) ? 0 : 2) + ((fi & 1) ? 0 : 1);
+  M.slot[pos] = is_static ? rank_s : -1;
   __syncwarp();
-  return vmask;
+  return (n_valid >= 32) ? 0xffffffffu : ((1u << n_valid) - 1u);
+}
+
+// pull the next node's R block (16 KB, contiguous) towards L2 while this node computes
+__device__ __forceinline__ void prefetch_rc(const float* rc_base, int i_next, int n_nodes, int lane) {
+  if (rc_base == nullptr || i_next >= n_nodes) return;
+  const char* b = reinterpret_cast<const char*>(rc_base + (size_t)i_next * (CBG_KMAX * CBG_H));
+#pragma unroll
+  for (int r = 0; r < 4; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (size_t)(lane + 32 * r) * 128));
 }
 
 // All-lane sums of 4 per-lane values, result in every lane: transposed butterfly (each step halves
@@ -99,10 +125,23 @@ __device__ __forceinline__ void allreduce4(float (&s)[4], int lane) {
 
 // First Linear + LayerNorm + ReLU of one edge MLP for the 4 edges e0..e0+3.
 // a[ee] = relu(LN(Pi + Pj[j] + c[t] + Wrf[t] g)) restricted to this lane's 4 features.
+// rc: this node's block of the R-cache ([32 static slots][128], R = c[t] + Wrf[t] g(d) of the static
+// edge) or nullptr.  Groups whose 4 edges are all static skip the RBF mat-vec and stream R instead.
 __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane, const float4 pi,
                                              const float* __restrict__ pj_plane, const MlpSmem W,
-                                             const float4 gamma, const float4 beta, float4 (&a)[4]) {
+                                             const float4 gamma, const float4 beta, float4 (&a)[4],
+                                             const float* __restrict__ rc) {
   int t[4];
+  const bool cached = (rc != nullptr) && (M.slot[e0 + 3] >= 0);   // static edges come first: slot[e0+3]>=0 => all 4
+  if (cached) {
+#pragma unroll
+    for (int ee = 0; ee < 4; ++ee) {
+      const int j = M.j[e0 + ee];
+      const float4 pj = ldg4(pj_plane + (size_t)j * CBG_H + 4 * lane);
+      const float4 r = ldg4(rc + M.slot[e0 + ee] * CBG_H + 4 * lane);
+      a[ee] = make_float4(pi.x + pj.x + r.x, pi.y + pj.y + r.y, pi.z + pj.z + r.z, pi.w + pj.w + r.w);
+    }
+  } else {
 #pragma unroll
   for (int ee = 0; ee < 4; ++ee) {
     const int j = M.j[e0 + ee];
@@ -129,6 +168,7 @@ __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane
       for (int ee = 0; ee < 4; ++ee)
         fma4(a[ee], ld4(W.wrf + (t[ee] * CBG_NRBF + m) * CBG_H + 4 * lane), gs[ee]);
     }
+  }
   }
   // LayerNorm(128, eps=1e-5) over the feature dim (4 per lane x 32 lanes), two-pass
   float s[4];
@@ -257,6 +297,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
 
   for (int i = blockIdx.x * kWarps + warp; i < p.n_nodes; i += gridDim.x * kWarps) {
     const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    const float* rc = p.rc_k ? p.rc_k + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
+    prefetch_rc(p.rc_k, i + gridDim.x * kWarps, p.n_nodes, lane);
     float U[4][CBG_HEADS];
     build_u(p.q + (size_t)i * CBG_H, s_w1, lane, U);
     const float4 pi = ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane);
@@ -264,7 +306,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float4 a[4];
-      first_layer4(M, 4 * g, lane, pi, p.pj_k, W, gamma, beta, a);
+      first_layer4(M, 4 * g, lane, pi, p.pj_k, W, gamma, beta, a, rc);
       float r0, r1;
       contract_heads(a, U, lane, r0, r1);
 #pragma unroll
@@ -310,6 +352,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
 
   for (int i = blockIdx.x * kWarps + warp; i < p.n_nodes; i += gridDim.x * kWarps) {
     edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    const float* rc = p.rc_v ? p.rc_v + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
+    prefetch_rc(p.rc_v, i + gridDim.x * kWarps, p.n_nodes, lane);
     {
       const float* wsrc = p.w + (size_t)i * (CBG_KMAX * CBG_HEADS);
 #pragma unroll
@@ -323,7 +367,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float4 a[4];
-      first_layer4(M, 4 * g, lane, pi, p.pj_v, W, gamma, beta, a);
+      first_layer4(M, 4 * g, lane, pi, p.pj_v, W, gamma, beta, a, rc);
 #pragma unroll
       for (int ee = 0; ee < 4; ++ee) {
         const float* wr = wbuf + (4 * g + ee) * 16;
@@ -432,13 +476,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) h2x_kernel(EdgeArgs p) {
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float4 a[4];
-      first_layer4(M, 4 * g, lane, pik, p.pj_k, WK, kga, kbe, a);
+      first_layer4(M, 4 * g, lane, pik, p.pj_k, WK, kga, kbe, a, nullptr);
       float r0, r1;
       contract_heads(a, U, lane, r0, r1);
       // dynamic g: keep the register arrays statically indexed
 #pragma unroll
       for (int gg = 0; gg < 8; ++gg) if (gg == g) { lg[gg][0] = r0; lg[gg][1] = r1; }
-      first_layer4(M, 4 * g, lane, piv, p.pj_v, WV, vga, vbe, a);
+      first_layer4(M, 4 * g, lane, piv, p.pj_v, WV, vga, vbe, a, nullptr);
       float part[64];
 #pragma unroll
       for (int hp = 0; hp < CBG_HEADS; ++hp) {
@@ -465,6 +509,63 @@ __global__ void __launch_bounds__(kWarps * 32, 1) h2x_kernel(EdgeArgs p) {
       }
     ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
     if (lane == 0) st4(p.dx + 4 * (size_t)n, make_float4(ax * (1.f / 16.f), ay * (1.f / 16.f), az * (1.f / 16.f), 0.f));
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// R-cache build (once per batch): R[i][s][:] = c[t] + Wrf[t] g(|x_i - x_j|) for the s-th entry j of
+// node i's static-only neighbour list.  blockIdx.y selects (layer, k|v MLP).
+constexpr int kRcFloats = 4 * 20 * 128 + 4 * 128;   // Wrf | c (contiguous in the blob)
+constexpr int kRcSmem = (kRcFloats + 32) * 4 + 8 * (20 * 32 + 32) * 4;
+
+__global__ void __launch_bounds__(256) rcache_kernel(const float* __restrict__ layers, long long layer_stride,
+                                                     const float4* __restrict__ x4, const int* __restrict__ snbr,
+                                                     int n_nodes, float* __restrict__ rcache) {
+  extern __shared__ __align__(16) float smem[];
+  const int which = blockIdx.y & 1, layer = blockIdx.y >> 1;
+  const float* L = layers + (size_t)layer * layer_stride;
+  const float* wsrc = L + (which ? kOffX2hV : kOffX2hK);
+  const float* rbf_src = L + (which ? kOffX2hVRbf : kOffX2hKRbf);
+  float* s_wrf = smem;
+  float* s_c = smem + 4 * 20 * 128;
+  float* s_rbf = smem + kRcFloats;
+  block_copy_f4(smem, wsrc, kRcFloats);
+  if (threadIdx.x < 32) s_rbf[threadIdx.x] = rbf_src[threadIdx.x];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* g = smem + kRcFloats + 32 + warp * (20 * 32 + 32);   // g[m][s]
+  int* ts = reinterpret_cast<int*>(g + 20 * 32);
+  float* out_base = rcache + (size_t)blockIdx.y * n_nodes * (CBG_KMAX * CBG_H);
+  for (int i = blockIdx.x * 8 + warp; i < n_nodes; i += gridDim.x * 8) {
+    const float4 xi = x4[i];
+    if (node_flags(xi) & 2) continue;                   // moving centre: no static edges
+    const int jn = snbr[(size_t)i * CBG_KMAX + lane];
+    const int j = jn >= 0 ? jn : i;
+    const float4 xj = x4[j];
+    const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+    const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+    const float coeff = s_rbf[20];
+#pragma unroll
+    for (int m = 0; m < CBG_NRBF; ++m) { const float u = d - s_rbf[m]; g[m * 32 + lane] = expf(coeff * u * u); }
+    ts[lane] = ((node_flags(xj) & 1) ? 0 : 2) + ((node_flags(xi) & 1) ? 0 : 1);
+    __syncwarp();
+    float* out = out_base + (size_t)i * (CBG_KMAX * CBG_H);
+    for (int s0 = 0; s0 < 32; s0 += 4) {
+      float4 a[4];
+#pragma unroll
+      for (int ee = 0; ee < 4; ++ee) a[ee] = ld4(s_c + ts[s0 + ee] * CBG_H + 4 * lane);
+#pragma unroll 4
+      for (int m = 0; m < CBG_NRBF; ++m) {
+        const float4 gv = ld4(g + m * 32 + s0);
+        const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int ee = 0; ee < 4; ++ee)
+          fma4(a[ee], ld4(s_wrf + (ts[s0 + ee] * CBG_NRBF + m) * CBG_H + 4 * lane), gs[ee]);
+      }
+#pragma unroll
+      for (int ee = 0; ee < 4; ++ee) st4(out + (s0 + ee) * CBG_H + 4 * lane, a[ee]);
+    }
     __syncwarp();
   }
 }
@@ -521,6 +622,22 @@ int cbg_edge_init(void) {
   if (int rc = set_attrs<12>()) return rc;
   if (int rc = set_attrs<16>()) return rc;
   done = true;
+  return 0;
+}
+
+int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, const int* snbr, int n_nodes,
+                      float* rcache, cudaStream_t st) {
+  if (n_nodes <= 0 || num_layers <= 0) return 0;
+  if (int rc = cbg_edge_init()) return rc;
+  static bool attr = false;
+  if (!attr) {
+    CBG_CUDA_OK(cudaFuncSetAttribute(rcache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRcSmem));
+    attr = true;
+  }
+  dim3 grid((unsigned)((n_nodes + 7) / 8 < 4 * g_num_sms ? (n_nodes + 7) / 8 : 4 * g_num_sms), 2 * num_layers);
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
+  rcache_kernel<<<grid, 256, kRcSmem, st>>>(layers, cbg_layout::kLayerFloats, x4, snbr, n_nodes, rcache);
+  CBG_LAUNCHED(CBG_K_MISC, st);
   return 0;
 }
 

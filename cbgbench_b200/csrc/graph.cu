@@ -43,7 +43,7 @@ __device__ __forceinline__ u64 bitonic_merge32(u64 v, int lane) {
 // bit-identical to the oracle (oracle/graph_ops.py).
 __global__ void __launch_bounds__(256) knn_kernel(const float4* __restrict__ x4,
                                                   const int* __restrict__ graph_ptr, int k, int mode,
-                                                  float r2max, int* __restrict__ nbr) {
+                                                  float r2max, int static_only, int* __restrict__ nbr) {
   extern __shared__ float4 xs[];
   const int g = blockIdx.y;
   const int s = graph_ptr[g];
@@ -57,10 +57,14 @@ __global__ void __launch_bounds__(256) knn_kernel(const float4* __restrict__ x4,
   for (int c = c0 + warp; c < c1; c += 8) {
     const float4 xc = xs[c];
     u64 best = kInfKey;
+    if (static_only && (node_flags(xc) & 2)) {          // moving centre: no static edges
+      nbr[(size_t)(s + c) * CBG_KMAX + lane] = -1;
+      continue;
+    }
     for (int base = 0; base < n; base += 32) {
       const int j = base + lane;
       u64 key = kInfKey;
-      if (j < n && j != c) {
+      if (j < n && j != c && !(static_only && (node_flags(xs[j]) & 2))) {
         const float4 xj = xs[j];
         const float dx = xc.x - xj.x, dy = xc.y - xj.y, dz = xc.z - xj.z;
         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -144,7 +148,7 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
 }  // namespace
 
 int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max_graph_nodes, int mode,
-                   int k, float r_max, int* nbr, cudaStream_t st) {
+                   int k, float r_max, int static_only, int* nbr, cudaStream_t st) {
   if (n_graphs <= 0) return 0;
   if (k < 1 || k > CBG_KMAX) { cbg_set_error("k=%d outside [1,%d]", k, CBG_KMAX); return 1; }
   const size_t smem = (size_t)max_graph_nodes * sizeof(float4);
@@ -160,7 +164,7 @@ int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max
   }
   dim3 grid((max_graph_nodes + 63) / 64, n_graphs);
   CBG_PROF_BEGIN(CBG_K_KNN, st);
-  knn_kernel<<<grid, 256, smem, st>>>(x4, graph_ptr, k, mode, r_max * r_max, nbr);
+  knn_kernel<<<grid, 256, smem, st>>>(x4, graph_ptr, k, mode, r_max * r_max, static_only, nbr);
   CBG_LAUNCHED(CBG_K_KNN, st);
   return 0;
 }

@@ -13,6 +13,7 @@ Random numbers are drawn with torch on the model device in the reference's order
 categorical.py:27), or injected for parity tests.
 """
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -100,7 +101,11 @@ class TargetDiffB200(nn.Module):
         self.context_embedder = PLContextEmbedderB200(cfg.embedder)
         self.denoiser = get_e3_gnn(cfg.encoder, num_classes=self.num_classes)
         self._ws = _Workspace()
+        self._rc = _Workspace()
         self.last_launches = 0
+        # R-cache: step-invariant first-Linear terms of edges between non-generated atoms are computed
+        # once per batch and streamed from HBM (2*L*N*16 KB).  CBG_RCACHE=0 / use_rcache=False turns it off.
+        self.use_rcache = os.environ.get('CBG_RCACHE', '1') != '0'
 
     def forward(self, batch):
         raise NotImplementedError('TargetDiffB200 is a forward-only sampling build: the training / '
@@ -158,13 +163,18 @@ class TargetDiffB200(nn.Module):
         ws_bytes = L.cbg_workspace_bytes(N, n_gen)
         ws_ptr, ws_have = self._ws.get(ws_bytes, dev)
         den = self.denoiser
+        rc_ptr, rc_bytes = None, 0
+        if self.use_rcache:
+            rc_bytes = L.cbg_rcache_bytes(N, den.num_layers)
+            rc_ptr, rc_bytes = self._rc.get(rc_bytes, dev)
         plan = _lib.SamplePlan(
             blob=blob.data_ptr(), num_layers=den.num_layers, num_classes=self.num_classes,
             emb_wt=emb_wt.data_ptr(), h_lig_bias=h_lig_bias.data_ptr(), h_static=h_static.data_ptr(),
             graph_ptr=gptr.data_ptr(), n_graphs=B, max_graph_nodes=max_n, n_nodes=N,
             lig_node=lig_node.data_ptr(), n_lig=n_lig, gen_lig=gen_lig8.data_ptr(),
             gen_node=gen_node.data_ptr() if n_gen else None, n_gen=n_gen,
-            mode=den.mode_id, k=den.cut_off, r_max=den.r_max, workspace=ws_ptr, workspace_bytes=ws_have)
+            mode=den.mode_id, k=den.cut_off, r_max=den.r_max, workspace=ws_ptr, workspace_bytes=ws_have,
+            rcache=rc_ptr, rcache_bytes=rc_bytes)
         with torch.cuda.device(dev):
             _lib.check(L.cbg_sample_begin_f32(C.byref(plan), x_nodes.data_ptr(), lig_nodes.data_ptr(),
                                               gen_nodes_flag.data_ptr(), _lib.stream_ptr(dev)))

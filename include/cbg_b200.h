@@ -61,6 +61,9 @@ const char* cbg_blob_field_name(int32_t section, int32_t idx);
 int64_t cbg_blob_field_offset(int32_t section, int32_t idx);
 int64_t cbg_blob_field_size(int32_t section, int32_t idx);
 
+/* bytes of the optional R-cache of a sampling plan: 2 * num_layers * n_nodes * 32 * 128 floats */
+int64_t cbg_rcache_bytes(int64_t n_nodes, int32_t num_layers);
+
 /* scratch bytes needed by the calls below for n_nodes nodes of which n_gen carry gen_flag */
 int64_t cbg_workspace_bytes(int64_t n_nodes, int64_t n_gen);
 
@@ -146,6 +149,10 @@ typedef struct cbg_sample_plan {
   float r_max;
   void* workspace;
   size_t workspace_bytes;
+  float* rcache;                /* optional (NULL = off): cbg_rcache_bytes() of scratch for the step-invariant
+                                   first-Linear terms of edges between non-generated atoms;
+                                   filled by cbg_sample_begin_f32, streamed by the fused X2H kernels */
+  size_t rcache_bytes;
 } cbg_sample_plan;
 
 typedef struct cbg_step_coef {  /* scheduler table entries of the current step (host scalars) */
