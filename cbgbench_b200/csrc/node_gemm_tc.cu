@@ -10,8 +10,8 @@
 // One CTA = one 128-row tile.  A (rows of h) is converted once per CTA into hi/lo tf32 tiles in
 // shared memory in the UMMA canonical K-major SWIZZLE_NONE layout (8x16B core matrices);
 // B (the weight plane) is pre-split and pre-laid-out on the host (packer) so a plain 1-D bulk
-// async copy (cp.async.bulk + mbarrier complete_tx) stages each 32 KB K-chunk; a 2-stage ring
-// overlaps the copy of chunk i+1 with the MMAs of chunk i.  One thread issues copies and MMAs,
+// async copy (cp.async.bulk + mbarrier complete_tx) stages each 16 KB K-chunk; a 4-stage ring
+// keeps three chunk copies in flight behind the MMAs (the kernel is bound by L2->SM weight traffic).  One thread issues copies and MMAs,
 // tcgen05.commit signals the mbarriers, all 8 warps drain the 128x128 fp32 accumulator from TMEM
 // (tcgen05.ld 32x32b) for the epilogue (+bias -> global, or LayerNorm+ReLU -> A tiles for the
 // second Linear of the q MLP).
@@ -20,16 +20,17 @@
 namespace {
 
 constexpr int TM = 128;                        // rows per CTA (UMMA M)
-constexpr int KC = 32;                         // K elements per weight chunk
-constexpr int NKC = CBG_H / KC;                // 4 chunks per plane
+constexpr int KC = 16;                         // K elements per weight chunk
+constexpr int NKC = CBG_H / KC;                // 8 chunks per plane
+constexpr int NSTAGE = 4;                      // weight-chunk ring depth (copies in flight hide L2 latency)
 constexpr uint32_t A_TILE_BYTES = TM * CBG_H * 4;          // 64 KB per (hi | lo)
-constexpr uint32_t B_CHUNK_BYTES = 128 * KC * 4;           // 16 KB per (hi | lo)
+constexpr uint32_t B_CHUNK_BYTES = 128 * KC * 4;           // 8 KB per (hi | lo)
 constexpr uint32_t B_STAGE_BYTES = 2 * B_CHUNK_BYTES;      // hi + lo, contiguous in the blob
 constexpr uint32_t SMEM_A_HI = 0;
 constexpr uint32_t SMEM_A_LO = A_TILE_BYTES;
 constexpr uint32_t SMEM_B0 = 2 * A_TILE_BYTES;
-constexpr uint32_t SMEM_BAR = SMEM_B0 + 2 * B_STAGE_BYTES;  // 5 mbarriers + tmem slot
-constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 64;
+constexpr uint32_t SMEM_BAR = SMEM_B0 + NSTAGE * B_STAGE_BYTES;  // 2*NSTAGE+1 mbarriers + tmem slot
+constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 128;
 constexpr uint32_t A_SBO = (CBG_H / 4) * 128;   // byte stride between 8-row groups of an A tile
 constexpr uint32_t B_SBO = (KC / 4) * 128;      // same for a B chunk
 constexpr uint32_t LBO = 128;                   // byte stride between core matrices along K
@@ -119,9 +120,10 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TM;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar_full0 = sbase + SMEM_BAR, bar_full1 = bar_full0 + 8;
-  const uint32_t bar_empty0 = bar_full0 + 16, bar_empty1 = bar_full0 + 24, bar_acc = bar_full0 + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 40);
+  const uint32_t bar_full = sbase + SMEM_BAR;                 // [NSTAGE]
+  const uint32_t bar_empty = bar_full + 8 * NSTAGE;           // [NSTAGE]
+  const uint32_t bar_acc = bar_empty + 8 * NSTAGE;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SMEM_BAR + 8 * (2 * NSTAGE + 1));
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -129,21 +131,25 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 32) {
-    mbar_init(bar_full0, 1); mbar_init(bar_full1, 1);
-    mbar_init(bar_empty0, 1); mbar_init(bar_empty1, 1);
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // A tile: rows of h -> (hi, lo) tf32 tiles; lanes <-> rows keeps the 16 B shared stores conflict free
-  for (int idx = tid; idx < TM * 32; idx += 256) {
-    const int r = idx & (TM - 1), k4 = idx >> 7;
+  {
+    const int r = tid & (TM - 1);
     const int row = row0 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < p.n_rows) {
-      const int src = p.row_idx ? p.row_idx[row] : row;
-      v = ldg4(p.a + (size_t)src * CBG_H + 4 * k4);
+    const bool live = row < p.n_rows;
+    const float* arow = p.a + (size_t)(live ? (p.row_idx ? p.row_idx[row] : row) : 0) * CBG_H;
+#pragma unroll
+    for (int it = 0; it < 16; it += 8) {          // thread handles k4 = (tid>>7) + 2*j, j < 16
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = live ? ldg4(arow + 4 * ((tid >> 7) + 2 * (it + j))) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) store_split(smem, r, (tid >> 7) + 2 * (it + j), v[j]);
     }
-    store_split(smem, r, k4, v);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -160,10 +166,9 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
     return p.tc_planes + (size_t)plane * (NKC * 2 * 128 * KC) + (size_t)c * (2 * 128 * KC);
   };
   if (tid == 0) {
-    for (int i = 0; i < 2 && i < total_chunks; ++i) {
-      const uint32_t bf = i ? bar_full1 : bar_full0;
-      mbar_expect_tx(bf, B_STAGE_BYTES);
-      bulk_g2s(sbase + SMEM_B0 + i * B_STAGE_BYTES, chunk_src(i), B_STAGE_BYTES, bf);
+    for (int i = 0; i < NSTAGE && i < total_chunks; ++i) {
+      mbar_expect_tx(bar_full + 8 * i, B_STAGE_BYTES);
+      bulk_g2s(sbase + SMEM_B0 + i * B_STAGE_BYTES, chunk_src(i), B_STAGE_BYTES, bar_full + 8 * i);
     }
   }
 
@@ -177,9 +182,8 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
   for (int g = 0; g < n_gemm; ++g) {
     if (tid == 0) {
       for (int c = 0; c < NKC; ++c) {
-        const int i = g * NKC + c, s = i & 1;
-        const uint32_t bf = s ? bar_full1 : bar_full0, be = s ? bar_empty1 : bar_empty0;
-        mbar_wait(bf, (uint32_t)((i >> 1) & 1));
+        const int i = g * NKC + c, s = i % NSTAGE;
+        mbar_wait(bar_full + 8 * s, (uint32_t)((i / NSTAGE) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t b_hi = sbase + SMEM_B0 + s * B_STAGE_BYTES, b_lo = b_hi + B_CHUNK_BYTES;
 #pragma unroll
@@ -195,13 +199,16 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
           umma_tf32(tmem, a_hi, d_blo, 1u);
           umma_tf32(tmem, a_hi, d_bhi, 1u);
         }
-        umma_commit(be);                            // stage reusable when these MMAs retire
+        umma_commit(bar_empty + 8 * s);             // stage reusable when these MMAs retire
         if (c == NKC - 1) umma_commit(bar_acc);     // accumulator of this plane complete
-        const int nxt = i + 2;
-        if (nxt < total_chunks) {
-          mbar_wait(be, (uint32_t)((i >> 1) & 1));
-          mbar_expect_tx(bf, B_STAGE_BYTES);
-          bulk_g2s(sbase + SMEM_B0 + s * B_STAGE_BYTES, chunk_src(nxt), B_STAGE_BYTES, bf);
+        // refill the stage of the PREVIOUS chunk (its MMAs retire before the ones just issued start),
+        // so the issuing thread never waits on the chunk it just queued
+        const int prev = i - 1, nxt = prev + NSTAGE;
+        if (prev >= 0 && nxt < total_chunks) {
+          const int ps = prev % NSTAGE;
+          mbar_wait(bar_empty + 8 * ps, (uint32_t)((prev / NSTAGE) & 1));
+          mbar_expect_tx(bar_full + 8 * ps, B_STAGE_BYTES);
+          bulk_g2s(sbase + SMEM_B0 + ps * B_STAGE_BYTES, chunk_src(nxt), B_STAGE_BYTES, bar_full + 8 * ps);
         }
       }
     }

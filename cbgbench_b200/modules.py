@@ -109,17 +109,18 @@ def _round_tf32(x):
 
 def tc_weight_plane(w):
     """[128 n][128 k] weight (natural nn.Linear layout) -> the tcgen05 operand image:
-    4 K-chunks x (hi | lo) x [128 n][32 k] tf32, each in the UMMA canonical K-major / no-swizzle layout
-    (8-row x 16-byte core matrices, 128 B apart along K, 1024 B between 8-row groups)."""
+    8 K-chunks x (hi | lo) x [128 n][16 k] tf32, each in the UMMA canonical K-major / no-swizzle layout
+    (8-row x 16-byte core matrices, 128 B apart along K, 512 B between 8-row groups)."""
     import numpy as np
     w = w.detach().cpu().to(torch.float32).numpy()
     assert w.shape == (128, 128)
     hi = _round_tf32(w)
     lo = _round_tf32(w - hi)
-    out = np.zeros((4, 2, 16, 8, 8, 4), dtype=np.float32)      # [chunk][hi/lo][n/8][k_local/4][n%8][k%4]
-    for c in range(4):
+    kc = 16
+    out = np.zeros((128 // kc, 2, 16, kc // 4, 8, 4), dtype=np.float32)   # [chunk][hi/lo][n/8][k_local/4][n%8][k%4]
+    for c in range(128 // kc):
         for part, src in enumerate((hi, lo)):
-            blk = src[:, 32 * c: 32 * c + 32].reshape(16, 8, 8, 4)   # [n/8][n%8][kl/4][kl%4]
+            blk = src[:, kc * c: kc * c + kc].reshape(16, 8, kc // 4, 4)    # [n/8][n%8][kl/4][kl%4]
             out[c, part] = blk.transpose(0, 2, 1, 3)
     return torch.from_numpy(out.reshape(-1)).to(torch.float64)
 
