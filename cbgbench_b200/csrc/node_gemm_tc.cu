@@ -15,6 +15,7 @@
 // tcgen05.commit signals the mbarriers, all 8 warps drain the 128x128 fp32 accumulator from TMEM
 // (tcgen05.ld 32x32b) for the epilogue (+bias -> global, or LayerNorm+ReLU -> A tiles for the
 // second Linear of the q MLP).
+#include <stdlib.h>
 #include "cbg_kernels.cuh"
 
 namespace {
@@ -71,6 +72,26 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// each CTA of a cluster copies its 1/CL slice of the chunk into the same offset of EVERY CTA's smem
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -115,7 +136,20 @@ __device__ __forceinline__ void store_split(uint8_t* smem, int row, int k4, floa
   *reinterpret_cast<float4*>(smem + SMEM_A_LO + off) = lo;
 }
 
+// CL = CTAs per cluster sharing every weight chunk through multicast bulk copies (1 = no cluster).
+// The kernel is bound by L2->SM weight traffic (every CTA needs all 6 x 128 KB of weight images), so a
+// cluster of CL row tiles cuts that traffic by CL.
+// weight chunk i lives at: plane(i / NKC) -> tc plane index, chunk (i % NKC)
+__device__ __forceinline__ const float* chunk_src_ptr(const NodeGemmArgs& p, int i) {
+  const int g = i / NKC, c = i % NKC;
+  const int plane = (g < p.n_planes) ? (p.tc_first_plane + g) : 5;       // plane 5 = q second Linear
+  return p.tc_planes + (size_t)plane * (NKC * 2 * 128 * KC) + (size_t)c * (2 * 128 * KC);
+}
+
+template <int CL>
 __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  const uint32_t crank = (CL > 1) ? cluster_rank() : 0u;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TM;
@@ -131,7 +165,7 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 32) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, CL); }
     mbar_init(bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,22 +188,26 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // every CTA's barriers exist before any peer copy / commit targets them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  // stage the weight chunk `i` into ring slot `slot`: own slice only when clustered
+  auto load_chunk = [&](int i, int slot) {
+    const uint32_t bf = bar_full + 8 * slot;
+    mbar_expect_tx(bf, B_STAGE_BYTES);                       // the whole chunk lands here (all slices)
+    if (CL > 1) {
+      constexpr uint32_t slice = B_STAGE_BYTES / CL;
+      bulk_g2s_mcast(sbase + SMEM_B0 + slot * B_STAGE_BYTES + crank * slice,
+                     reinterpret_cast<const char*>(chunk_src_ptr(p, i)) + crank * slice, slice, bf, kMask);
+    } else {
+      bulk_g2s(sbase + SMEM_B0 + slot * B_STAGE_BYTES, chunk_src_ptr(p, i), B_STAGE_BYTES, bf);
+    }
+  };
 
   const int n_gemm = p.n_planes + (p.has_q ? 1 : 0);      // + the second Linear of the q MLP
   const int total_chunks = n_gemm * NKC;
-  // weight chunk i lives at: plane(i / NKC) -> tc plane index, chunk (i % NKC)
-  auto chunk_src = [&](int i) -> const float* {
-    const int g = i / NKC, c = i % NKC;
-    const int plane = (g < p.n_planes) ? (p.tc_first_plane + g) : 5;       // plane 5 = q second Linear
-    return p.tc_planes + (size_t)plane * (NKC * 2 * 128 * KC) + (size_t)c * (2 * 128 * KC);
-  };
   if (tid == 0) {
-    for (int i = 0; i < NSTAGE && i < total_chunks; ++i) {
-      mbar_expect_tx(bar_full + 8 * i, B_STAGE_BYTES);
-      bulk_g2s(sbase + SMEM_B0 + i * B_STAGE_BYTES, chunk_src(i), B_STAGE_BYTES, bar_full + 8 * i);
-    }
+    for (int i = 0; i < NSTAGE && i < total_chunks; ++i) load_chunk(i, i);
   }
 
   // destination node ids for the epilogue: this thread's accumulator row
@@ -199,16 +237,16 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
           umma_tf32(tmem, a_hi, d_blo, 1u);
           umma_tf32(tmem, a_hi, d_bhi, 1u);
         }
-        umma_commit(bar_empty + 8 * s);             // stage reusable when these MMAs retire
+        if (CL > 1) umma_commit_mcast(bar_empty + 8 * s, kMask);   // every peer learns this CTA is done with the slot
+        else umma_commit(bar_empty + 8 * s);        // stage reusable when these MMAs retire
         if (c == NKC - 1) umma_commit(bar_acc);     // accumulator of this plane complete
         // refill the stage of the PREVIOUS chunk (its MMAs retire before the ones just issued start),
         // so the issuing thread never waits on the chunk it just queued
         const int prev = i - 1, nxt = prev + NSTAGE;
         if (prev >= 0 && nxt < total_chunks) {
           const int ps = prev % NSTAGE;
-          mbar_wait(bar_empty + 8 * ps, (uint32_t)((prev / NSTAGE) & 1));
-          mbar_expect_tx(bar_full + 8 * ps, B_STAGE_BYTES);
-          bulk_g2s(sbase + SMEM_B0 + ps * B_STAGE_BYTES, chunk_src(nxt), B_STAGE_BYTES, bar_full + 8 * ps);
+          mbar_wait(bar_empty + 8 * ps, (uint32_t)((prev / NSTAGE) & 1));   // all CL CTAs retired chunk prev
+          load_chunk(nxt, ps);
         }
       }
     }
@@ -269,9 +307,35 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
     __syncthreads();      // TMEM drained (and A rewritten for the q path) before the next plane's MMAs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
+  if (CL > 1) cluster_sync_all();      // no CTA may exit while peers can still write its smem / signal its barriers
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
   }
+}
+
+
+
+template <int CL>
+int launch_tc(const NodeGemmArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    attr_set = true;
+  }
+  const int tiles = (a.n_rows + TM - 1) / TM;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((tiles + CL - 1) / CL * CL));   // padded tiles run the protocol with zero rows
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = (CL > 1) ? 1 : 0;
+  CBG_PROF_BEGIN(CBG_K_NODE_GEMM, st);
+  CBG_CUDA_OK(cudaLaunchKernelEx(&cfg, node_gemm_tc_kernel<CL>, a));
+  CBG_LAUNCHED(CBG_K_NODE_GEMM, st);
+  return 0;
 }
 
 }  // namespace
@@ -279,13 +343,15 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
 int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st) {
   if (a.n_rows <= 0) return 0;
   if (!a.tc_planes) { cbg_set_error("tensor-core node GEMM needs the pre-split weight planes"); return 1; }
-  static bool attr_set = false;
-  if (!attr_set) {
-    CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-    attr_set = true;
+  static int cl = -1;
+  if (cl < 0) {
+    const char* e = getenv("CBG_GEMM_CLUSTER");
+    cl = e ? atoi(e) : 4;
+    if (cl != 1 && cl != 2 && cl != 4) cl = 4;
   }
-  CBG_PROF_BEGIN(CBG_K_NODE_GEMM, st);
-  node_gemm_tc_kernel<<<(a.n_rows + TM - 1) / TM, 256, SMEM_TOTAL, st>>>(a);
-  CBG_LAUNCHED(CBG_K_NODE_GEMM, st);
-  return 0;
+  switch (cl) {
+    case 1: return launch_tc<1>(a, st);
+    case 2: return launch_tc<2>(a, st);
+    default: return launch_tc<4>(a, st);
+  }
 }
