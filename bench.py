@@ -154,12 +154,19 @@ def cpu_reference_steps(workload, n_graphs, steps, warmup, threads):
     return sum(times) / len(times)
 
 
-def pick_cpu_sample(workload, threads, budget_s):
-    """Largest graph count (<= the workload's) whose `steps` fit the time budget; probes with 1 graph."""
+def pick_cpu_sample(workload, budget_s):
+    """Choose the torch thread count that runs the reference path fastest on this host (all cores is often
+    slower than a moderate count for these op sizes) and the largest graph count (<= the workload's) whose
+    step fits the time budget.  Returns (n_graphs, threads, tried)."""
     B = WORKLOADS[workload][0]
-    t1 = cpu_reference_steps(workload, 1, 1, 1, threads)
-    n = max(1, min(B, int(budget_s / max(t1, 1e-3))))
-    return n, t1
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (ncpu, 32, 16, 8) if c <= ncpu}, reverse=True)
+    tried = {}
+    for c in cands:
+        tried[c] = cpu_reference_steps(workload, 1, 1, 1, c)
+    threads = min(tried, key=tried.get)
+    n = max(1, min(B, int(budget_s / max(tried[threads], 1e-3))))
+    return n, threads, {k: round(v, 3) for k, v in tried.items()}
 
 
 def run_reference(args):
@@ -168,14 +175,14 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
     B, n_prot, n_lig, _, enc, desc = WORKLOADS[args.workload]
     total_steps = args.steps + args.warmup
-    n_graphs, _ = pick_cpu_sample(args.workload, threads, budget_s=max(0.5, 150.0 / max(total_steps, 1)))
+    n_graphs, threads, tried = pick_cpu_sample(args.workload, budget_s=max(0.5, 120.0 / max(total_steps, 1)))
     sec = cpu_reference_steps(args.workload, n_graphs, args.steps, args.warmup, threads)
     value = n_graphs / (T_STEPS * sec)
     sample = (f'{n_graphs} of {B} pockets ({n_prot}+{n_lig} atoms each), {args.steps} denoise steps after {args.warmup} '
-              f'warm-up, ligands/s = pockets / (1000 x s/step)')
+              f'warm-up, ligands/s = pockets / (1000 x s/step); {threads} torch threads of {os.cpu_count()} host cores '
+              f'(fastest of s/step for 1 pocket: {tried})')
     line = {
         'impl': 'reference', 'metric': 'ligands/sec sampled (1000-step denoise, batch 64)', 'value': value,
         'unit': 'ligands/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
@@ -269,21 +276,30 @@ def run_b200(args):
                    for k, v in prof.items() if v[1]}
         dom = max(('x2h_k', 'x2h_v'), key=lambda k: prof[k][0])
         dom_ms = prof[dom][0] / prof[dom][1]
-        # ALGORITHMIC bytes per launch of the fused X2H kernels: per node
+        # ALGORITHMIC bytes per launch of the fused X2H kernels, per node:
         #   x2h_k: Pj_k + Pi_k + q rows (3 x 512 B) + nbr (128) + e_w (128) + x (16) read, w (2048) written
         #   x2h_v: Pj_v + Pi_v (2 x 512) + nbr + e_w + x (272) + w (2048) + h (512) read, h (512) written
+        #   + the node's R-cache block (32 slots x 512 B) streamed for static (non-generated) nodes
+        n_static = N - state['plan'].n_gen
+        rc_bytes = 32 * 512 * n_static if model.use_rcache else 0
         per_node = {'x2h_k': 3 * 512 + 272 + 2048, 'x2h_v': 2 * 512 + 272 + 2048 + 1024}[dom]
-        alg_bytes = per_node * N
+        alg_bytes = per_node * N + rc_bytes
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        # fp32 work of the same launch: FMAs per node (first Linear via RBF, LN, folded second Linear)
-        flops_node = {'x2h_k': 2 * (32 * 20 * 128 + 128 * 128 + 32 * 128 * 16),
-                      'x2h_v': 2 * (32 * 20 * 128 + 32 * 128 * 16 + 128 * 128)}[dom]
+        # useful fp32 work of the same launch (query-folded / aggregated second Linears; the RBF mat-vec only
+        # for the edges that are not served from the R-cache is NOT counted: lower bound of useful FLOPs)
+        flops_node = {'x2h_k': 2 * (128 * 128 + 32 * 128 * 16), 'x2h_v': 2 * (32 * 128 * 16 + 128 * 128)}[dom]
         sm_max = (clocks.summary()['sm_max_mhz'] or peaks.get('sm_max_mhz') or 1965.0)
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')      # dram bytes/launch from the last ncu --set full capture
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = (json.load(f).get(dom) or {}).get('dram_bytes_per_launch')
         roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                     'frac': achieved / peaks['hbm_gbs'], 'peak_source': f'{peak_kind} copy bandwidth (MEASURED_PEAKS.json)',
-                    'traffic': None, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': dom_ms,
-                    'note': 'k/v edge tensors are never materialised, so the kernel is fp32-FMA bound, not HBM bound',
+                    'traffic': traffic, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': dom_ms,
+                    'note': 'per-edge k/v tensors are never materialised; the kernel streams node planes + the R-cache '
+                            'and is co-limited by fp32 issue rate (see fp32)',
                     'fp32': {'achieved_tflops': flops_node * N / (dom_ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
                              'frac': flops_node * N / (dom_ms * 1e-3) / 1e12 / fp32_peak,
                              'peak_source': 'nominal 148 SM x 128 FMA x 2 x max SM clock'}}
@@ -318,12 +334,12 @@ def run_b200(args):
     # ---- CPU baseline beside it (rank 0, N = 1) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        n_graphs, _ = pick_cpu_sample(args.workload, threads, budget_s=6.0)
+        n_graphs, threads, tried = pick_cpu_sample(args.workload, budget_s=6.0)
         sec = cpu_reference_steps(args.workload, n_graphs, 2, 1, threads)
         cpu = {'value': n_graphs / (T_STEPS * sec), 'unit': 'ligands/s', 'cores': threads, 'kind': 'port',
                'sample': f'{n_graphs} of {B} pockets ({n_prot}+{n_lig} atoms), 2 denoise steps after 1 warm-up, '
-                         f'oracle port (torch CPU fp32), extrapolated: pockets / (1000 x s/step)'}
+                         f'oracle port (torch CPU fp32), extrapolated: pockets / (1000 x s/step); {threads} torch threads '
+                         f'of {os.cpu_count()} host cores (fastest of {tried} s/step for 1 pocket)'}
 
     if rank == 0:
         line = {

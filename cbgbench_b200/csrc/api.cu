@@ -393,7 +393,7 @@ int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_float
 
 int32_t cbg_node_proj_f32(const float* blob_layer, int32_t sublayer, int32_t impl, const float* h,
                           const int32_t* row_idx, int32_t n_rows, int64_t n_nodes, float* planes, void* stream) {
-  if (sublayer < 0 || sublayer > 1 || impl < 0 || impl > 1) { cbg_set_error("bad sublayer/impl"); return 1; }
+  if (sublayer < 0 || sublayer > 1 || (impl != 0 && impl != 1 && impl != 12 && impl != 14)) { cbg_set_error("bad sublayer/impl"); return 1; }
   const float* L = blob_layer;
   NodeGemmArgs g{};
   g.a = h; g.row_idx = row_idx; g.n_rows = n_rows;
@@ -408,7 +408,8 @@ int32_t cbg_node_proj_f32(const float* blob_layer, int32_t sublayer, int32_t imp
   g.out_q = planes + (size_t)4 * n_nodes * CBG_H;
   g.tc_planes = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_NODE_TC : CBG_LF_X2H_NODE_TC);
   g.tc_first_plane = 0;
-  return impl ? cbg_launch_node_gemm_tc(g, (cudaStream_t)stream) : cbg_launch_node_gemm(g, (cudaStream_t)stream);
+  if (impl == 0) return cbg_launch_node_gemm(g, (cudaStream_t)stream);
+  return cbg_launch_node_gemm_tc(g, (cudaStream_t)stream, impl == 12 ? 2 : (impl == 14 ? 4 : 1));
 }
 
 int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, const uint8_t* lig_flag,

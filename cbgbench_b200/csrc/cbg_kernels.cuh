@@ -33,7 +33,8 @@ struct NodeGemmArgs {
   int tc_first_plane;      // index of this launch's first plane (q second Linear is always plane 5)
 };
 int cbg_launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st);      // fp32 SIMT
-int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st);   // tcgen05 3xTF32
+// tcgen05 3xTF32; cluster = 1/2/4 CTAs sharing weight chunks by multicast, 0 = default (env CBG_GEMM_CLUSTER)
+int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st, int cluster = 0);
 
 // edge.cu
 struct EdgeArgs {

@@ -10,8 +10,8 @@
 // One CTA = one 128-row tile.  A (rows of h) is converted once per CTA into hi/lo tf32 tiles in
 // shared memory in the UMMA canonical K-major SWIZZLE_NONE layout (8x16B core matrices);
 // B (the weight plane) is pre-split and pre-laid-out on the host (packer) so a plain 1-D bulk
-// async copy (cp.async.bulk + mbarrier complete_tx) stages each 16 KB K-chunk; a 4-stage ring
-// keeps three chunk copies in flight behind the MMAs (the kernel is bound by L2->SM weight traffic).  One thread issues copies and MMAs,
+// async copy (cp.async.bulk + mbarrier complete_tx) stages each 32 KB K-chunk into a 3-stage ring
+// (optionally multicast across a thread-block cluster of row tiles).  One thread issues copies and MMAs,
 // tcgen05.commit signals the mbarriers, all 8 warps drain the 128x128 fp32 accumulator from TMEM
 // (tcgen05.ld 32x32b) for the epilogue (+bias -> global, or LayerNorm+ReLU -> A tiles for the
 // second Linear of the q MLP).
@@ -21,17 +21,16 @@
 namespace {
 
 constexpr int TM = 128;                        // rows per CTA (UMMA M)
-constexpr int KC = 16;                         // K elements per weight chunk
-constexpr int NKC = CBG_H / KC;                // 8 chunks per plane
-constexpr int NSTAGE = 4;                      // weight-chunk ring depth (copies in flight hide L2 latency)
+constexpr int KC = 32;                         // K elements per weight chunk
+constexpr int NKC = CBG_H / KC;                // 4 chunks per plane
+constexpr int MAX_STAGE = 3;                   // weight-chunk ring depth is a template parameter (2 or 3)
 constexpr uint32_t A_TILE_BYTES = TM * CBG_H * 4;          // 64 KB per (hi | lo)
-constexpr uint32_t B_CHUNK_BYTES = 128 * KC * 4;           // 8 KB per (hi | lo)
+constexpr uint32_t B_CHUNK_BYTES = 128 * KC * 4;           // 16 KB per (hi | lo)
 constexpr uint32_t B_STAGE_BYTES = 2 * B_CHUNK_BYTES;      // hi + lo, contiguous in the blob
 constexpr uint32_t SMEM_A_HI = 0;
 constexpr uint32_t SMEM_A_LO = A_TILE_BYTES;
 constexpr uint32_t SMEM_B0 = 2 * A_TILE_BYTES;
-constexpr uint32_t SMEM_BAR = SMEM_B0 + NSTAGE * B_STAGE_BYTES;  // 2*NSTAGE+1 mbarriers + tmem slot
-constexpr uint32_t SMEM_TOTAL = SMEM_BAR + 128;
+constexpr uint32_t smem_total(int nstage) { return SMEM_B0 + nstage * B_STAGE_BYTES + 128; }  // + mbarriers, tmem slot
 constexpr uint32_t A_SBO = (CBG_H / 4) * 128;   // byte stride between 8-row groups of an A tile
 constexpr uint32_t B_SBO = (KC / 4) * 128;      // same for a B chunk
 constexpr uint32_t LBO = 128;                   // byte stride between core matrices along K
@@ -146,8 +145,9 @@ __device__ __forceinline__ const float* chunk_src_ptr(const NodeGemmArgs& p, int
   return p.tc_planes + (size_t)plane * (NKC * 2 * 128 * KC) + (size_t)c * (2 * 128 * KC);
 }
 
-template <int CL>
+template <int CL, int NSTAGE>
 __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
+  constexpr uint32_t SMEM_BAR = SMEM_B0 + NSTAGE * B_STAGE_BYTES;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   const uint32_t crank = (CL > 1) ? cluster_rank() : 0u;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -315,11 +315,12 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
 
 
 
-template <int CL>
+template <int CL, int NSTAGE>
 int launch_tc(const NodeGemmArgs& a, cudaStream_t st) {
+  constexpr uint32_t SMEM_TOTAL = smem_total(NSTAGE);
   static bool attr_set = false;
   if (!attr_set) {
-    CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_tc_kernel<CL, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
     attr_set = true;
   }
   const int tiles = (a.n_rows + TM - 1) / TM;
@@ -333,25 +334,35 @@ int launch_tc(const NodeGemmArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = (CL > 1) ? 1 : 0;
   CBG_PROF_BEGIN(CBG_K_NODE_GEMM, st);
-  CBG_CUDA_OK(cudaLaunchKernelEx(&cfg, node_gemm_tc_kernel<CL>, a));
+  CBG_CUDA_OK(cudaLaunchKernelEx(&cfg, node_gemm_tc_kernel<CL, NSTAGE>, a));
   CBG_LAUNCHED(CBG_K_NODE_GEMM, st);
   return 0;
 }
 
 }  // namespace
 
-int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st) {
+int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st, int cluster) {
   if (a.n_rows <= 0) return 0;
   if (!a.tc_planes) { cbg_set_error("tensor-core node GEMM needs the pre-split weight planes"); return 1; }
-  static int cl = -1;
-  if (cl < 0) {
+  static int cl_env = -1, stages = -1;
+  if (cl_env < 0) {
     const char* e = getenv("CBG_GEMM_CLUSTER");
-    cl = e ? atoi(e) : 4;
-    if (cl != 1 && cl != 2 && cl != 4) cl = 4;
+    cl_env = e ? atoi(e) : 1;
+    if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 1;
+    const char* s = getenv("CBG_GEMM_STAGES");
+    stages = (s && atoi(s) == 2) ? 2 : 3;
+  }
+  const int cl = (cluster == 1 || cluster == 2 || cluster == 4) ? cluster : cl_env;
+  if (stages == 2) {
+    switch (cl) {
+      case 2: return launch_tc<2, 2>(a, st);
+      case 4: return launch_tc<4, 2>(a, st);
+      default: return launch_tc<1, 2>(a, st);
+    }
   }
   switch (cl) {
-    case 1: return launch_tc<1>(a, st);
-    case 2: return launch_tc<2>(a, st);
-    default: return launch_tc<4>(a, st);
+    case 2: return launch_tc<2, 3>(a, st);
+    case 4: return launch_tc<4, 3>(a, st);
+    default: return launch_tc<1, 3>(a, st);
   }
 }

@@ -109,14 +109,14 @@ def _round_tf32(x):
 
 def tc_weight_plane(w):
     """[128 n][128 k] weight (natural nn.Linear layout) -> the tcgen05 operand image:
-    8 K-chunks x (hi | lo) x [128 n][16 k] tf32, each in the UMMA canonical K-major / no-swizzle layout
-    (8-row x 16-byte core matrices, 128 B apart along K, 512 B between 8-row groups)."""
+    4 K-chunks x (hi | lo) x [128 n][32 k] tf32, each in the UMMA canonical K-major / no-swizzle layout
+    (8-row x 16-byte core matrices, 128 B apart along K, 1024 B between 8-row groups)."""
     import numpy as np
     w = w.detach().cpu().to(torch.float32).numpy()
     assert w.shape == (128, 128)
     hi = _round_tf32(w)
     lo = _round_tf32(w - hi)
-    kc = 16
+    kc = 32
     out = np.zeros((128 // kc, 2, 16, kc // 4, 8, 4), dtype=np.float32)   # [chunk][hi/lo][n/8][k_local/4][n%8][k%4]
     for c in range(128 // kc):
         for part, src in enumerate((hi, lo)):
