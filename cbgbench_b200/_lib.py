@@ -21,7 +21,7 @@ class SamplePlan(C.Structure):
         ('gen_lig', C.c_void_p), ('gen_node', C.c_void_p), ('n_gen', C.c_int32),
         ('mode', C.c_int32), ('k', C.c_int32), ('r_max', C.c_float),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
-        ('rcache', C.c_void_p), ('rcache_bytes', C.c_size_t),
+        ('rcache', C.c_void_p), ('rcache_bytes', C.c_size_t), ('prune', C.c_int32),
     ]
 
 

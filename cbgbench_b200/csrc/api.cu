@@ -59,6 +59,9 @@ struct Workspace {
   float* w;
   int* nbr;
   int* snbr;                   // static-only neighbour lists (R-cache build)
+  int* depth;                  // receptive-field pruning: per-node depth, nodes ordered by depth, counts
+  int* order;
+  int* cnt;
   float* ew;
   float* dx;
   size_t bytes;
@@ -76,6 +79,9 @@ Workspace carve(void* base, long long n_nodes, long long n_gen) {
   ws.w = (float*)take((size_t)n_nodes * CBG_KMAX * CBG_HEADS * 4);
   ws.nbr = (int*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.snbr = (int*)take((size_t)n_nodes * CBG_KMAX * 4);
+  ws.depth = (int*)take((size_t)n_nodes * 4);
+  ws.order = (int*)take((size_t)n_nodes * 4);
+  ws.cnt = (int*)take(96 * 4);
   ws.ew = (float*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.dx = (float*)take((size_t)(n_gen > 0 ? n_gen : 1) * 16);
   ws.bytes = off;
@@ -129,20 +135,37 @@ int aux_ready() {
   return 1;
 }
 
+// receptive-field pruning of the sampling step (exact); CBG_PRUNE=0 turns it off
+bool prune_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("CBG_PRUNE");
+    on = (e && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return on != 0;
+}
+
 // graph build + gate + layers on an initialised workspace (x4, h valid)
 int run_core(const float* blob, int num_layers, const Workspace& ws, const int* graph_ptr, int n_graphs,
              int max_graph_nodes, long long n_nodes, const int* gen_idx, int n_gen, int mode, int k,
-             float r_max, const float* rcache, cudaStream_t st) {
+             float r_max, const float* rcache, const int* cls_idx, int n_cls, bool prune, cudaStream_t st) {
   if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
   if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, ws.nbr, st)) return rc;
   if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, ws.ew, st)) return rc;
   const float* layers = blob + cbg_layout::kGlobalFloats;
+  // Receptive-field pruning (only when the caller consumes nothing but the generated / classified rows):
+  // layer l updates h only for the nodes that can still reach such a row through the remaining layers.
+  prune = prune && num_layers > 0 && (n_gen > 0 || n_cls > 0);
+  if (prune) {
+    if (int rc = cbg_launch_depth(ws.nbr, graph_ptr, n_graphs, max_graph_nodes, n_nodes, gen_idx, n_gen, cls_idx, n_cls,
+                                  num_layers, ws.depth, ws.order, ws.cnt, st)) return rc;
+  }
   const bool overlap = (n_gen > 0) && aux_ready();
   cudaStream_t sx = overlap ? g_aux.s2 : st;       // stream of the H2X chain
   bool x_pending = false;                          // an apply_dx on sx has not been joined yet
   for (int l = 0; l < num_layers; ++l) {
     const float* L = layers + (size_t)l * cbg_layout::kLayerFloats;
-    // ---- X2H: node planes (all nodes), attention weights, aggregation (h updated in place)
+    // ---- X2H: node planes, attention weights, aggregation (h updated in place)
     NodeGemmArgs g{};
     g.a = ws.h; g.row_idx = nullptr; g.n_rows = (int)n_nodes;
     g.wt = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_WT);
@@ -155,12 +178,26 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     g.q_b1 = L + cbg_layout::layer_offset(CBG_LF_X2H_Q_B1);
     g.out_q = ws.plane[4];
     g.tc_planes = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_TC); g.tc_first_plane = 0;
-    if (int rc = launch_node_gemm(g, st)) return rc;          // reads h only: may overlap the previous H2X chain
+    if (!prune) {
+      if (int rc = launch_node_gemm(g, st)) return rc;          // reads h only: may overlap the previous H2X chain
+    } else {
+      // source planes Pj for every node a needed destination can gather (depth >= l-1), destination planes
+      // Pi / q only for the needed destinations (depth >= l); both lists are prefixes of ws.order
+      NodeGemmArgs gp = g;
+      gp.row_idx = ws.order; gp.n_rows_dev = ws.cnt + l; gp.n_planes = 2; gp.has_q = 0;
+      if (int rc = launch_node_gemm(gp, st)) return rc;
+      NodeGemmArgs gd = g;
+      gd.row_idx = ws.order; gd.n_rows_dev = ws.cnt + l + 1;
+      gd.wt = g.wt + 256; gd.bias = g.bias + 256; gd.n_planes = 3; gd.tc_first_plane = 2;
+      gd.out[0] = ws.plane[2]; gd.out[1] = ws.plane[3]; gd.out[2] = nullptr;
+      if (int rc = launch_node_gemm(gd, st)) return rc;
+    }
     if (overlap && x_pending) { CBG_CUDA_OK(cudaStreamWaitEvent(st, g_aux.ev_x, 0)); x_pending = false; }
     EdgeArgs e{};
     e.x4 = ws.x4; e.nbr = ws.nbr; e.ew = ws.ew;
     e.pj_k = ws.plane[0]; e.pj_v = ws.plane[1]; e.pi_k = ws.plane[2]; e.pi_v = ws.plane[3]; e.q = ws.plane[4];
     e.layer = L; e.w = ws.w; e.h = ws.h; e.node_idx = nullptr; e.n_nodes = (int)n_nodes; e.dx = nullptr;
+    if (prune) { e.node_idx = ws.order; e.n_nodes_dev = ws.cnt + l + 1; }
     if (rcache) {
       const size_t per = (size_t)n_nodes * (CBG_KMAX * CBG_H);
       e.rc_k = rcache + (size_t)(2 * l) * per;
@@ -180,6 +217,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     gj.ldw = 640; gj.n_planes = 2; gj.has_q = 0;
     gj.out[0] = ws.hplane[0]; gj.out[1] = ws.hplane[1];
     gj.tc_planes = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_TC); gj.tc_first_plane = 0;
+    if (prune) { gj.row_idx = ws.order; gj.n_rows_dev = ws.cnt + num_layers; }   // depth == top: generated atoms + neighbours
     if (int rc = launch_node_gemm(gj, sx)) return rc;
     NodeGemmArgs gi{};
     gi.a = ws.h; gi.row_idx = gen_idx; gi.n_rows = n_gen;
@@ -194,7 +232,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     if (int rc = launch_node_gemm(gi, sx)) return rc;
     EdgeArgs x = e;
     x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
-    x.node_idx = gen_idx; x.n_nodes = n_gen; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr;
+    x.node_idx = gen_idx; x.n_nodes = n_gen; x.n_nodes_dev = nullptr; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr;
     if (int rc = cbg_launch_h2x(x, sx)) return rc;
     if (int rc = cbg_launch_apply_dx(ws.x4, gen_idx, ws.dx, n_gen, sx)) return rc;
     if (overlap) { CBG_CUDA_OK(cudaEventRecord(g_aux.ev_x, sx)); x_pending = true; }
@@ -318,7 +356,7 @@ int32_t cbg_denoiser_forward_f32(const float* blob, int32_t num_layers, int32_t 
   if (int rc = cbg_launch_pack_x4(x, lig_flag, gen_flag, n_nodes, ws.x4, st)) return rc;
   CBG_CUDA_OK(cudaMemcpyAsync(ws.h, h, (size_t)n_nodes * CBG_H * 4, cudaMemcpyDeviceToDevice, st));
   const int L = (stop_after_layers >= 0 && stop_after_layers < num_layers) ? stop_after_layers : num_layers;
-  if (int rc = run_core(blob, L, ws, graph_ptr, n_graphs, max_graph_nodes, n_nodes, gen_idx, n_gen, mode, k, r_max, nullptr, st)) return rc;
+  if (int rc = run_core(blob, L, ws, graph_ptr, n_graphs, max_graph_nodes, n_nodes, gen_idx, n_gen, mode, k, r_max, nullptr, nullptr, 0, false, st)) return rc;
   if (x_out) { if (int rc = cbg_launch_unpack_x(ws.x4, n_nodes, x_out, st)) return rc; }
   if (h_out) CBG_CUDA_OK(cudaMemcpyAsync(h_out, ws.h, (size_t)n_nodes * CBG_H * 4, cudaMemcpyDeviceToDevice, st));
   if (logits_out) {
@@ -443,7 +481,8 @@ int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* co
   if (int rc = cbg_launch_step_init(x_t, c_t, plan->lig_node, plan->n_lig, K, plan->emb_wt, plan->h_lig_bias,
                                     plan->h_static, plan->n_nodes, ws.x4, ws.h, st)) return rc;
   if (int rc = run_core(plan->blob, plan->num_layers, ws, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes,
-                        plan->n_nodes, plan->gen_node, plan->n_gen, plan->mode, plan->k, plan->r_max, plan->rcache, st)) return rc;
+                        plan->n_nodes, plan->gen_node, plan->n_gen, plan->mode, plan->k, plan->r_max, plan->rcache,
+                        plan->lig_node, plan->n_lig, plan->prune != 0 && prune_enabled(), st)) return rc;
   // classifier on ligand rows only; logits scratch lives in the w buffer (free after the layers)
   float* lg = logits ? logits : ws.w;
   if (int rc = cbg_launch_classifier(plan->blob, ws.h, plan->lig_node, plan->n_lig, K, lg, st)) return rc;

@@ -13,6 +13,13 @@ int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max
 int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
                          float* ew, cudaStream_t st);
 
+// Receptive-field pruning (sampling path): depth[i] = last layer whose X2H output of node i can still
+// influence a generated / classified atom (-2: never).  order[] lists nodes by decreasing depth,
+// cnt_ge[l + 1] = number of nodes with depth >= l for l = -1 .. num_layers-1.
+int cbg_launch_depth(const int* nbr, const int* graph_ptr, int n_graphs, int max_graph_nodes, long long n_nodes,
+                     const int* seed_idx, int n_seed, const int* cls_idx, int n_cls, int num_layers,
+                     int* depth, int* order, int* cnt_ge, cudaStream_t st);
+
 // node_gemm.cu
 struct NodeGemmArgs {
   const float* a;        // [*,128] input rows (h)
@@ -29,6 +36,7 @@ struct NodeGemmArgs {
   const float* q_b1;     // [128]
   float* out_q;          // [N,128]
   // tensor-core path only: pre-split weight planes of the sub-layer (layout: cbg_layout.h *_NODE_TC)
+  const int* n_rows_dev;   // optional: rows to process is min(n_rows, *n_rows_dev) (device-side list length)
   const float* tc_planes;  // plane 0 of the sub-layer
   int tc_first_plane;      // index of this launch's first plane (q second Linear is always plane 5)
 };
@@ -52,6 +60,7 @@ struct EdgeArgs {
   const int* node_idx;   // h2x: list of generated nodes
   int n_nodes;           // x2h: N ; h2x: number of generated nodes
   float* dx;             // h2x: [n_nodes,4] coordinate deltas (compact, same order as node_idx)
+  const int* n_nodes_dev; // optional device-side length of node_idx (x2h with a pruned node list)
   const float* rc_k;     // x2h: R-cache of this layer's hk / hv MLP ([N][32][128]) or nullptr
   const float* rc_v;
 };

@@ -95,11 +95,18 @@ __device__ __forceinline__ unsigned edge_setup(EdgeMeta& M, int i, int lane, con
 }
 
 // pull the next node's R block (16 KB, contiguous) towards L2 while this node computes
-__device__ __forceinline__ void prefetch_rc(const float* rc_base, int i_next, int n_nodes, int lane) {
-  if (rc_base == nullptr || i_next >= n_nodes) return;
+__device__ __forceinline__ void prefetch_rc(const float* rc_base, int i_next, int lane) {
+  if (rc_base == nullptr) return;
   const char* b = reinterpret_cast<const char*>(rc_base + (size_t)i_next * (CBG_KMAX * CBG_H));
 #pragma unroll
   for (int r = 0; r < 4; ++r) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (size_t)(lane + 32 * r) * 128));
+}
+
+// number of entries of the node list of this launch (host bound, optionally clipped by a device count)
+__device__ __forceinline__ int list_length(const EdgeArgs& p) {
+  int n = p.n_nodes;
+  if (p.n_nodes_dev) { const int nd = *p.n_nodes_dev; n = nd < n ? nd : n; }
+  return n;
 }
 
 // All-lane sums of 4 per-lane values, result in every lane: transposed butterfly (each step halves
@@ -295,10 +302,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
   const MlpSmem W{s_wrf, s_c};
   const float4 gamma = ld4(s_ln + 4 * lane), beta = ld4(s_ln + 128 + 4 * lane);
 
-  for (int i = blockIdx.x * kWarps + warp; i < p.n_nodes; i += gridDim.x * kWarps) {
+  const int n_list = list_length(p);
+  for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
+    const int i = p.node_idx ? p.node_idx[n] : n;
     const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
     const float* rc = p.rc_k ? p.rc_k + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
-    prefetch_rc(p.rc_k, i + gridDim.x * kWarps, p.n_nodes, lane);
+    {
+      const int nn = n + gridDim.x * kWarps;
+      if (nn < n_list) prefetch_rc(p.rc_k, p.node_idx ? p.node_idx[nn] : nn, lane);
+    }
     float U[4][CBG_HEADS];
     build_u(p.q + (size_t)i * CBG_H, s_w1, lane, U);
     const float4 pi = ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane);
@@ -350,10 +362,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
   const MlpSmem W{s_wrf, s_c};
   const float4 gamma = ld4(s_ln + 4 * lane), beta = ld4(s_ln + 128 + 4 * lane);
 
-  for (int i = blockIdx.x * kWarps + warp; i < p.n_nodes; i += gridDim.x * kWarps) {
+  const int n_list = list_length(p);
+  for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
+    const int i = p.node_idx ? p.node_idx[n] : n;
     edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
     const float* rc = p.rc_v ? p.rc_v + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
-    prefetch_rc(p.rc_v, i + gridDim.x * kWarps, p.n_nodes, lane);
+    {
+      const int nn = n + gridDim.x * kWarps;
+      if (nn < n_list) prefetch_rc(p.rc_v, p.node_idx ? p.node_idx[nn] : nn, lane);
+    }
     {
       const float* wsrc = p.w + (size_t)i * (CBG_KMAX * CBG_HEADS);
 #pragma unroll

@@ -145,7 +145,92 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
   ew[idx] = 1.f / (1.f + expf(-o));
 }
 
+// ---- receptive-field depth ------------------------------------------------------------------------
+// X2H(l) must produce h for D_l, with D_{L-1} = seeds U nbr(seeds) U cls (H2X of every layer reads the
+// new h of the generated atoms and of their neighbours; the classifier reads the last h of cls) and
+// D_{l-1} = D_l U nbr(D_l).  depth[i] = max l with i in D_l (down to -1 for the Pj planes of layer 0).
+__global__ void depth_seed_kernel(const int* __restrict__ nbr, const int* __restrict__ seed_idx, int n_seed,
+                                  const int* __restrict__ cls_idx, int n_cls, int top, int* __restrict__ depth) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_seed * (CBG_KMAX + 1)) {
+    const int g = seed_idx[t / (CBG_KMAX + 1)], s = t % (CBG_KMAX + 1);
+    const int j = (s == CBG_KMAX) ? g : nbr[(size_t)g * CBG_KMAX + s];
+    if (j >= 0) depth[j] = top;      // benign race: every writer stores the same value
+  }
+  if (t < n_cls) depth[cls_idx[t]] = top;
+}
+
+// one CTA per graph: relax level by level inside the graph's node range
+__global__ void __launch_bounds__(256) depth_relax_kernel(const int* __restrict__ nbr, const int* __restrict__ graph_ptr,
+                                                          int top, int* __restrict__ depth) {
+  const int s = graph_ptr[blockIdx.x], e = graph_ptr[blockIdx.x + 1];
+  for (int l = top; l >= 0; --l) {
+    for (int t = threadIdx.x; t < (e - s) * CBG_KMAX; t += blockDim.x) {
+      const int i = s + t / CBG_KMAX;
+      if (depth[i] >= l) {
+        const int j = nbr[(size_t)i * CBG_KMAX + (t % CBG_KMAX)];
+        if (j >= 0 && depth[j] < l - 1) atomicMax(&depth[j], l - 1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// counting sort of the nodes by decreasing depth (bins top .. -1; depth -2 nodes are dropped)
+__global__ void depth_hist_kernel(const int* __restrict__ depth, long long n, int top, int* __restrict__ hist) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && depth[i] >= -1) atomicAdd(&hist[top - depth[i]], 1);
+}
+__global__ void depth_scan_kernel(int top, int* __restrict__ hist, int* __restrict__ cursor, int* __restrict__ cnt_ge) {
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b <= top + 1; ++b) {          // bin b holds depth top - b
+      cursor[b] = acc;
+      acc += hist[b];
+      cnt_ge[(top - b) + 1] = acc;                // nodes with depth >= top - b
+    }
+  }
+}
+__global__ void depth_scatter_kernel(const int* __restrict__ depth, long long n, int top, int* __restrict__ cursor,
+                                     int* __restrict__ order) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && depth[i] >= -1) order[atomicAdd(&cursor[top - depth[i]], 1)] = (int)i;
+}
+
 }  // namespace
+
+int cbg_launch_depth(const int* nbr, const int* graph_ptr, int n_graphs, int max_graph_nodes, long long n_nodes,
+                     const int* seed_idx, int n_seed, const int* cls_idx, int n_cls, int num_layers,
+                     int* depth, int* order, int* cnt_ge, cudaStream_t st) {
+  if (n_nodes <= 0 || num_layers <= 0) return 0;
+  if (num_layers > 30) { cbg_set_error("too many layers for receptive-field pruning"); return 1; }
+  const int top = num_layers - 1;
+  int* hist = cnt_ge + 32;      // scratch behind the counts: hist[32], cursor[32]
+  int* cursor = cnt_ge + 64;
+  CBG_CUDA_OK(cudaMemsetAsync(depth, 0xFE, (size_t)n_nodes * sizeof(int), st));   // 0xFEFEFEFE = -16843010 < -1
+  CBG_CUDA_OK(cudaMemsetAsync(cnt_ge, 0, 96 * sizeof(int), st));
+  const int work = (n_seed * (CBG_KMAX + 1) > n_cls) ? n_seed * (CBG_KMAX + 1) : n_cls;
+  if (work > 0) {
+    CBG_PROF_BEGIN(CBG_K_MISC, st);
+    depth_seed_kernel<<<(work + 255) / 256, 256, 0, st>>>(nbr, seed_idx, n_seed, cls_idx, n_cls, top, depth);
+    CBG_LAUNCHED(CBG_K_MISC, st);
+  }
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
+  depth_relax_kernel<<<n_graphs, 256, 0, st>>>(nbr, graph_ptr, top, depth);
+  CBG_LAUNCHED(CBG_K_MISC, st);
+  const unsigned nb = (unsigned)((n_nodes + 255) / 256);
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
+  depth_hist_kernel<<<nb, 256, 0, st>>>(depth, n_nodes, top, hist);
+  CBG_LAUNCHED(CBG_K_MISC, st);
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
+  depth_scan_kernel<<<1, 32, 0, st>>>(top, hist, cursor, cnt_ge);
+  CBG_LAUNCHED(CBG_K_MISC, st);
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
+  depth_scatter_kernel<<<nb, 256, 0, st>>>(depth, n_nodes, top, cursor, order);
+  CBG_LAUNCHED(CBG_K_MISC, st);
+  (void)max_graph_nodes;
+  return 0;
+}
 
 int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max_graph_nodes, int mode,
                    int k, float r_max, int static_only, int* nbr, cudaStream_t st) {

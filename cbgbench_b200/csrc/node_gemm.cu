@@ -38,6 +38,11 @@ __global__ void __launch_bounds__(256, 2) node_gemm_kernel(NodeGemmArgs p) {
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int row0 = blockIdx.x * BM;
+  if (p.n_rows_dev) {
+    const int nd = *p.n_rows_dev;
+    p.n_rows = nd < p.n_rows ? nd : p.n_rows;
+  }
+  if (row0 >= p.n_rows) return;
 
   // A tile, transposed to k-major; lanes <-> rows so the shared stores are conflict-free
   for (int idx = tid; idx < BM * 32; idx += 256) {

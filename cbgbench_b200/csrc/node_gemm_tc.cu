@@ -150,6 +150,11 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
   constexpr uint32_t SMEM_BAR = SMEM_B0 + NSTAGE * B_STAGE_BYTES;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
   const uint32_t crank = (CL > 1) ? cluster_rank() : 0u;
+  if (p.n_rows_dev) {                 // list length lives on the device (receptive-field pruning)
+    const int nd = *p.n_rows_dev;
+    p.n_rows = nd < p.n_rows ? nd : p.n_rows;
+  }
+  if ((int)(blockIdx.x / CL) * CL * TM >= p.n_rows) return;   // whole cluster beyond the list: nothing to do
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TM;

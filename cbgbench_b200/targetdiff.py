@@ -106,6 +106,8 @@ class TargetDiffB200(nn.Module):
         # R-cache: step-invariant first-Linear terms of edges between non-generated atoms are computed
         # once per batch and streamed from HBM (2*L*N*16 KB).  CBG_RCACHE=0 / use_rcache=False turns it off.
         self.use_rcache = os.environ.get('CBG_RCACHE', '1') != '0'
+        # receptive-field pruning of the per-step denoiser (exact for the sampled ligand rows)
+        self.use_prune = os.environ.get('CBG_PRUNE', '1') != '0'
 
     def forward(self, batch):
         raise NotImplementedError('TargetDiffB200 is a forward-only sampling build: the training / '
@@ -174,7 +176,7 @@ class TargetDiffB200(nn.Module):
             lig_node=lig_node.data_ptr(), n_lig=n_lig, gen_lig=gen_lig8.data_ptr(),
             gen_node=gen_node.data_ptr() if n_gen else None, n_gen=n_gen,
             mode=den.mode_id, k=den.cut_off, r_max=den.r_max, workspace=ws_ptr, workspace_bytes=ws_have,
-            rcache=rc_ptr, rcache_bytes=rc_bytes)
+            rcache=rc_ptr, rcache_bytes=rc_bytes, prune=1 if self.use_prune else 0)
         with torch.cuda.device(dev):
             _lib.check(L.cbg_sample_begin_f32(C.byref(plan), x_nodes.data_ptr(), lig_nodes.data_ptr(),
                                               gen_nodes_flag.data_ptr(), _lib.stream_ptr(dev)))

@@ -153,6 +153,9 @@ typedef struct cbg_sample_plan {
                                    first-Linear terms of edges between non-generated atoms;
                                    filled by cbg_sample_begin_f32, streamed by the fused X2H kernels */
   size_t rcache_bytes;
+  int32_t prune;                /* 1: receptive-field pruning - layer l only updates the nodes that can still
+                                   influence a generated / ligand atom through the remaining layers (exact for
+                                   everything cbg_sample_step_f32 returns; intermediate h of other nodes is skipped) */
 } cbg_sample_plan;
 
 typedef struct cbg_step_coef {  /* scheduler table entries of the current step (host scalars) */

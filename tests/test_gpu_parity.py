@@ -378,3 +378,21 @@ def test_rcache_matches_uncached_path():
         for t in range(-1, T):
             assert torch.equal(a[t][1].cpu().argmax(-1), b[t][1].cpu().argmax(-1)), (gen_mode, t)
             assert rel_err(a[t][0].cpu(), b[t][0].cpu()) < 1e-5, (gen_mode, t)
+
+
+def test_receptive_field_pruning_is_exact():
+    """Skipping the per-layer work of nodes that cannot reach a generated / ligand atom any more must
+    leave every sampled coordinate and atom type bit-identical."""
+    T = 4
+    for gen_mode, sizes in (('denovo', ([300, 120, 40], [24, 10, 6])), ('partial', ([200, 150], [18, 12]))):
+        model, sd = make_model(T, device=dev())
+        batch = synthetic.make_batch(*sizes, seed=111, gen_mode=gen_mode)
+        n_lig = int(batch['ligand_pos'].shape[0])
+        pn, tu = synthetic.make_noise(T, n_lig, 13, seed=10)
+        model.use_prune = True
+        a = model.sample(batch, pos_noise=pn, type_uniform=tu)
+        model.use_prune = False
+        b = model.sample(batch, pos_noise=pn, type_uniform=tu)
+        for t in range(-1, T):
+            assert torch.equal(a[t][0].cpu(), b[t][0].cpu()), (gen_mode, t)
+            assert torch.equal(a[t][1].cpu(), b[t][1].cpu()), (gen_mode, t)
