@@ -132,59 +132,31 @@ __device__ __forceinline__ void allreduce4(float (&s)[4], int lane) {
 
 // First Linear + LayerNorm + ReLU of one edge MLP for the 4 edges e0..e0+3.
 // a[ee] = relu(LN(Pi + Pj[j] + c[t] + Wrf[t] g)) restricted to this lane's 4 features.
-// Per-warp staging of the gathered rows of one 4-edge group (4 x Pj row, 4 x R row, 512 B each): the
-// rows of group g+1 are fetched with cp.async while group g computes, so the first Linear never waits
-// on L2 / HBM.  Every lane copies and later reads only its own 16-byte column: no cross-lane sync.
-struct __align__(16) RowStage { float4 row[8][32]; };   // 4 KB
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
-               : "memory");
-}
-__device__ __forceinline__ void stage_issue(RowStage* stg, const EdgeMeta& M, int e0, int lane,
-                                            const float* __restrict__ pj_plane, const float* __restrict__ rc) {
-#pragma unroll
-  for (int ee = 0; ee < 4; ++ee)
-    cp_async16(&stg->row[ee][lane], pj_plane + (size_t)M.j[e0 + ee] * CBG_H + 4 * lane);
-  if (rc != nullptr && M.slot[e0 + 3] >= 0) {
-#pragma unroll
-    for (int ee = 0; ee < 4; ++ee) cp_async16(&stg->row[4 + ee][lane], rc + M.slot[e0 + ee] * CBG_H + 4 * lane);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
 // rc: this node's block of the R-cache ([32 static slots][128], R = c[t] + Wrf[t] g(d) of the static
 // edge) or nullptr.  Groups whose 4 edges are all static skip the RBF mat-vec and stream R instead.
 __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane, const float4 pi,
                                              const float* __restrict__ pj_plane, const MlpSmem W,
                                              const float4 gamma, const float4 beta, float4 (&a)[4],
-                                             const float* __restrict__ rc, RowStage* stg = nullptr, int e_next = -1) {
+                                             const float* __restrict__ rc) {
   int t[4];
   const bool cached = (rc != nullptr) && (M.slot[e0 + 3] >= 0);   // static edges come first: slot[e0+3]>=0 => all 4
-  float4 pj[4];
-  if (stg != nullptr) {                     // rows of this group were staged by stage_issue()
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-    for (int ee = 0; ee < 4; ++ee) pj[ee] = stg->row[ee][lane];
-  } else {
-#pragma unroll
-    for (int ee = 0; ee < 4; ++ee) pj[ee] = ldg4(pj_plane + (size_t)M.j[e0 + ee] * CBG_H + 4 * lane);
-  }
   if (cached) {
 #pragma unroll
     for (int ee = 0; ee < 4; ++ee) {
-      const float4 r = (stg != nullptr) ? stg->row[4 + ee][lane] : ldg4(rc + M.slot[e0 + ee] * CBG_H + 4 * lane);
-      a[ee] = make_float4(pi.x + pj[ee].x + r.x, pi.y + pj[ee].y + r.y, pi.z + pj[ee].z + r.z, pi.w + pj[ee].w + r.w);
+      const int j = M.j[e0 + ee];
+      const float4 pj = ldg4(pj_plane + (size_t)j * CBG_H + 4 * lane);
+      const float4 r = ldg4(rc + M.slot[e0 + ee] * CBG_H + 4 * lane);
+      a[ee] = make_float4(pi.x + pj.x + r.x, pi.y + pj.y + r.y, pi.z + pj.z + r.z, pi.w + pj.w + r.w);
     }
-    if (stg != nullptr && e_next >= 0) stage_issue(stg, M, e_next, lane, pj_plane, rc);   // overlap with this group's math
   } else {
 #pragma unroll
   for (int ee = 0; ee < 4; ++ee) {
+    const int j = M.j[e0 + ee];
     t[ee] = M.t[e0 + ee];
+    const float4 pj = ldg4(pj_plane + (size_t)j * CBG_H + 4 * lane);
     const float4 c = ld4(W.c + t[ee] * CBG_H + 4 * lane);
-    a[ee] = make_float4(pi.x + pj[ee].x + c.x, pi.y + pj[ee].y + c.y, pi.z + pj[ee].z + c.z, pi.w + pj[ee].w + c.w);
+    a[ee] = make_float4(pi.x + pj.x + c.x, pi.y + pj.y + c.y, pi.z + pj.z + c.z, pi.w + pj.w + c.w);
   }
-  if (stg != nullptr && e_next >= 0) stage_issue(stg, M, e_next, lane, pj_plane, rc);
   const bool uniform = (t[0] == t[1]) && (t[0] == t[2]) && (t[0] == t[3]);   // warp-uniform
   if (uniform) {
     const float* w = W.wrf + t[0] * (CBG_NRBF * CBG_H) + 4 * lane;
@@ -312,7 +284,7 @@ __device__ __forceinline__ void softmax32(float (&lg)[8][2], int lane, unsigned 
 // X2H, part 1: attention weights  w[i][e][hd] = softmax_e(<q_i, k_ie>) * e_w[i][e]
 // smem: K_WRF | K_C | K_LN | K_W1 | K_RBF  (contiguous in the blob) + per-warp EdgeMeta
 constexpr int kX2hKFloats = 4 * 20 * 128 + 4 * 128 + 256 + 128 * 128 + 32;
-constexpr int x2hk_smem(int w) { return kX2hKFloats * 4 + w * ((int)sizeof(EdgeMeta) + (int)sizeof(RowStage)); }
+constexpr int x2hk_smem(int w) { return kX2hKFloats * 4 + w * (int)sizeof(EdgeMeta); }
 
 template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
@@ -323,7 +295,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
   const float* s_w1 = s_ln + 256;
   const float* s_rbf = s_w1 + 128 * 128;
   EdgeMeta* metas = reinterpret_cast<EdgeMeta*>(smem + kX2hKFloats);
-  RowStage* stages = reinterpret_cast<RowStage*>(metas + kWarps);
   block_copy_f4(smem, p.layer + kOffX2hK, kX2hKFloats);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -340,8 +311,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
       const int nn = n + gridDim.x * kWarps;
       if (nn < n_list) prefetch_rc(p.rc_k, p.node_idx ? p.node_idx[nn] : nn, lane);
     }
-    RowStage* stg = stages + warp;
-    stage_issue(stg, M, 0, lane, p.pj_k, rc);       // rows of group 0 travel while U is built
     float U[4][CBG_HEADS];
     build_u(p.q + (size_t)i * CBG_H, s_w1, lane, U);
     const float4 pi = ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane);
@@ -349,7 +318,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float4 a[4];
-      first_layer4(M, 4 * g, lane, pi, p.pj_k, W, gamma, beta, a, rc, stg, g < 7 ? 4 * g + 4 : -1);
+      first_layer4(M, 4 * g, lane, pi, p.pj_k, W, gamma, beta, a, rc);
       float r0, r1;
       contract_heads(a, U, lane, r0, r1);
 #pragma unroll
@@ -372,7 +341,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
 // X2H, part 2: h_i += W1v (sum_e w_ie a_ie) + b1v sum_e w_ie   (per head)
 // smem: V_WRF | V_C | V_LN | V_W1 | V_B1 | V_RBF + per-warp (EdgeMeta, wbuf[32][16])
 constexpr int kX2hVFloats = 4 * 20 * 128 + 4 * 128 + 256 + 128 * 128 + 128 + 32;
-constexpr int x2hv_smem(int w) { return kX2hVFloats * 4 + w * ((int)sizeof(EdgeMeta) + 32 * 16 * 4 + (int)sizeof(RowStage)); }
+constexpr int x2hv_smem(int w) { return kX2hVFloats * 4 + w * ((int)sizeof(EdgeMeta) + 32 * 16 * 4); }
 
 template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
@@ -385,7 +354,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
   const float* s_rbf = s_b1 + 128;
   EdgeMeta* metas = reinterpret_cast<EdgeMeta*>(smem + kX2hVFloats);
   float* wbufs = reinterpret_cast<float*>(metas + kWarps);
-  RowStage* stages = reinterpret_cast<RowStage*>(wbufs + kWarps * (32 * 16));
   block_copy_f4(smem, p.layer + kOffX2hV, kX2hVFloats);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -403,8 +371,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
       const int nn = n + gridDim.x * kWarps;
       if (nn < n_list) prefetch_rc(p.rc_v, p.node_idx ? p.node_idx[nn] : nn, lane);
     }
-    RowStage* stg = stages + warp;
-    stage_issue(stg, M, 0, lane, p.pj_v, rc);
     {
       const float* wsrc = p.w + (size_t)i * (CBG_KMAX * CBG_HEADS);
 #pragma unroll
@@ -418,7 +384,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float4 a[4];
-      first_layer4(M, 4 * g, lane, pi, p.pj_v, W, gamma, beta, a, rc, stg, g < 7 ? 4 * g + 4 : -1);
+      first_layer4(M, 4 * g, lane, pi, p.pj_v, W, gamma, beta, a, rc);
 #pragma unroll
       for (int ee = 0; ee < 4; ++ee) {
         const float* wr = wbuf + (4 * g + ee) * 16;
@@ -667,10 +633,11 @@ int cbg_edge_init(void) {
   CBG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   if (const char* e = getenv("CBG_EDGE_WARPS")) {
     const int w = atoi(e);
-    if (w == 8 || w == 12) g_edge_warps = w;
+    if (w == 8 || w == 12 || w == 16) g_edge_warps = w;
   }
   if (int rc = set_attrs<8>()) return rc;
   if (int rc = set_attrs<12>()) return rc;
+  if (int rc = set_attrs<16>()) return rc;
   done = true;
   return 0;
 }
@@ -696,6 +663,7 @@ int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   if (int rc = cbg_edge_init()) return rc;
   switch (g_edge_warps) {
     case 8: return launch_x2h<8>(a, st);
+    case 16: return launch_x2h<16>(a, st);
     default: return launch_x2h<12>(a, st);
   }
 }
@@ -705,6 +673,7 @@ int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
   if (int rc = cbg_edge_init()) return rc;
   switch (g_edge_warps) {
     case 8: return launch_h2x<8>(a, st);
+    case 16: return launch_h2x<16>(a, st);
     default: return launch_h2x<12>(a, st);
   }
 }
