@@ -216,36 +216,67 @@ __device__ __forceinline__ void build_u(const float* __restrict__ q_i, const flo
   }
 }
 
-// Reduce part[hp*4 + ee] (hp = lane-permuted head slot, ee = edge in the group) over the warp.
-// Steps 1-4 split on the head bits; because slot hp holds head hp ^ (lane>>1), every lane keeps
-// its lower half and sends its upper half: no selects.  Step 5 splits the high edge bit.
-// Result: r0, r1 = totals for head lane>>1 and edges 2*(lane&1), 2*(lane&1)+1 of the group.
-__device__ __forceinline__ void reduce_heads(float (&part)[64], int lane, float& r0, float& r1) {
+// Streaming head contraction + warp reduction.  For the 4 edges of a group and the 16 lane-permuted head
+// slots hp, leaf(hp)[ee] = a[ee] . W(hp) (this lane's 4 features) must be summed over all lanes.  The
+// halving butterfly  level 0: hp vs hp+8 (xor 16), 1: hp+4 (xor 8), 2: hp+2 (xor 4), 3: hp+1 (xor 2)  is
+// evaluated depth first, so a partial result is shuffled as soon as its two halves exist: only ~24
+// values are live instead of 64 and the shuffles overlap the FMAs of the next leaves.  Because slot hp
+// holds head hp ^ (lane>>1), every lane keeps its lower half and sends its upper half: no selects.
+template <int LVL, int HP, class Leaf>
+struct HeadReduce {
+  static __device__ __forceinline__ void run(const Leaf& leaf, float (&out)[4]) {
+    float lo[4], hi[4];
+    HeadReduce<LVL + 1, HP, Leaf>::run(leaf, lo);
+    HeadReduce<LVL + 1, HP + (8 >> LVL), Leaf>::run(leaf, hi);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) part[i] += __shfl_xor_sync(CBG_FULL, part[i + 32], 16);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) part[i] += __shfl_xor_sync(CBG_FULL, part[i + 16], 8);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) part[i] += __shfl_xor_sync(CBG_FULL, part[i + 8], 4);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) part[i] += __shfl_xor_sync(CBG_FULL, part[i + 4], 2);
+    for (int ee = 0; ee < 4; ++ee) out[ee] = lo[ee] + __shfl_xor_sync(CBG_FULL, hi[ee], 16 >> LVL);
+  }
+};
+template <int HP, class Leaf>
+struct HeadReduce<4, HP, Leaf> {
+  static __device__ __forceinline__ void run(const Leaf& leaf, float (&out)[4]) { leaf.template eval<HP>(out); }
+};
+// last step: split on the high edge bit (lane bit 0).  r0, r1 = totals for head lane>>1 and edges
+// 2*(lane&1), 2*(lane&1)+1 of the group.
+template <class Leaf>
+__device__ __forceinline__ void reduce_heads(const Leaf& leaf, int lane, float& r0, float& r1) {
+  float f[4];
+  HeadReduce<0, 0, Leaf>::run(leaf, f);
   const bool up = (lane & 1) != 0;
-  const float s0 = up ? part[0] : part[2], s1 = up ? part[1] : part[3];
-  const float k0 = up ? part[2] : part[0], k1 = up ? part[3] : part[1];
+  const float s0 = up ? f[0] : f[2], s1 = up ? f[1] : f[3];
+  const float k0 = up ? f[2] : f[0], k1 = up ? f[3] : f[1];
   r0 = k0 + __shfl_xor_sync(CBG_FULL, s0, 1);
   r1 = k1 + __shfl_xor_sync(CBG_FULL, s1, 1);
 }
 
-// part[hp*4+ee] = a[ee] . Up[:,hp] (this lane's 4 features), then all-lane sums (see reduce_heads).
-__device__ __forceinline__ void contract_heads(const float4 (&a)[4], const float (&U)[4][CBG_HEADS], int lane,
-                                               float& r0, float& r1) {
-  float part[64];
-#pragma unroll
-  for (int hp = 0; hp < CBG_HEADS; ++hp)
+// leaf = a[ee] . Up[:,hp] with the lane-permuted, query-folded key matrix in registers
+struct ULeaf {
+  const float4 (&a)[4];
+  const float (&U)[4][CBG_HEADS];
+  template <int HP>
+  __device__ __forceinline__ void eval(float (&out)[4]) const {
 #pragma unroll
     for (int ee = 0; ee < 4; ++ee)
-      part[hp * 4 + ee] = fmaf(a[ee].w, U[3][hp], fmaf(a[ee].z, U[2][hp], fmaf(a[ee].y, U[1][hp], a[ee].x * U[0][hp])));
-  reduce_heads(part, lane, r0, r1);
+      out[ee] = fmaf(a[ee].w, U[3][HP], fmaf(a[ee].z, U[2][HP], fmaf(a[ee].y, U[1][HP], a[ee].x * U[0][HP])));
+  }
+};
+// leaf = a[ee] . W[head][:] with the weight rows in shared memory ([16][128], lane-permuted head slot)
+struct SmemLeaf {
+  const float4 (&a)[4];
+  const float* w;      // base of the [16][128] matrix
+  int lane;
+  template <int HP>
+  __device__ __forceinline__ void eval(float (&out)[4]) const {
+    const float4 wv = ld4(w + (HP ^ (lane >> 1)) * CBG_H + 4 * lane);
+#pragma unroll
+    for (int ee = 0; ee < 4; ++ee)
+      out[ee] = fmaf(a[ee].w, wv.w, fmaf(a[ee].z, wv.z, fmaf(a[ee].y, wv.y, a[ee].x * wv.x)));
+  }
+};
+
+__device__ __forceinline__ void contract_heads(const float4 (&a)[4], const float (&U)[4][CBG_HEADS], int lane,
+                                               float& r0, float& r1) {
+  reduce_heads(ULeaf{a, U}, lane, r0, r1);
 }
 
 // edge handled by this lane for value i (0/1) of group g under the reduce_heads mapping
@@ -403,22 +434,25 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
     const int dx3 = lane >> 2;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      float part[64];
+      // g[hh] = sum over lanes of W1v[f(dp,hh)] . S[half*8+hh], reduced over the three within-head bits
+      // (dp vs dp+4: xor 16, dp+2: xor 8, dp+1: xor 4) depth first, then the two head-bit steps with selects
+      float part[8];
 #pragma unroll
-      for (int dp = 0; dp < 8; ++dp)
+      for (int hh = 0; hh < 8; ++hh) {
+        const float4 sv = S[half * 8 + hh];
+        float lv[8];
 #pragma unroll
-        for (int hh = 0; hh < 8; ++hh) {
+        for (int dp = 0; dp < 8; ++dp) {
           const int f = half * 64 + hh * 8 + (dp ^ dx3);
           const float4 wv = ld4(s_w1 + f * CBG_H + 4 * lane);
-          const float4 sv = S[half * 8 + hh];
-          part[dp * 8 + hh] = fmaf(wv.w, sv.w, fmaf(wv.z, sv.z, fmaf(wv.y, sv.y, wv.x * sv.x)));
+          lv[dp] = fmaf(wv.w, sv.w, fmaf(wv.z, sv.z, fmaf(wv.y, sv.y, wv.x * sv.x)));
         }
 #pragma unroll
-      for (int k = 0; k < 32; ++k) part[k] += __shfl_xor_sync(CBG_FULL, part[k + 32], 16);
+        for (int k = 0; k < 4; ++k) lv[k] += __shfl_xor_sync(CBG_FULL, lv[k + 4], 16);
 #pragma unroll
-      for (int k = 0; k < 16; ++k) part[k] += __shfl_xor_sync(CBG_FULL, part[k + 16], 8);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) part[k] += __shfl_xor_sync(CBG_FULL, part[k + 8], 4);
+        for (int k = 0; k < 2; ++k) lv[k] += __shfl_xor_sync(CBG_FULL, lv[k + 2], 8);
+        part[hh] = lv[0] + __shfl_xor_sync(CBG_FULL, lv[1], 4);
+      }
       {   // hh bit 2 <-> lane bit 1
         const bool up = (lane & 2) != 0;
 #pragma unroll
@@ -500,15 +534,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) h2x_kernel(EdgeArgs p) {
 #pragma unroll
       for (int gg = 0; gg < 8; ++gg) if (gg == g) { lg[gg][0] = r0; lg[gg][1] = r1; }
       first_layer4(M, 4 * g, lane, piv, p.pj_v, WV, vga, vbe, a, nullptr);
-      float part[64];
-#pragma unroll
-      for (int hp = 0; hp < CBG_HEADS; ++hp) {
-        const float4 wv = ld4(v_w1 + (hp ^ (lane >> 1)) * CBG_H + 4 * lane);   // lane-permuted head slot
-#pragma unroll
-        for (int ee = 0; ee < 4; ++ee)
-          part[hp * 4 + ee] = fmaf(a[ee].w, wv.w, fmaf(a[ee].z, wv.z, fmaf(a[ee].y, wv.y, a[ee].x * wv.x)));
-      }
-      reduce_heads(part, lane, r0, r1);
+      reduce_heads(SmemLeaf{a, v_w1, lane}, lane, r0, r1);
 #pragma unroll
       for (int gg = 0; gg < 8; ++gg) if (gg == g) { vx[gg][0] = r0 + b1; vx[gg][1] = r1 + b1; }
     }
