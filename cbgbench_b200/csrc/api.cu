@@ -59,6 +59,7 @@ struct Workspace {
   float* w;
   int* nbr;
   int* snbr;                   // static-only neighbour lists (R-cache build)
+  float* sew;                  // edge gates of the static-only lists (valid when the plan has an R-cache)
   int* depth;                  // receptive-field pruning: per-node depth, nodes ordered by depth, counts
   int* order;
   int* cnt;
@@ -79,6 +80,7 @@ Workspace carve(void* base, long long n_nodes, long long n_gen) {
   ws.w = (float*)take((size_t)n_nodes * CBG_KMAX * CBG_HEADS * 4);
   ws.nbr = (int*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.snbr = (int*)take((size_t)n_nodes * CBG_KMAX * 4);
+  ws.sew = (float*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.depth = (int*)take((size_t)n_nodes * 4);
   ws.order = (int*)take((size_t)n_nodes * 4);
   ws.cnt = (int*)take(96 * 4);
@@ -151,7 +153,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
              float r_max, const float* rcache, const int* cls_idx, int n_cls, bool prune, cudaStream_t st) {
   if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
   if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, ws.nbr, st)) return rc;
-  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, ws.ew, st)) return rc;
+  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, rcache ? ws.sew : nullptr, ws.ew, st)) return rc;
   const float* layers = blob + cbg_layout::kGlobalFloats;
   // Receptive-field pruning (only when the caller consumes nothing but the generated / classified rows):
   // layer l updates h only for the nodes that can still reach such a row through the remaining layers.
@@ -339,7 +341,7 @@ int32_t cbg_edge_gate_f32(const float* blob, const float* x, const int32_t* nbr,
   cudaStream_t st = (cudaStream_t)stream;
   CBG_CUDA_OK(cudaMemsetAsync(ws.nbr, 0, (size_t)n_nodes, st));
   if (int rc = cbg_launch_pack_x4(x, (const unsigned char*)ws.nbr, (const unsigned char*)ws.nbr, n_nodes, ws.x4, st)) return rc;
-  return cbg_launch_edge_gate(blob, ws.x4, nbr, n_nodes, ew, st);
+  return cbg_launch_edge_gate(blob, ws.x4, nbr, n_nodes, nullptr, ew, st);
 }
 
 int32_t cbg_denoiser_forward_f32(const float* blob, int32_t num_layers, int32_t num_classes, const float* x,
@@ -431,7 +433,7 @@ int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_float
 
 int32_t cbg_node_proj_f32(const float* blob_layer, int32_t sublayer, int32_t impl, const float* h,
                           const int32_t* row_idx, int32_t n_rows, int64_t n_nodes, float* planes, void* stream) {
-  if (sublayer < 0 || sublayer > 1 || (impl != 0 && impl != 1 && impl != 12 && impl != 14)) { cbg_set_error("bad sublayer/impl"); return 1; }
+  if (sublayer < 0 || sublayer > 1 || (impl != 0 && impl != 1 && impl != 11 && impl != 12 && impl != 14)) { cbg_set_error("bad sublayer/impl"); return 1; }
   const float* L = blob_layer;
   NodeGemmArgs g{};
   g.a = h; g.row_idx = row_idx; g.n_rows = n_rows;
@@ -447,7 +449,7 @@ int32_t cbg_node_proj_f32(const float* blob_layer, int32_t sublayer, int32_t imp
   g.tc_planes = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_NODE_TC : CBG_LF_X2H_NODE_TC);
   g.tc_first_plane = 0;
   if (impl == 0) return cbg_launch_node_gemm(g, (cudaStream_t)stream);
-  return cbg_launch_node_gemm_tc(g, (cudaStream_t)stream, impl == 12 ? 2 : (impl == 14 ? 4 : 1));
+  return cbg_launch_node_gemm_tc(g, (cudaStream_t)stream, impl == 12 ? 2 : (impl == 14 ? 4 : (impl == 11 ? 1 : 0)));
 }
 
 int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, const uint8_t* lig_flag,
@@ -463,6 +465,7 @@ int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, 
     if ((int64_t)plan->rcache_bytes < need) { cbg_set_error("rcache too small: have %zu bytes, need %lld", plan->rcache_bytes, (long long)need); return 1; }
     if (int rc = cbg_launch_knn(ws.x4, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes, CBG_MODE_KNN, CBG_KMAX,
                                 0.f, 1, ws.snbr, st)) return rc;
+    if (int rc = cbg_launch_edge_gate(plan->blob, ws.x4, ws.snbr, plan->n_nodes, nullptr, ws.sew, st)) return rc;
     if (int rc = cbg_launch_rcache(plan->blob + cbg_layout::kGlobalFloats, plan->num_layers, ws.x4, ws.snbr,
                                    (int)plan->n_nodes, plan->rcache, st)) return rc;
   }

@@ -10,8 +10,9 @@
 // the bit get an empty row) - the static-only kNN lists behind the R-cache
 int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max_graph_nodes, int mode,
                    int k, float r_max, int static_only, int* nbr, cudaStream_t st);
+// ew_static (optional): gates of the static-only neighbour lists, reused for static edges
 int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
-                         float* ew, cudaStream_t st);
+                         const float* ew_static, float* ew, cudaStream_t st);
 
 // Receptive-field pruning (sampling path): depth[i] = last layer whose X2H output of node i can still
 // influence a generated / classified atom (-2: never).  order[] lists nodes by decreasing depth,

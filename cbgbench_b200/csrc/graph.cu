@@ -92,6 +92,7 @@ constexpr int kGateSmemFloats = 20 * 160 + 160 + 320 + 160 + 32;
 __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict__ gw,  // GATE_W0T..GATE_RBF
                                                         const float4* __restrict__ x4,
                                                         const int* __restrict__ nbr, long long n_slots,
+                                                        const float* __restrict__ ew_static,
                                                         float* __restrict__ ew) {
   __shared__ __align__(16) float sm[kGateSmemFloats];
   block_copy_f4(sm, gw, kGateSmemFloats);
@@ -102,12 +103,24 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
   const float* beta = gamma + 160;
   const float* w1 = beta + 160;
   const float* rbf = w1 + 160;           // offsets[20], coeff, b1
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_slots) return;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one warp = one node's 32 slots
+  if (idx >= n_slots) return;                      // n_slots is a multiple of 32: whole warps leave together
   const int j = nbr[idx];
-  if (j < 0) { ew[idx] = 0.f; return; }
   const int i = (int)(idx / CBG_KMAX);
-  const float4 xi = x4[i], xj = x4[j];
+  const float4 xi = x4[i];
+  const float4 xj = x4[j >= 0 ? j : i];
+  if (ew_static != nullptr) {
+    // gate of an edge between two non-generated atoms never changes over the diffusion steps: it was
+    // computed once per batch for the node's static-only neighbour list; the p-th static edge of the
+    // current list is the p-th entry of that list (prefix property, see edge.cu: edge_setup)
+    const bool is_static = j >= 0 && ((node_flags(xi) | node_flags(xj)) & 2) == 0;
+    const unsigned sm = __ballot_sync(CBG_FULL, is_static);
+    if (is_static) {
+      ew[idx] = ew_static[(size_t)i * CBG_KMAX + __popc(sm & ((1u << (threadIdx.x & 31)) - 1u))];
+      return;
+    }
+  }
+  if (j < 0) { ew[idx] = 0.f; return; }
   const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
   const float d = sqrtf(rx * rx + ry * ry + rz * rz);
   float g[CBG_NRBF];
@@ -161,7 +174,7 @@ __global__ void depth_seed_kernel(const int* __restrict__ nbr, const int* __rest
 }
 
 // one CTA per graph: relax level by level inside the graph's node range
-__global__ void __launch_bounds__(256) depth_relax_kernel(const int* __restrict__ nbr, const int* __restrict__ graph_ptr,
+__global__ void __launch_bounds__(1024) depth_relax_kernel(const int* __restrict__ nbr, const int* __restrict__ graph_ptr,
                                                           int top, int* __restrict__ depth) {
   const int s = graph_ptr[blockIdx.x], e = graph_ptr[blockIdx.x + 1];
   for (int l = top; l >= 0; --l) {
@@ -216,7 +229,7 @@ int cbg_launch_depth(const int* nbr, const int* graph_ptr, int n_graphs, int max
     CBG_LAUNCHED(CBG_K_MISC, st);
   }
   CBG_PROF_BEGIN(CBG_K_MISC, st);
-  depth_relax_kernel<<<n_graphs, 256, 0, st>>>(nbr, graph_ptr, top, depth);
+  depth_relax_kernel<<<n_graphs, 1024, 0, st>>>(nbr, graph_ptr, top, depth);
   CBG_LAUNCHED(CBG_K_MISC, st);
   const unsigned nb = (unsigned)((n_nodes + 255) / 256);
   CBG_PROF_BEGIN(CBG_K_MISC, st);
@@ -255,12 +268,12 @@ int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max
 }
 
 int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
-                         float* ew, cudaStream_t st) {
+                         const float* ew_static, float* ew, cudaStream_t st) {
   const long long n_slots = n_nodes * CBG_KMAX;
   if (n_slots == 0) return 0;
   const float* gw = blob_global + cbg_layout::global_offset(CBG_GF_GATE_W0T);
   CBG_PROF_BEGIN(CBG_K_GATE, st);
-  edge_gate_kernel<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(gw, x4, nbr, n_slots, ew);
+  edge_gate_kernel<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(gw, x4, nbr, n_slots, ew_static, ew);
   CBG_LAUNCHED(CBG_K_GATE, st);
   return 0;
 }

@@ -320,6 +320,214 @@ __global__ void __launch_bounds__(256, 1) node_gemm_tc_kernel(NodeGemmArgs p) {
 
 
 
+// ------------------------------------------------------------------------------------------------
+// Warp-specialised variant (default): 8 staging/epilogue warps + a weight-copy thread + an MMA-issuing
+// thread, two TMEM accumulators.  The copy thread runs ahead through the 3-stage weight ring, the MMA
+// thread streams the planes back to back (plane g+1 accumulates while the epilogue warps drain plane
+// g), the epilogue warps never wait on copies.  mbarriers: full/empty per ring stage, acc_full/acc_free
+// per accumulator, a_ready for the LayerNorm'ed operand of the q MLP's second Linear.
+constexpr int WS_STAGES = 3;
+constexpr uint32_t WS_SMEM_BAR = SMEM_B0 + WS_STAGES * B_STAGE_BYTES;
+constexpr uint32_t WS_SMEM_TOTAL = WS_SMEM_BAR + 128;
+constexpr uint32_t WS_TMEM_COLS = 256;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(320, 1) node_gemm_ws_kernel(NodeGemmArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (p.n_rows_dev) {
+    const int nd = *p.n_rows_dev;
+    p.n_rows = nd < p.n_rows ? nd : p.n_rows;
+  }
+  const int row0 = blockIdx.x * TM;
+  if (row0 >= p.n_rows) return;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full = sbase + WS_SMEM_BAR;              // [WS_STAGES]
+  const uint32_t bar_empty = bar_full + 8 * WS_STAGES;        // [WS_STAGES]
+  const uint32_t bar_acc_full = bar_empty + 8 * WS_STAGES;    // [2]
+  const uint32_t bar_acc_free = bar_acc_full + 16;            // [2]
+  const uint32_t bar_a_ready = bar_acc_free + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + WS_SMEM_BAR + 8 * (2 * WS_STAGES + 5));
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(WS_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 32) {
+    for (int s = 0; s < WS_STAGES; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_acc_full + 8 * b, 1); mbar_init(bar_acc_free + 8 * b, 8); }
+    mbar_init(bar_a_ready, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const int n_gemm = p.n_planes + (p.has_q ? 1 : 0);
+  const int total_chunks = n_gemm * NKC;
+
+  if (warp < 8) {
+    // A tile: rows of h -> (hi, lo) tf32 tiles; lanes <-> rows keeps the 16 B shared stores conflict free
+    const int r = tid & (TM - 1);
+    const int row = row0 + r;
+    const bool live = row < p.n_rows;
+    const float* arow = p.a + (size_t)(live ? (p.row_idx ? p.row_idx[row] : row) : 0) * CBG_H;
+#pragma unroll
+    for (int it = 0; it < 16; it += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = live ? ldg4(arow + 4 * ((tid >> 7) + 2 * (it + j))) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) store_split(smem, r, (tid >> 7) + 2 * (it + j), v[j]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 9) {
+    // ===== weight-chunk producer =====
+    if (lane == 0) {
+      for (int i = 0; i < total_chunks; ++i) {
+        const int s = i % WS_STAGES;
+        if (i >= WS_STAGES) mbar_wait(bar_empty + 8 * s, (uint32_t)(((i / WS_STAGES) - 1) & 1));
+        mbar_expect_tx(bar_full + 8 * s, B_STAGE_BYTES);
+        bulk_g2s(sbase + SMEM_B0 + s * B_STAGE_BYTES, chunk_src_ptr(p, i), B_STAGE_BYTES, bar_full + 8 * s);
+      }
+    }
+  } else if (warp == 8) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      for (int g = 0; g < n_gemm; ++g) {
+        const int buf = g & 1;
+        if (g >= 2) mbar_wait(bar_acc_free + 8 * buf, (uint32_t)(((g >> 1) - 1) & 1));   // epilogue drained this accumulator
+        if (p.has_q && g == p.n_planes) mbar_wait(bar_a_ready, 0u);                      // A tiles now hold relu(LN(q_hidden))
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_tmem = tmem + (uint32_t)(buf * 128);
+        for (int c = 0; c < NKC; ++c) {
+          const int i = g * NKC + c, s = i % WS_STAGES;
+          mbar_wait(bar_full + 8 * s, (uint32_t)((i / WS_STAGES) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b_hi = sbase + SMEM_B0 + s * B_STAGE_BYTES, b_lo = b_hi + B_CHUNK_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < KC / 8; ++ks) {
+            const uint32_t koff_a = (uint32_t)(c * (KC / 4) + ks * 2) * 128u;
+            const uint32_t koff_b = (uint32_t)(ks * 2) * 128u;
+            const uint64_t a_hi = make_desc(sbase + SMEM_A_HI + koff_a, A_SBO);
+            const uint64_t a_lo = make_desc(sbase + SMEM_A_LO + koff_a, A_SBO);
+            const uint64_t d_bhi = make_desc(b_hi + koff_b, B_SBO);
+            const uint64_t d_blo = make_desc(b_lo + koff_b, B_SBO);
+            const uint32_t first = (c == 0 && ks == 0) ? 0u : 1u;
+            umma_tf32(d_tmem, a_lo, d_bhi, first);
+            umma_tf32(d_tmem, a_hi, d_blo, 1u);
+            umma_tf32(d_tmem, a_hi, d_bhi, 1u);
+          }
+          umma_commit(bar_empty + 8 * s);
+        }
+        umma_commit(bar_acc_full + 8 * buf);
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    const int q4 = warp & 3, chalf = warp >> 2;
+    const int my_row = 32 * q4 + lane;
+    const int grow = row0 + my_row;
+    const int dst = (grow < p.n_rows) ? (p.row_idx ? p.row_idx[grow] : grow) : -1;
+    for (int g = 0; g < n_gemm; ++g) {
+      const int buf = g & 1;
+      mbar_wait(bar_acc_full + 8 * buf, (uint32_t)((g >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t t_lane = tmem + ((uint32_t)(32 * q4) << 16) + (uint32_t)(buf * 128);
+      const bool is_qhid = p.has_q && (g == p.n_planes - 1);
+      const bool is_q2 = p.has_q && (g == p.n_planes);
+      if (!is_qhid) {
+        const float* bias = is_q2 ? p.q_b1 : (p.bias + g * CBG_H);
+        float* out = is_q2 ? p.out_q : p.out[g];
+#pragma unroll 1
+        for (int cb = 0; cb < 2; ++cb) {
+          const int col0 = chalf * 64 + cb * 32;
+          float v[32];
+          tmem_ld32(t_lane + (uint32_t)col0, v);
+          if (dst >= 0) {
+            float* o = out + (size_t)dst * CBG_H + col0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = ldg4(bias + col0 + 4 * j);
+              st4(o + 4 * j, make_float4(v[4 * j] + b.x, v[4 * j + 1] + b.y, v[4 * j + 2] + b.z, v[4 * j + 3] + b.w));
+            }
+          }
+        }
+      } else {
+        if (chalf == 0) {
+          // q hidden: + bias, two-pass LayerNorm over the row (TMEM is re-read instead of keeping 128 values
+          // live), ReLU, back into the A tiles as the operand of the second Linear
+          const float* bias = p.bias + g * CBG_H;
+          float s = 0.f;
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            float t[32];
+            tmem_ld32(t_lane + (uint32_t)(cb * 32), t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += t[j] + __ldg(bias + cb * 32 + j);
+          }
+          const float mean = s * (1.f / 128.f);
+          float q = 0.f;
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            float t[32];
+            tmem_ld32(t_lane + (uint32_t)(cb * 32), t);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const float d = t[j] + __ldg(bias + cb * 32 + j) - mean; q = fmaf(d, d, q); }
+          }
+          const float rstd = 1.f / sqrtf(q * (1.f / 128.f) + 1e-5f);
+#pragma unroll 1
+          for (int cb = 0; cb < 4; ++cb) {
+            float t[32];
+            tmem_ld32(t_lane + (uint32_t)(cb * 32), t);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const int col = cb * 32 + 4 * k4;
+              const float4 bi = ldg4(bias + col), ga = ldg4(p.q_ln + col), be = ldg4(p.q_ln + 128 + col);
+              float4 a;
+              a.x = fmaxf(fmaf((t[4 * k4 + 0] + bi.x - mean) * rstd, ga.x, be.x), 0.f);
+              a.y = fmaxf(fmaf((t[4 * k4 + 1] + bi.y - mean) * rstd, ga.y, be.y), 0.f);
+              a.z = fmaxf(fmaf((t[4 * k4 + 2] + bi.z - mean) * rstd, ga.z, be.z), 0.f);
+              a.w = fmaxf(fmaf((t[4 * k4 + 3] + bi.w - mean) * rstd, ga.w, be.w), 0.f);
+              store_split(smem, my_row, col >> 2, a);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_a_ready);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acc_free + 8 * buf);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(WS_TMEM_COLS));
+  }
+}
+
+int launch_ws(const NodeGemmArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_TOTAL));
+    attr_set = true;
+  }
+  CBG_PROF_BEGIN(CBG_K_NODE_GEMM, st);
+  node_gemm_ws_kernel<<<(a.n_rows + TM - 1) / TM, 320, WS_SMEM_TOTAL, st>>>(a);
+  CBG_LAUNCHED(CBG_K_NODE_GEMM, st);
+  return 0;
+}
+
 template <int CL, int NSTAGE>
 int launch_tc(const NodeGemmArgs& a, cudaStream_t st) {
   constexpr uint32_t SMEM_TOTAL = smem_total(NSTAGE);
@@ -349,14 +557,17 @@ int launch_tc(const NodeGemmArgs& a, cudaStream_t st) {
 int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st, int cluster) {
   if (a.n_rows <= 0) return 0;
   if (!a.tc_planes) { cbg_set_error("tensor-core node GEMM needs the pre-split weight planes"); return 1; }
-  static int cl_env = -1, stages = -1;
+  static int cl_env = -1, stages = -1, use_ws = 1;
   if (cl_env < 0) {
+    const char* v = getenv("CBG_GEMM_WS");
+    use_ws = !(v && atoi(v) == 0);
     const char* e = getenv("CBG_GEMM_CLUSTER");
     cl_env = e ? atoi(e) : 1;
     if (cl_env != 1 && cl_env != 2 && cl_env != 4) cl_env = 1;
     const char* s = getenv("CBG_GEMM_STAGES");
     stages = (s && atoi(s) == 2) ? 2 : 3;
   }
+  if (cluster == 0 && use_ws && cl_env == 1) return launch_ws(a, st);     // default: warp-specialised kernel
   const int cl = (cluster == 1 || cluster == 2 || cluster == 4) ? cluster : cl_env;
   if (stages == 2) {
     switch (cl) {

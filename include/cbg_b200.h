@@ -116,7 +116,8 @@ int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_float
 /* Node projections of one attention sub-layer alone (testing / integration hook): the five planes
  * [Pj_k, Pj_v, Pi_k, Pi_v, q] of sub-layer `sublayer` (0 = X2H, 1 = H2X) for the listed rows
  * (row_idx NULL = rows 0..n_rows-1), planes = [5][n_nodes][128].  impl 0 = fp32 SIMT kernel,
- * 1 = tcgen05 3xTF32 kernel, 12 / 14 = the same with weight chunks multicast over clusters of 2 / 4 CTAs.  blob_layer points at the layer's block inside the packed blob.
+ * 1 = tcgen05 3xTF32 kernel (warp-specialised, default), 11 = single-issuer variant, 12 / 14 = that variant
+ * with weight chunks multicast over clusters of 2 / 4 CTAs.  blob_layer points at the layer's block inside the packed blob.
  * Replaces the h-dependent part of MLP.net[0] and hq_func/xq_func (x2h_attention.py:58-83). */
 int32_t cbg_node_proj_f32(const float* blob_layer, int32_t sublayer, int32_t impl, const float* h,
                           const int32_t* row_idx, int32_t n_rows, int64_t n_nodes, float* planes, void* stream);
