@@ -95,8 +95,6 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
                                                         const float* __restrict__ ew_static,
                                                         float* __restrict__ ew) {
   __shared__ __align__(16) float sm[kGateSmemFloats];
-  block_copy_f4(sm, gw, kGateSmemFloats);
-  __syncthreads();
   const float* w0t = sm;                 // [20][160]
   const float* b0 = sm + 3200;
   const float* gamma = b0 + 160;
@@ -104,23 +102,33 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
   const float* w1 = beta + 160;
   const float* rbf = w1 + 160;           // offsets[20], coeff, b1
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one warp = one node's 32 slots
-  if (idx >= n_slots) return;                      // n_slots is a multiple of 32: whole warps leave together
-  const int j = nbr[idx];
-  const int i = (int)(idx / CBG_KMAX);
-  const float4 xi = x4[i];
-  const float4 xj = x4[j >= 0 ? j : i];
-  if (ew_static != nullptr) {
-    // gate of an edge between two non-generated atoms never changes over the diffusion steps: it was
-    // computed once per batch for the node's static-only neighbour list; the p-th static edge of the
-    // current list is the p-th entry of that list (prefix property, see edge.cu: edge_setup)
-    const bool is_static = j >= 0 && ((node_flags(xi) | node_flags(xj)) & 2) == 0;
-    const unsigned sm = __ballot_sync(CBG_FULL, is_static);
-    if (is_static) {
-      ew[idx] = ew_static[(size_t)i * CBG_KMAX + __popc(sm & ((1u << (threadIdx.x & 31)) - 1u))];
-      return;
+  const bool in_range = idx < n_slots;   // n_slots is a multiple of 32: whole warps are in or out
+  int j = -1, i = 0;
+  float4 xi = make_float4(0.f, 0.f, 0.f, 0.f), xj = xi;
+  bool need = false;
+  if (in_range) {
+    j = nbr[idx];
+    i = (int)(idx / CBG_KMAX);
+    xi = x4[i];
+    xj = x4[j >= 0 ? j : i];
+    need = j >= 0;
+    if (ew_static != nullptr) {
+      // gate of an edge between two non-generated atoms never changes over the diffusion steps: it was
+      // computed once per batch for the node's static-only neighbour list; the p-th static edge of the
+      // current list is the p-th entry of that list (prefix property, see edge.cu: edge_setup)
+      const bool is_static = j >= 0 && ((node_flags(xi) | node_flags(xj)) & 2) == 0;
+      const unsigned sm_mask = __ballot_sync(CBG_FULL, is_static);
+      if (is_static) {
+        ew[idx] = ew_static[(size_t)i * CBG_KMAX + __popc(sm_mask & ((1u << (threadIdx.x & 31)) - 1u))];
+        need = false;
+      }
     }
+    if (j < 0) ew[idx] = 0.f;
   }
-  if (j < 0) { ew[idx] = 0.f; return; }
+  if (!__syncthreads_or(need ? 1 : 0)) return;     // nothing to compute in this CTA: skip the weight staging
+  block_copy_f4(sm, gw, kGateSmemFloats);
+  __syncthreads();
+  if (!need) return;
   const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
   const float d = sqrtf(rx * rx + ry * ry + rz * rz);
   float g[CBG_NRBF];
