@@ -132,52 +132,31 @@ __device__ __forceinline__ void allreduce4(float (&s)[4], int lane) {
 
 // First Linear + LayerNorm + ReLU of one edge MLP for the 4 edges e0..e0+3.
 // a[ee] = relu(LN(Pi + Pj[j] + c[t] + Wrf[t] g)) restricted to this lane's 4 features.
-// Register prefetch of the gathered rows of the NEXT 4-edge group (software pipelining by one group):
-// PF = 0 none, 1 = the R-cache rows (HBM), 2 = R rows and Pj rows.  The loads are issued right after the
-// current group's rows were consumed and travel during its LayerNorm / contraction.
-struct RowPf { float4 pj[4]; float4 r[4]; };
-
-template <int PF>
-__device__ __forceinline__ void load_rows(const EdgeMeta& M, int e0, int lane, const float* __restrict__ pj_plane,
-                                          const float* __restrict__ rc, RowPf& pf) {
-  if (PF >= 2) {
-#pragma unroll
-    for (int ee = 0; ee < 4; ++ee) pf.pj[ee] = ldg4(pj_plane + (size_t)M.j[e0 + ee] * CBG_H + 4 * lane);
-  }
-  if (PF >= 1 && rc != nullptr && M.slot[e0 + 3] >= 0) {
-#pragma unroll
-    for (int ee = 0; ee < 4; ++ee) pf.r[ee] = ldg4(rc + M.slot[e0 + ee] * CBG_H + 4 * lane);
-  }
-}
-
 // rc: this node's block of the R-cache ([32 static slots][128], R = c[t] + Wrf[t] g(d) of the static
 // edge) or nullptr.  Groups whose 4 edges are all static skip the RBF mat-vec and stream R instead.
-template <int PF>
 __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane, const float4 pi,
                                              const float* __restrict__ pj_plane, const MlpSmem W,
                                              const float4 gamma, const float4 beta, float4 (&a)[4],
-                                             const float* __restrict__ rc, RowPf& pf, int e_next) {
+                                             const float* __restrict__ rc) {
   int t[4];
   const bool cached = (rc != nullptr) && (M.slot[e0 + 3] >= 0);   // static edges come first: slot[e0+3]>=0 => all 4
-  float4 pj[4];
-#pragma unroll
-  for (int ee = 0; ee < 4; ++ee)
-    pj[ee] = (PF >= 2) ? pf.pj[ee] : ldg4(pj_plane + (size_t)M.j[e0 + ee] * CBG_H + 4 * lane);
   if (cached) {
 #pragma unroll
     for (int ee = 0; ee < 4; ++ee) {
-      const float4 r = (PF >= 1) ? pf.r[ee] : ldg4(rc + M.slot[e0 + ee] * CBG_H + 4 * lane);
-      a[ee] = make_float4(pi.x + pj[ee].x + r.x, pi.y + pj[ee].y + r.y, pi.z + pj[ee].z + r.z, pi.w + pj[ee].w + r.w);
+      const int j = M.j[e0 + ee];
+      const float4 pj = ldg4(pj_plane + (size_t)j * CBG_H + 4 * lane);
+      const float4 r = ldg4(rc + M.slot[e0 + ee] * CBG_H + 4 * lane);
+      a[ee] = make_float4(pi.x + pj.x + r.x, pi.y + pj.y + r.y, pi.z + pj.z + r.z, pi.w + pj.w + r.w);
     }
-    if (PF >= 1 && e_next >= 0) load_rows<PF>(M, e_next, lane, pj_plane, rc, pf);
   } else {
 #pragma unroll
   for (int ee = 0; ee < 4; ++ee) {
+    const int j = M.j[e0 + ee];
     t[ee] = M.t[e0 + ee];
+    const float4 pj = ldg4(pj_plane + (size_t)j * CBG_H + 4 * lane);
     const float4 c = ld4(W.c + t[ee] * CBG_H + 4 * lane);
-    a[ee] = make_float4(pi.x + pj[ee].x + c.x, pi.y + pj[ee].y + c.y, pi.z + pj[ee].z + c.z, pi.w + pj[ee].w + c.w);
+    a[ee] = make_float4(pi.x + pj.x + c.x, pi.y + pj.y + c.y, pi.z + pj.z + c.z, pi.w + pj.w + c.w);
   }
-  if (PF >= 1 && e_next >= 0) load_rows<PF>(M, e_next, lane, pj_plane, rc, pf);
   const bool uniform = (t[0] == t[1]) && (t[0] == t[2]) && (t[0] == t[3]);   // warp-uniform
   if (uniform) {
     const float* w = W.wrf + t[0] * (CBG_NRBF * CBG_H) + 4 * lane;
@@ -338,7 +317,7 @@ __device__ __forceinline__ void softmax32(float (&lg)[8][2], int lane, unsigned 
 constexpr int kX2hKFloats = 4 * 20 * 128 + 4 * 128 + 256 + 128 * 128 + 32;
 constexpr int x2hk_smem(int w) { return kX2hKFloats * 4 + w * (int)sizeof(EdgeMeta); }
 
-template <int kWarps, int PF>
+template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
   extern __shared__ __align__(16) float smem[];
   const float* s_wrf = smem;
@@ -363,8 +342,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
       const int nn = n + gridDim.x * kWarps;
       if (nn < n_list) prefetch_rc(p.rc_k, p.node_idx ? p.node_idx[nn] : nn, lane);
     }
-    RowPf pf;
-    load_rows<PF>(M, 0, lane, p.pj_k, rc, pf);      // rows of group 0 travel while U is built
     float U[4][CBG_HEADS];
     build_u(p.q + (size_t)i * CBG_H, s_w1, lane, U);
     const float4 pi = ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane);
@@ -372,7 +349,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float4 a[4];
-      first_layer4<PF>(M, 4 * g, lane, pi, p.pj_k, W, gamma, beta, a, rc, pf, g < 7 ? 4 * g + 4 : -1);
+      first_layer4(M, 4 * g, lane, pi, p.pj_k, W, gamma, beta, a, rc);
       float r0, r1;
       contract_heads(a, U, lane, r0, r1);
 #pragma unroll
@@ -397,7 +374,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
 constexpr int kX2hVFloats = 4 * 20 * 128 + 4 * 128 + 256 + 128 * 128 + 128 + 32;
 constexpr int x2hv_smem(int w) { return kX2hVFloats * 4 + w * ((int)sizeof(EdgeMeta) + 32 * 16 * 4); }
 
-template <int kWarps, int PF>
+template <int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
   extern __shared__ __align__(16) float smem[];
   const float* s_wrf = smem;
@@ -425,8 +402,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
       const int nn = n + gridDim.x * kWarps;
       if (nn < n_list) prefetch_rc(p.rc_v, p.node_idx ? p.node_idx[nn] : nn, lane);
     }
-    RowPf pf;
-    load_rows<PF>(M, 0, lane, p.pj_v, rc, pf);
     {
       const float* wsrc = p.w + (size_t)i * (CBG_KMAX * CBG_HEADS);
 #pragma unroll
@@ -440,7 +415,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float4 a[4];
-      first_layer4<PF>(M, 4 * g, lane, pi, p.pj_v, W, gamma, beta, a, rc, pf, g < 7 ? 4 * g + 4 : -1);
+      first_layer4(M, 4 * g, lane, pi, p.pj_v, W, gamma, beta, a, rc);
 #pragma unroll
       for (int ee = 0; ee < 4; ++ee) {
         const float* wr = wbuf + (4 * g + ee) * 16;
@@ -549,17 +524,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) h2x_kernel(EdgeArgs p) {
     const float4 pik = ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane);
     const float4 piv = ldg4(p.pi_v + (size_t)i * CBG_H + 4 * lane);
     float lg[8][2], vx[8][2];
-    RowPf pf0;   // unused (PF = 0)
 #pragma unroll 1
     for (int g = 0; g < 8; ++g) {
       float4 a[4];
-      first_layer4<0>(M, 4 * g, lane, pik, p.pj_k, WK, kga, kbe, a, nullptr, pf0, -1);
+      first_layer4(M, 4 * g, lane, pik, p.pj_k, WK, kga, kbe, a, nullptr);
       float r0, r1;
       contract_heads(a, U, lane, r0, r1);
       // dynamic g: keep the register arrays statically indexed
 #pragma unroll
       for (int gg = 0; gg < 8; ++gg) if (gg == g) { lg[gg][0] = r0; lg[gg][1] = r1; }
-      first_layer4<0>(M, 4 * g, lane, piv, p.pj_v, WV, vga, vbe, a, nullptr, pf0, -1);
+      first_layer4(M, 4 * g, lane, piv, p.pj_v, WV, vga, vbe, a, nullptr);
       reduce_heads(SmemLeaf{a, v_w1, lane}, lane, r0, r1);
 #pragma unroll
       for (int gg = 0; gg < 8; ++gg) if (gg == g) { vx[gg][0] = r0 + b1; vx[gg][1] = r1 + b1; }
@@ -641,16 +615,11 @@ __global__ void __launch_bounds__(256) rcache_kernel(const float* __restrict__ l
 
 int g_num_sms = 0;
 int g_edge_warps = 12;
-int g_edge_pf = 1;
 
-template <int W, int PF>
-int set_attrs_x2h() {
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_kernel<W, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_smem(W)));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_kernel<W, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_smem(W)));
-  return 0;
-}
 template <int W>
-int set_attrs_h2x() {
+int set_attrs() {
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_smem(W)));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(h2x_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_smem(W)));
   return 0;
 }
@@ -660,14 +629,14 @@ int edge_grid(int n_nodes, int warps) {
   return need < g_num_sms ? need : g_num_sms;
 }
 
-template <int W, int PF>
+template <int W>
 int launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   const int grid = edge_grid(a.n_nodes, W);
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
-  x2h_k_kernel<W, PF><<<grid, W * 32, x2hk_smem(W), st>>>(a);
+  x2h_k_kernel<W><<<grid, W * 32, x2hk_smem(W), st>>>(a);
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
-  x2h_v_kernel<W, PF><<<grid, W * 32, x2hv_smem(W), st>>>(a);
+  x2h_v_kernel<W><<<grid, W * 32, x2hv_smem(W), st>>>(a);
   CBG_LAUNCHED(CBG_K_X2H_V, st);
   return 0;
 }
@@ -690,18 +659,11 @@ int cbg_edge_init(void) {
   CBG_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   if (const char* e = getenv("CBG_EDGE_WARPS")) {
     const int w = atoi(e);
-    if (w == 8 || w == 12) g_edge_warps = w;
+    if (w == 8 || w == 12 || w == 16) g_edge_warps = w;
   }
-  if (const char* e = getenv("CBG_EDGE_PF")) {
-    const int v = atoi(e);
-    if (v >= 0 && v <= 2) g_edge_pf = v;
-  }
-  if (int rc = set_attrs_x2h<8, 0>()) return rc;
-  if (int rc = set_attrs_x2h<12, 0>()) return rc;
-  if (int rc = set_attrs_x2h<12, 1>()) return rc;
-  if (int rc = set_attrs_x2h<12, 2>()) return rc;
-  if (int rc = set_attrs_h2x<8>()) return rc;
-  if (int rc = set_attrs_h2x<12>()) return rc;
+  if (int rc = set_attrs<8>()) return rc;
+  if (int rc = set_attrs<12>()) return rc;
+  if (int rc = set_attrs<16>()) return rc;
   done = true;
   return 0;
 }
@@ -725,16 +687,19 @@ int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, con
 int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
-  if (g_edge_warps == 8) return launch_x2h<8, 0>(a, st);
-  switch (g_edge_pf) {
-    case 0: return launch_x2h<12, 0>(a, st);
-    case 2: return launch_x2h<12, 2>(a, st);
-    default: return launch_x2h<12, 1>(a, st);
+  switch (g_edge_warps) {
+    case 8: return launch_x2h<8>(a, st);
+    case 16: return launch_x2h<16>(a, st);
+    default: return launch_x2h<12>(a, st);
   }
 }
 
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
-  return g_edge_warps == 8 ? launch_h2x<8>(a, st) : launch_h2x<12>(a, st);
+  switch (g_edge_warps) {
+    case 8: return launch_h2x<8>(a, st);
+    case 16: return launch_h2x<16>(a, st);
+    default: return launch_h2x<12>(a, st);
+  }
 }
