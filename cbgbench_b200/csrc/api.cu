@@ -118,8 +118,8 @@ int launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st) {
 // Second stream for the H2X chain of layer l, which overlaps the X2H node GEMM of layer l+1
 // (that GEMM needs only h).  Fork/join with two events; CBG_OVERLAP=0 keeps everything on one stream.
 struct AuxStream {
-  cudaStream_t s2 = nullptr;
-  cudaEvent_t ev_h = nullptr, ev_x = nullptr;
+  cudaStream_t s2 = nullptr, s3 = nullptr, s4 = nullptr;   // H2X chain, X2H source-plane GEMM, H2X destination GEMM
+  cudaEvent_t ev_h = nullptr, ev_x = nullptr, ev_h0 = nullptr, ev_p = nullptr, ev_gi = nullptr;
   int state = -1;   // -1 unknown, 0 disabled, 1 ready
 } g_aux;
 
@@ -128,8 +128,13 @@ int aux_ready() {
   const char* e = getenv("CBG_OVERLAP");
   if (e && strcmp(e, "0") == 0) { g_aux.state = 0; return 0; }
   if (cudaStreamCreateWithFlags(&g_aux.s2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g_aux.s3, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&g_aux.s4, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&g_aux.ev_h, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&g_aux.ev_x, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&g_aux.ev_x, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g_aux.ev_h0, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g_aux.ev_p, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g_aux.ev_gi, cudaEventDisableTiming) != cudaSuccess) {
     g_aux.state = 0;
     return 0;
   }
@@ -187,12 +192,19 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
       // Pi / q only for the needed destinations (depth >= l); both lists are prefixes of ws.order
       NodeGemmArgs gp = g;
       gp.row_idx = ws.order; gp.n_rows_dev = ws.cnt + l; gp.n_planes = 2; gp.has_q = 0;
-      if (int rc = launch_node_gemm(gp, st)) return rc;
+      const bool fork_p = overlap;          // the two X2H GEMMs only read h: run them side by side
+      if (fork_p) {
+        CBG_CUDA_OK(cudaEventRecord(g_aux.ev_h0, st));
+        CBG_CUDA_OK(cudaStreamWaitEvent(g_aux.s3, g_aux.ev_h0, 0));
+      }
+      if (int rc = launch_node_gemm(gp, fork_p ? g_aux.s3 : st)) return rc;
+      if (fork_p) CBG_CUDA_OK(cudaEventRecord(g_aux.ev_p, g_aux.s3));
       NodeGemmArgs gd = g;
       gd.row_idx = ws.order; gd.n_rows_dev = ws.cnt + l + 1;
       gd.wt = g.wt + 256; gd.bias = g.bias + 256; gd.n_planes = 3; gd.tc_first_plane = 2;
       gd.out[0] = ws.plane[2]; gd.out[1] = ws.plane[3]; gd.out[2] = nullptr;
       if (int rc = launch_node_gemm(gd, st)) return rc;
+      if (fork_p) CBG_CUDA_OK(cudaStreamWaitEvent(st, g_aux.ev_p, 0));
     }
     if (overlap && x_pending) { CBG_CUDA_OK(cudaStreamWaitEvent(st, g_aux.ev_x, 0)); x_pending = false; }
     EdgeArgs e{};
@@ -210,6 +222,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     if (overlap) {
       CBG_CUDA_OK(cudaEventRecord(g_aux.ev_h, st));
       CBG_CUDA_OK(cudaStreamWaitEvent(sx, g_aux.ev_h, 0));
+      CBG_CUDA_OK(cudaStreamWaitEvent(g_aux.s4, g_aux.ev_h, 0));
     }
     // ---- H2X (uses the NEW h and the layer-input x): Pj planes for all nodes, Pi/q for generated nodes
     NodeGemmArgs gj{};
@@ -231,7 +244,11 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     gi.q_b1 = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_B1);
     gi.out_q = ws.hplane[4];
     gi.tc_planes = gj.tc_planes; gi.tc_first_plane = 2;
-    if (int rc = launch_node_gemm(gi, sx)) return rc;
+    if (int rc = launch_node_gemm(gi, overlap ? g_aux.s4 : sx)) return rc;     // beside gj
+    if (overlap) {
+      CBG_CUDA_OK(cudaEventRecord(g_aux.ev_gi, g_aux.s4));
+      CBG_CUDA_OK(cudaStreamWaitEvent(sx, g_aux.ev_gi, 0));
+    }
     EdgeArgs x = e;
     x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
     x.node_idx = gen_idx; x.n_nodes = n_gen; x.n_nodes_dev = nullptr; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr;
