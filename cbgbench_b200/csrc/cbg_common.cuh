@@ -65,11 +65,39 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// Blackwell packed fp32: FFMA2 / FMUL2 / FADD2 execute two IEEE-rn operations per issued instruction
+// (sm_100a; a scalar second operand is broadcast by the hardware).  Bit-identical to the scalar forms,
+// half the issue slots - the edge kernels are issue-limited, not FMA-pipe-limited.
 __device__ __forceinline__ void fma4(float4& acc, const float4 w, const float s) {
-  acc.x = fmaf(w.x, s, acc.x);
-  acc.y = fmaf(w.y, s, acc.y);
-  acc.z = fmaf(w.z, s, acc.z);
-  acc.w = fmaf(w.w, s, acc.w);
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __ffma2_rn(make_float2(w.x, w.y), ss, make_float2(acc.x, acc.y));
+  const float2 hi = __ffma2_rn(make_float2(w.z, w.w), ss, make_float2(acc.z, acc.w));
+  acc = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
+  const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 add4s(const float4 a, const float s) {
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __fadd2_rn(make_float2(a.x, a.y), ss);
+  const float2 hi = __fadd2_rn(make_float2(a.z, a.w), ss);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// a.x*b.x + a.y*b.y + a.z*b.z + a.w*b.w as (x,z | y,w) packed partial sums
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+  float2 t = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  t = __ffma2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), t);
+  return t.x + t.y;
+}
+// relu((a * rstd) * gamma + beta)
+__device__ __forceinline__ float4 ln_relu4(const float4 a, const float rstd, const float4 gamma, const float4 beta) {
+  const float2 rr = make_float2(rstd, rstd);
+  float2 lo = __fmul2_rn(make_float2(a.x, a.y), rr), hi = __fmul2_rn(make_float2(a.z, a.w), rr);
+  lo = __ffma2_rn(lo, make_float2(gamma.x, gamma.y), make_float2(beta.x, beta.y));
+  hi = __ffma2_rn(hi, make_float2(gamma.z, gamma.w), make_float2(beta.z, beta.w));
+  return make_float4(fmaxf(lo.x, 0.f), fmaxf(lo.y, 0.f), fmaxf(hi.x, 0.f), fmaxf(hi.y, 0.f));
 }
 
 // cooperative contiguous copy global -> shared, n floats (multiple of 4), both 16B aligned

@@ -146,7 +146,7 @@ __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane
       const int j = M.j[e0 + ee];
       const float4 pj = ldg4(pj_plane + (size_t)j * CBG_H + 4 * lane);
       const float4 r = ldg4(rc + M.slot[e0 + ee] * CBG_H + 4 * lane);
-      a[ee] = make_float4(pi.x + pj.x + r.x, pi.y + pj.y + r.y, pi.z + pj.z + r.z, pi.w + pj.w + r.w);
+      a[ee] = add4(add4(pi, pj), r);
     }
   } else {
 #pragma unroll
@@ -155,7 +155,7 @@ __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane
     t[ee] = M.t[e0 + ee];
     const float4 pj = ldg4(pj_plane + (size_t)j * CBG_H + 4 * lane);
     const float4 c = ld4(W.c + t[ee] * CBG_H + 4 * lane);
-    a[ee] = make_float4(pi.x + pj.x + c.x, pi.y + pj.y + c.y, pi.z + pj.z + c.z, pi.w + pj.w + c.w);
+    a[ee] = add4(add4(pi, pj), c);
   }
   const bool uniform = (t[0] == t[1]) && (t[0] == t[2]) && (t[0] == t[3]);   // warp-uniform
   if (uniform) {
@@ -184,18 +184,14 @@ __device__ __forceinline__ void first_layer4(const EdgeMeta& M, int e0, int lane
   allreduce4(s, lane);
 #pragma unroll
   for (int ee = 0; ee < 4; ++ee) {
-    const float mean = s[ee] * (1.f / 128.f);
-    a[ee].x -= mean; a[ee].y -= mean; a[ee].z -= mean; a[ee].w -= mean;
-    s[ee] = (a[ee].x * a[ee].x + a[ee].y * a[ee].y) + (a[ee].z * a[ee].z + a[ee].w * a[ee].w);
+    a[ee] = add4s(a[ee], -(s[ee] * (1.f / 128.f)));
+    s[ee] = dot4(a[ee], a[ee]);
   }
   allreduce4(s, lane);
 #pragma unroll
   for (int ee = 0; ee < 4; ++ee) {
     const float rstd = 1.f / sqrtf(s[ee] * (1.f / 128.f) + 1e-5f);
-    a[ee].x = fmaxf(fmaf(a[ee].x * rstd, gamma.x, beta.x), 0.f);
-    a[ee].y = fmaxf(fmaf(a[ee].y * rstd, gamma.y, beta.y), 0.f);
-    a[ee].z = fmaxf(fmaf(a[ee].z * rstd, gamma.z, beta.z), 0.f);
-    a[ee].w = fmaxf(fmaf(a[ee].w * rstd, gamma.w, beta.w), 0.f);
+    a[ee] = ln_relu4(a[ee], rstd, gamma, beta);
   }
 }
 
@@ -232,9 +228,15 @@ struct HeadReduce {
     for (int ee = 0; ee < 4; ++ee) out[ee] = lo[ee] + __shfl_xor_sync(CBG_FULL, hi[ee], 16 >> LVL);
   }
 };
+// level 3 evaluates its two leaves (head slots HP, HP+1) together so the dot products can use packed FMAs
 template <int HP, class Leaf>
-struct HeadReduce<4, HP, Leaf> {
-  static __device__ __forceinline__ void run(const Leaf& leaf, float (&out)[4]) { leaf.template eval<HP>(out); }
+struct HeadReduce<3, HP, Leaf> {
+  static __device__ __forceinline__ void run(const Leaf& leaf, float (&out)[4]) {
+    float lo[4], hi[4];
+    leaf.template eval2<HP>(lo, hi);
+#pragma unroll
+    for (int ee = 0; ee < 4; ++ee) out[ee] = lo[ee] + __shfl_xor_sync(CBG_FULL, hi[ee], 2);
+  }
 };
 // last step: split on the high edge bit (lane bit 0).  r0, r1 = totals for head lane>>1 and edges
 // 2*(lane&1), 2*(lane&1)+1 of the group.
@@ -254,10 +256,16 @@ struct ULeaf {
   const float4 (&a)[4];
   const float (&U)[4][CBG_HEADS];
   template <int HP>
-  __device__ __forceinline__ void eval(float (&out)[4]) const {
+  __device__ __forceinline__ void eval2(float (&lo)[4], float (&hi)[4]) const {
 #pragma unroll
-    for (int ee = 0; ee < 4; ++ee)
-      out[ee] = fmaf(a[ee].w, U[3][HP], fmaf(a[ee].z, U[2][HP], fmaf(a[ee].y, U[1][HP], a[ee].x * U[0][HP])));
+    for (int ee = 0; ee < 4; ++ee) {
+      float2 t = __fmul2_rn(make_float2(U[0][HP], U[0][HP + 1]), make_float2(a[ee].x, a[ee].x));
+      t = __ffma2_rn(make_float2(U[1][HP], U[1][HP + 1]), make_float2(a[ee].y, a[ee].y), t);
+      t = __ffma2_rn(make_float2(U[2][HP], U[2][HP + 1]), make_float2(a[ee].z, a[ee].z), t);
+      t = __ffma2_rn(make_float2(U[3][HP], U[3][HP + 1]), make_float2(a[ee].w, a[ee].w), t);
+      lo[ee] = t.x;
+      hi[ee] = t.y;
+    }
   }
 };
 // leaf = a[ee] . W[head][:] with the weight rows in shared memory ([16][128], lane-permuted head slot)
@@ -266,11 +274,11 @@ struct SmemLeaf {
   const float* w;      // base of the [16][128] matrix
   int lane;
   template <int HP>
-  __device__ __forceinline__ void eval(float (&out)[4]) const {
-    const float4 wv = ld4(w + (HP ^ (lane >> 1)) * CBG_H + 4 * lane);
+  __device__ __forceinline__ void eval2(float (&lo)[4], float (&hi)[4]) const {
+    const float4 w0 = ld4(w + (HP ^ (lane >> 1)) * CBG_H + 4 * lane);
+    const float4 w1 = ld4(w + ((HP + 1) ^ (lane >> 1)) * CBG_H + 4 * lane);
 #pragma unroll
-    for (int ee = 0; ee < 4; ++ee)
-      out[ee] = fmaf(a[ee].w, wv.w, fmaf(a[ee].z, wv.z, fmaf(a[ee].y, wv.y, a[ee].x * wv.x)));
+    for (int ee = 0; ee < 4; ++ee) { lo[ee] = dot4(a[ee], w0); hi[ee] = dot4(a[ee], w1); }
   }
 };
 
@@ -445,7 +453,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
         for (int dp = 0; dp < 8; ++dp) {
           const int f = half * 64 + hh * 8 + (dp ^ dx3);
           const float4 wv = ld4(s_w1 + f * CBG_H + 4 * lane);
-          lv[dp] = fmaf(wv.w, sv.w, fmaf(wv.z, sv.z, fmaf(wv.y, sv.y, wv.x * sv.x)));
+          lv[dp] = dot4(wv, sv);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) lv[k] += __shfl_xor_sync(CBG_FULL, lv[k + 4], 16);
