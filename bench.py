@@ -32,6 +32,8 @@ WORKLOADS = {
     'c3': (128, 300, 24, 'partial', {'cutoff_mode': 'radius', 'r_max': 10.0},
            'linker task, batch 128, radius graph r=10 A (cap 32), 1000 steps'),
     'c1': (1, 200, 24, 'denovo', {}, 'de novo, 1 pocket 200+24 atoms (plumbing case)'),
+    # ragged pockets 100..800 protein atoms (mean 450), 24 ligand atoms, context fixed: 32 pockets per GPU (256 over 8)
+    'c5': (32, None, 24, 'partial', {}, 'scaffold task, ragged pockets 100-800 atoms, 32 pockets per GPU (256 over 8 GPUs)'),
 }
 
 
@@ -117,9 +119,14 @@ def measured_peaks():
 
 def workload_batch(name, rank, n_graphs=None):
     from cbgbench_b200 import synthetic
+    import numpy as np
     B, n_prot, n_lig, gen_mode, enc, _ = WORKLOADS[name]
     B = n_graphs or B
-    return synthetic.make_batch([n_prot] * B, [n_lig] * B, seed=2024 + rank, gen_mode=gen_mode), enc
+    if n_prot is None:
+        sizes = [int(v) for v in np.random.RandomState(77 + rank).randint(100, 801, size=B)]
+    else:
+        sizes = [n_prot] * B
+    return synthetic.make_batch(sizes, [n_lig] * B, seed=2024 + rank, gen_mode=gen_mode), enc
 
 
 # ---------------------------------------------------------------------------------------------

@@ -168,7 +168,12 @@ class TargetDiffB200(nn.Module):
         rc_ptr, rc_bytes = None, 0
         if self.use_rcache:
             rc_bytes = L.cbg_rcache_bytes(N, den.num_layers)
-            rc_ptr, rc_bytes = self._rc.get(rc_bytes, dev)
+            have = self._rc.buf.numel() if self._rc.buf is not None and self._rc.buf.device == dev else 0
+            free_b, _ = torch.cuda.mem_get_info(dev)
+            if rc_bytes + 256 > have and rc_bytes > 0.6 * (free_b + have):
+                rc_bytes = 0          # batch too large for the cache on this GPU: fall back to recomputing the terms
+            else:
+                rc_ptr, rc_bytes = self._rc.get(rc_bytes, dev)
         plan = _lib.SamplePlan(
             blob=blob.data_ptr(), num_layers=den.num_layers, num_classes=self.num_classes,
             emb_wt=emb_wt.data_ptr(), h_lig_bias=h_lig_bias.data_ptr(), h_static=h_static.data_ptr(),
