@@ -317,6 +317,13 @@ def run_b200(args):
         host_batch = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
         h2d = sum(v.numel() * v.element_size() for v in host_batch.values() if torch.is_tensor(v))
         steps_e2e = min(args.e2e_steps, T_STEPS)
+        # warm-up of the public-API path (allocations, R-cache buffers, NCCL channels of the final gather)
+        model.sample(host_batch, num_steps=2, traj_mode='final')
+        if world > 1:
+            from cbgbench_b200 import sharding
+            gid0 = (batch['ligand_element_batch'] + rank * B).to(dev)
+            sharding.gather_final(torch.zeros(n_lig_tot, 3, device=dev), torch.zeros(n_lig_tot, dtype=torch.int64, device=dev),
+                                  gid0, counts=[n_lig_tot] * world)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
