@@ -397,3 +397,38 @@ def test_receptive_field_pruning_is_exact():
         for t in range(-1, T):
             assert torch.equal(a[t][0].cpu(), b[t][0].cpu()), (gen_mode, t)
             assert torch.equal(a[t][1].cpu(), b[t][1].cpu()), (gen_mode, t)
+
+
+@pytest.mark.parametrize('enc', [{'cutoff_mode': 'radius', 'r_max': 7.0}, {'k': 8}, {'k': 20}],
+                         ids=['radius7', 'k8', 'k20'])
+def test_sample_path_other_graph_modes_vs_oracle(enc):
+    """The fused sampling step (R-cache + pruning on) in radius mode and with k < 32: every step's atom
+    types bit-exact and coordinates within tolerance of the oracle trajectory."""
+    from oracle import diffusion as OD
+    T = 5
+    model, sd = make_model(T, device=dev(), **enc)
+    batch = synthetic.make_batch([160, 70, 33], [20, 11, 6], seed=131, gen_mode='partial')
+    n_lig = int(batch['ligand_pos'].shape[0])
+    pn, tu = synthetic.make_noise(T, n_lig, 13, seed=12)
+    traj = model.sample(batch, pos_noise=pn, type_uniform=tu)
+    want = OD.sample(sd, batch, T, pn, tu, k=enc.get('k', 32), cutoff_mode=enc.get('cutoff_mode', 'knn'),
+                     r_max=enc.get('r_max', 10.0))
+    for t in range(-1, T):
+        assert torch.equal(traj[t][1].cpu().argmax(-1), want[t][1].argmax(-1)), t
+        assert rel_err(traj[t][0].cpu(), want[t][0]) < TOL, t
+
+
+def test_knn_random_ragged_batches_bit_exact():
+    """Many random ragged batches (graph sizes 1..400, clustered and duplicated points)."""
+    from oracle import graph_ops as G
+    rs = np.random.RandomState(1234)
+    for trial in range(6):
+        sizes = [int(v) for v in rs.randint(1, 400, size=rs.randint(1, 9))]
+        x = (rs.normal(size=(sum(sizes), 3)) * rs.choice([0.5, 3.0, 10.0])).astype(np.float32)
+        if len(x) > 10:
+            x[rs.randint(0, len(x), size=5)] = x[rs.randint(0, len(x), size=5)]     # exact duplicates -> ties
+        x = torch.from_numpy(x)
+        bidx = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+        ptr = [0] + list(np.cumsum(sizes))
+        k = int(rs.choice([32, 17, 3]))
+        assert torch.equal(cuda_neighbors(x, bidx, k=k), G.neighbor_table(x, ptr, k=k)), (trial, sizes, k)
