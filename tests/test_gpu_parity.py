@@ -432,3 +432,54 @@ def test_knn_random_ragged_batches_bit_exact():
         ptr = [0] + list(np.cumsum(sizes))
         k = int(rs.choice([32, 17, 3]))
         assert torch.equal(cuda_neighbors(x, bidx, k=k), G.neighbor_table(x, ptr, k=k)), (trial, sizes, k)
+
+
+@pytest.mark.parametrize('layers,classes,wseed', [(3, 8, 1), (6, 16, 2), (9, 13, 3)], ids=['L3-K8', 'L6-K16', 'L9-K13-seed3'])
+def test_other_depths_class_counts_and_weights_vs_oracle(layers, classes, wseed):
+    """num_layers / num_atomtype other than the de-novo defaults (the reference infers the class count from
+    the featuriser mode, configuration.py:13-38) and different weight draws: forward + 3 sampling steps."""
+    from cbgbench_b200.targetdiff import TargetDiffB200
+    from oracle import denoiser as ODn, diffusion as OD
+    T = 3
+    cfg = synthetic.targetdiff_config(num_steps=T, num_layers=layers, num_atomtype=classes)
+    model = TargetDiffB200(cfg)
+    sd = synthetic.seeded_state_dict(model, seed=wseed)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev()).eval()
+    batch = synthetic.make_batch([140, 55], [17, 9], seed=141 + wseed, num_classes=classes)
+    # single forward through the nn.Module seam
+    c_lig = F.one_hot(batch['ligand_atom_type'], classes).float()
+    h_lig, h_rec = OD.context_embed(sd, c_lig, batch['protein_atom_feature'], batch['protein_aa_type'],
+                                    batch['ligand_lig_flag'], batch['protein_lig_flag'])
+    sort_idx, bidx, is_lig = OD.compose(batch['ligand_element_batch'], batch['protein_element_batch'])
+    x = torch.cat([batch['protein_pos'], batch['ligand_pos']], 0)[sort_idx]
+    h = torch.cat([h_rec, h_lig], 0)[sort_idx]
+    xo, ho, co = ODn.unitransformer_forward(sd, x, h, bidx, is_lig, is_lig)
+    d = dev()
+    xg, hg, cg = model.denoiser(x.to(d), h.to(d), bidx.to(d), is_lig.to(d), is_lig.to(d))
+    assert cg.shape == (x.shape[0], classes)
+    assert rel_err(xg.cpu(), xo) < TOL and rel_err(hg.cpu(), ho) < TOL and rel_err(cg.cpu(), co) < TOL
+    # fused sampling steps
+    n_lig = int(batch['ligand_pos'].shape[0])
+    pn, tu = synthetic.make_noise(T, n_lig, classes, seed=13)
+    traj = model.sample(batch, pos_noise=pn, type_uniform=tu)
+    want = OD.sample(sd, batch, T, pn, tu, num_classes=classes)
+    for t in range(-1, T):
+        assert torch.equal(traj[t][1].cpu().argmax(-1), want[t][1].argmax(-1)), t
+        assert rel_err(traj[t][0].cpu(), want[t][0]) < TOL, t
+
+
+def test_sample_driver_single_gpu(tmp_path):
+    """The sample.py-style driver (section 8 row f1): per-pocket results, reproducible from the seed."""
+    from cbgbench_b200 import sample_driver
+    out = str(tmp_path / 'res.pt')
+    argv = ['--pockets', '5', '--batch-size', '2', '--n-prot', '40', '--n-lig', '6', '--steps', '4', '--layers', '2',
+            '--out', out]
+    a = sample_driver.main(argv)
+    b = sample_driver.main(argv)
+    saved = torch.load(out)
+    assert len(a) == len(saved) == 5
+    for ra, rb in zip(a, b):
+        assert ra['pos'].shape == (6, 3) and ra['v'].shape == (6,)
+        assert torch.equal(ra['pos'], rb['pos']) and torch.equal(ra['v'], rb['v'])
+        assert torch.isfinite(ra['pos']).all() and int(ra['v'].max()) < 13
