@@ -121,9 +121,17 @@ struct AuxStream {
   cudaStream_t s2 = nullptr, s3 = nullptr, s4 = nullptr;   // H2X chain, X2H source-plane GEMM, H2X destination GEMM
   cudaEvent_t ev_h = nullptr, ev_x = nullptr, ev_h0 = nullptr, ev_p = nullptr, ev_gi = nullptr;
   int state = -1;   // -1 unknown, 0 disabled, 1 ready
-} g_aux;
+};
+constexpr int kMaxDevices = 64;
+AuxStream g_aux_dev[kMaxDevices];   // streams and events belong to a device: one set per device the caller uses
+AuxStream g_aux_off;                // state 0: what aux() returns when overlap is unavailable
+#define g_aux (*g_aux_cur)
+thread_local AuxStream* g_aux_cur = &g_aux_off;
 
 int aux_ready() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { g_aux_cur = &g_aux_off; g_aux_off.state = 0; return 0; }
+  g_aux_cur = &g_aux_dev[dev];
   if (g_aux.state >= 0) return g_aux.state;
   const char* e = getenv("CBG_OVERLAP");
   if (e && strcmp(e, "0") == 0) { g_aux.state = 0; return 0; }
@@ -152,13 +160,22 @@ bool prune_enabled() {
   return on != 0;
 }
 
+// compact the moving edges before computing their gates (ws.w is free until the first X2H): CBG_GATE_COMPACT=0
+// keeps the in-place kernel
+bool gate_compact() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("CBG_GATE_COMPACT"); on = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  return on != 0;
+}
+
 // graph build + gate + layers on an initialised workspace (x4, h valid)
 int run_core(const float* blob, int num_layers, const Workspace& ws, const int* graph_ptr, int n_graphs,
              int max_graph_nodes, long long n_nodes, const int* gen_idx, int n_gen, int mode, int k,
              float r_max, const float* rcache, const int* cls_idx, int n_cls, bool prune, cudaStream_t st) {
   if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
-  if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, ws.nbr, st)) return rc;
-  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, rcache ? ws.sew : nullptr, ws.ew, st)) return rc;
+  if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, rcache ? ws.snbr : nullptr, ws.nbr, st)) return rc;
+  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, rcache ? ws.sew : nullptr,
+                                    gate_compact() ? (int*)ws.w : nullptr, ws.ew, st)) return rc;
   const float* layers = blob + cbg_layout::kGlobalFloats;
   // Receptive-field pruning (only when the caller consumes nothing but the generated / classified rows):
   // layer l updates h only for the nodes that can still reach such a row through the remaining layers.
@@ -348,7 +365,7 @@ int32_t cbg_build_neighbors_f32(const float* x, const int32_t* graph_ptr, int32_
   // flags are irrelevant for the neighbour search: pack with zeros
   CBG_CUDA_OK(cudaMemsetAsync(ws.nbr, 0, (size_t)n_nodes, st));   // reuse as a zero flag array
   if (int rc = cbg_launch_pack_x4(x, (const unsigned char*)ws.nbr, (const unsigned char*)ws.nbr, n_nodes, ws.x4, st)) return rc;
-  return cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, nbr, st);
+  return cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, nullptr, nbr, st);
 }
 
 int32_t cbg_edge_gate_f32(const float* blob, const float* x, const int32_t* nbr, int64_t n_nodes, float* ew,
@@ -358,7 +375,7 @@ int32_t cbg_edge_gate_f32(const float* blob, const float* x, const int32_t* nbr,
   cudaStream_t st = (cudaStream_t)stream;
   CBG_CUDA_OK(cudaMemsetAsync(ws.nbr, 0, (size_t)n_nodes, st));
   if (int rc = cbg_launch_pack_x4(x, (const unsigned char*)ws.nbr, (const unsigned char*)ws.nbr, n_nodes, ws.x4, st)) return rc;
-  return cbg_launch_edge_gate(blob, ws.x4, nbr, n_nodes, nullptr, ew, st);
+  return cbg_launch_edge_gate(blob, ws.x4, nbr, n_nodes, nullptr, nullptr, ew, st);
 }
 
 int32_t cbg_denoiser_forward_f32(const float* blob, int32_t num_layers, int32_t num_classes, const float* x,
@@ -481,8 +498,8 @@ int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, 
     const int64_t need = cbg_rcache_bytes(plan->n_nodes, plan->num_layers);
     if ((int64_t)plan->rcache_bytes < need) { cbg_set_error("rcache too small: have %zu bytes, need %lld", plan->rcache_bytes, (long long)need); return 1; }
     if (int rc = cbg_launch_knn(ws.x4, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes, CBG_MODE_KNN, CBG_KMAX,
-                                0.f, 1, ws.snbr, st)) return rc;
-    if (int rc = cbg_launch_edge_gate(plan->blob, ws.x4, ws.snbr, plan->n_nodes, nullptr, ws.sew, st)) return rc;
+                                0.f, 1, nullptr, ws.snbr, st)) return rc;
+    if (int rc = cbg_launch_edge_gate(plan->blob, ws.x4, ws.snbr, plan->n_nodes, nullptr, nullptr, ws.sew, st)) return rc;
     if (int rc = cbg_launch_rcache(plan->blob + cbg_layout::kGlobalFloats, plan->num_layers, ws.x4, ws.snbr,
                                    (int)plan->n_nodes, plan->rcache, st)) return rc;
   }

@@ -17,6 +17,15 @@ void cbg_set_error(const char* fmt, ...);
     }                                                                            \
   } while (0)
 
+// One-time per-DEVICE setup guards: kernel attributes (opt-in shared memory) belong to a device's context, so a
+// process that drives several GPUs must set them once on each.
+constexpr int CBG_MAX_DEVICES = 64;
+inline bool& cbg_dev_flag(bool (&flags)[CBG_MAX_DEVICES]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= CBG_MAX_DEVICES) dev = 0;
+  return flags[dev];
+}
+
 extern long long g_cbg_launches;
 extern int g_cbg_prof_on;
 // kernel families for the optional per-kernel CUDA-event profile (bench.py roofline)

@@ -8,11 +8,14 @@
 // graph.cu
 // static_only != 0: neighbour search restricted to nodes without the generate bit (centres with
 // the bit get an empty row) - the static-only kNN lists behind the R-cache
+// snbr (optional): static-only lists of the same graphs -> incremental search for non-moving centres
 int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max_graph_nodes, int mode,
-                   int k, float r_max, int static_only, int* nbr, cudaStream_t st);
+                   int k, float r_max, int static_only, const int* snbr, int* nbr, cudaStream_t st);
 // ew_static (optional): gates of the static-only neighbour lists, reused for static edges
+// glist (optional, with ew_static): scratch of 64 + 32*n_nodes ints; the moving edges are compacted into it
+// and their gates computed by a second, dense launch
 int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
-                         const float* ew_static, float* ew, cudaStream_t st);
+                         const float* ew_static, int* glist, float* ew, cudaStream_t st);
 
 // Receptive-field pruning (sampling path): depth[i] = last layer whose X2H output of node i can still
 // influence a generated / classified atom (-2: never).  order[] lists nodes by decreasing depth,

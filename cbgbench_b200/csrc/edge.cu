@@ -660,7 +660,8 @@ int launch_h2x(const EdgeArgs& a, cudaStream_t st) {
 }  // namespace
 
 int cbg_edge_init(void) {
-  static bool done = false;
+  static bool done_dev[CBG_MAX_DEVICES] = {};
+  bool& done = cbg_dev_flag(done_dev);
   if (done) return 0;
   int dev = 0;
   CBG_CUDA_OK(cudaGetDevice(&dev));
@@ -680,7 +681,8 @@ int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, con
                       float* rcache, cudaStream_t st) {
   if (n_nodes <= 0 || num_layers <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
-  static bool attr = false;
+  static bool attr_dev[CBG_MAX_DEVICES] = {};
+  bool& attr = cbg_dev_flag(attr_dev);
   if (!attr) {
     CBG_CUDA_OK(cudaFuncSetAttribute(rcache_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRcSmem));
     attr = true;

@@ -43,7 +43,8 @@ __device__ __forceinline__ u64 bitonic_merge32(u64 v, int lane) {
 // bit-identical to the oracle (oracle/graph_ops.py).
 __global__ void __launch_bounds__(256) knn_kernel(const float4* __restrict__ x4,
                                                   const int* __restrict__ graph_ptr, int k, int mode,
-                                                  float r2max, int static_only, int* __restrict__ nbr) {
+                                                  float r2max, int static_only, const int* __restrict__ snbr,
+                                                  int* __restrict__ nbr) {
   extern __shared__ float4 xs[];
   const int g = blockIdx.y;
   const int s = graph_ptr[g];
@@ -61,10 +62,23 @@ __global__ void __launch_bounds__(256) knn_kernel(const float4* __restrict__ x4,
       nbr[(size_t)(s + c) * CBG_KMAX + lane] = -1;
       continue;
     }
+    // Incremental search for a non-moving centre: its 32 nearest NON-moving neighbours are known (static list,
+    // same keys, already sorted), so only the moving atoms of the graph have to be merged in.
+    const bool incremental = (snbr != nullptr) && !(node_flags(xc) & 2);
+    if (incremental) {
+      const int js = snbr[(size_t)(s + c) * CBG_KMAX + lane];
+      if (js >= 0) {
+        const float4 xj = xs[js - s];
+        const float dx = xc.x - xj.x, dy = xc.y - xj.y, dz = xc.z - xj.z;
+        const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        best = ((u64)__float_as_uint(d2) << 32) | (u64)(unsigned)(js - s);
+      }
+    }
     for (int base = 0; base < n; base += 32) {
       const int j = base + lane;
       u64 key = kInfKey;
-      if (j < n && j != c && !(static_only && (node_flags(xs[j]) & 2))) {
+      if (j < n && j != c && !(static_only && (node_flags(xs[j]) & 2)) &&
+          !(incremental && !(node_flags(xs[j]) & 2))) {
         const float4 xj = xs[j];
         const float dx = xc.x - xj.x, dy = xc.y - xj.y, dz = xc.z - xj.z;
         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -89,18 +103,18 @@ __global__ void __launch_bounds__(256) knn_kernel(const float4* __restrict__ x4,
 // Edge gate: one thread per (node, slot).  e_w = sigmoid(W1 . relu(LN(W0 g(d) + b0)) + b1).
 constexpr int kGateSmemFloats = 20 * 160 + 160 + 320 + 160 + 32;
 
+__device__ __forceinline__ float gate_value(const float* sm, const float4 xi, const float4 xj);
+
+// `glist` (optional, needs ew_static): instead of computing the gates of the moving edges in place (a few
+// scattered lanes per warp), append their slot indices to glist[64..] (count in glist[0]) and leave the
+// arithmetic to edge_gate_list_kernel, which runs it on dense warps.
 __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict__ gw,  // GATE_W0T..GATE_RBF
                                                         const float4* __restrict__ x4,
                                                         const int* __restrict__ nbr, long long n_slots,
                                                         const float* __restrict__ ew_static,
+                                                        int* __restrict__ glist,
                                                         float* __restrict__ ew) {
   __shared__ __align__(16) float sm[kGateSmemFloats];
-  const float* w0t = sm;                 // [20][160]
-  const float* b0 = sm + 3200;
-  const float* gamma = b0 + 160;
-  const float* beta = gamma + 160;
-  const float* w1 = beta + 160;
-  const float* rbf = w1 + 160;           // offsets[20], coeff, b1
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one warp = one node's 32 slots
   const bool in_range = idx < n_slots;   // n_slots is a multiple of 32: whole warps are in or out
   int j = -1, i = 0;
@@ -125,10 +139,48 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
     }
     if (j < 0) ew[idx] = 0.f;
   }
+  if (glist != nullptr) {
+    const unsigned m = __ballot_sync(CBG_FULL, need);
+    if (m) {
+      const int lane = threadIdx.x & 31;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(glist, __popc(m));
+      base = __shfl_sync(CBG_FULL, base, 0);
+      if (need) glist[64 + base + __popc(m & ((1u << lane) - 1u))] = (int)idx;
+    }
+    return;
+  }
   if (!__syncthreads_or(need ? 1 : 0)) return;     // nothing to compute in this CTA: skip the weight staging
   block_copy_f4(sm, gw, kGateSmemFloats);
   __syncthreads();
   if (!need) return;
+  ew[idx] = gate_value(sm, xi, xj);
+}
+
+// gates of the compacted moving edges (any order: every entry owns its slot)
+__global__ void __launch_bounds__(128) edge_gate_list_kernel(const float* __restrict__ gw,
+                                                             const float4* __restrict__ x4,
+                                                             const int* __restrict__ nbr,
+                                                             const int* __restrict__ glist,
+                                                             float* __restrict__ ew) {
+  __shared__ __align__(16) float sm[kGateSmemFloats];
+  const int n = glist[0];
+  if ((long long)blockIdx.x * blockDim.x >= n) return;
+  block_copy_f4(sm, gw, kGateSmemFloats);
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int idx = glist[64 + t];
+  ew[idx] = gate_value(sm, x4[idx / CBG_KMAX], x4[nbr[idx]]);
+}
+
+__device__ __forceinline__ float gate_value(const float* sm, const float4 xi, const float4 xj) {
+  const float* w0t = sm;                 // [20][160]
+  const float* b0 = sm + 3200;
+  const float* gamma = b0 + 160;
+  const float* beta = gamma + 160;
+  const float* w1 = beta + 160;
+  const float* rbf = w1 + 160;           // offsets[20], coeff, b1
   const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
   const float d = sqrtf(rx * rx + ry * ry + rz * rz);
   float g[CBG_NRBF];
@@ -163,7 +215,7 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
     o = fmaf(ww.z, fmaxf(fmaf(hid[u].z * rstd, ga.z, be.z), 0.f), o);
     o = fmaf(ww.w, fmaxf(fmaf(hid[u].w * rstd, ga.w, be.w), 0.f), o);
   }
-  ew[idx] = 1.f / (1.f + expf(-o));
+  return 1.f / (1.f + expf(-o));
 }
 
 // ---- receptive-field depth ------------------------------------------------------------------------
@@ -254,7 +306,7 @@ int cbg_launch_depth(const int* nbr, const int* graph_ptr, int n_graphs, int max
 }
 
 int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max_graph_nodes, int mode,
-                   int k, float r_max, int static_only, int* nbr, cudaStream_t st) {
+                   int k, float r_max, int static_only, const int* snbr, int* nbr, cudaStream_t st) {
   if (n_graphs <= 0) return 0;
   if (k < 1 || k > CBG_KMAX) { cbg_set_error("k=%d outside [1,%d]", k, CBG_KMAX); return 1; }
   const size_t smem = (size_t)max_graph_nodes * sizeof(float4);
@@ -263,25 +315,35 @@ int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max
                   max_graph_nodes, 200 * 1024 / 16);
     return 1;
   }
-  static size_t smem_attr = 0;
+  static size_t smem_attr_dev[CBG_MAX_DEVICES] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= CBG_MAX_DEVICES) dev = 0;
+  size_t& smem_attr = smem_attr_dev[dev];
   if (smem > 48 * 1024 && smem > smem_attr) {
     CBG_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
   dim3 grid((max_graph_nodes + 63) / 64, n_graphs);
   CBG_PROF_BEGIN(CBG_K_KNN, st);
-  knn_kernel<<<grid, 256, smem, st>>>(x4, graph_ptr, k, mode, r_max * r_max, static_only, nbr);
+  knn_kernel<<<grid, 256, smem, st>>>(x4, graph_ptr, k, mode, r_max * r_max, static_only, snbr, nbr);
   CBG_LAUNCHED(CBG_K_KNN, st);
   return 0;
 }
 
 int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
-                         const float* ew_static, float* ew, cudaStream_t st) {
+                         const float* ew_static, int* glist, float* ew, cudaStream_t st) {
   const long long n_slots = n_nodes * CBG_KMAX;
   if (n_slots == 0) return 0;
   const float* gw = blob_global + cbg_layout::global_offset(CBG_GF_GATE_W0T);
   CBG_PROF_BEGIN(CBG_K_GATE, st);
-  edge_gate_kernel<<<(unsigned)((n_slots + 127) / 128), 128, 0, st>>>(gw, x4, nbr, n_slots, ew_static, ew);
+  const unsigned grid = (unsigned)((n_slots + 127) / 128);
+  if (ew_static == nullptr) glist = nullptr;
+  if (glist) CBG_CUDA_OK(cudaMemsetAsync(glist, 0, sizeof(int), st));
+  edge_gate_kernel<<<grid, 128, 0, st>>>(gw, x4, nbr, n_slots, ew_static, glist, ew);
+  if (glist) {
+    edge_gate_list_kernel<<<grid, 128, 0, st>>>(gw, x4, nbr, glist, ew);
+    g_cbg_launches += 1;
+  }
   CBG_LAUNCHED(CBG_K_GATE, st);
   return 0;
 }

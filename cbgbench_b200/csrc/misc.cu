@@ -210,7 +210,8 @@ int cbg_launch_classifier(const float* blob_global, const float* h, const int* r
                           int num_classes, float* logits, cudaStream_t st) {
   if (n_rows <= 0) return 0;
   if (num_classes < 1 || num_classes > CBG_MAXCLS) { cbg_set_error("num_classes=%d outside [1,%d]", num_classes, CBG_MAXCLS); return 1; }
-  static bool attr_set = false;
+  static bool attr_dev[CBG_MAX_DEVICES] = {};
+  bool& attr_set = cbg_dev_flag(attr_dev);
   if (!attr_set) {
     CBG_CUDA_OK(cudaFuncSetAttribute(classifier_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kClsFloats * 4));
     attr_set = true;

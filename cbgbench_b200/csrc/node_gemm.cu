@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(256, 2) node_gemm_kernel(NodeGemmArgs p) {
 
 int cbg_launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st) {
   if (a.n_rows <= 0) return 0;
-  static bool attr_set = false;
+  static bool attr_dev[CBG_MAX_DEVICES] = {};
+  bool& attr_set = cbg_dev_flag(attr_dev);
   if (!attr_set) {
     CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     attr_set = true;

@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(320, 1) node_gemm_ws_kernel(NodeGemmArgs p) {
 }
 
 int launch_ws(const NodeGemmArgs& a, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_dev[CBG_MAX_DEVICES] = {};
+  bool& attr_set = cbg_dev_flag(attr_dev);
   if (!attr_set) {
     CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_TOTAL));
     attr_set = true;
@@ -531,7 +532,8 @@ int launch_ws(const NodeGemmArgs& a, cudaStream_t st) {
 template <int CL, int NSTAGE>
 int launch_tc(const NodeGemmArgs& a, cudaStream_t st) {
   constexpr uint32_t SMEM_TOTAL = smem_total(NSTAGE);
-  static bool attr_set = false;
+  static bool attr_dev[CBG_MAX_DEVICES] = {};
+  bool& attr_set = cbg_dev_flag(attr_dev);
   if (!attr_set) {
     CBG_CUDA_OK(cudaFuncSetAttribute(node_gemm_tc_kernel<CL, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
     attr_set = true;
