@@ -537,6 +537,35 @@ int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* co
   return 0;
 }
 
+int32_t cbg_sbdd_step_f32(const cbg_sample_plan* plan, const cbg_sbdd_coef* coef, const float* x_t, const float* c_t,
+                          const float* x_noise, const float* c_noise, float* x_next, float* c_next,
+                          float* x_pred, float* logits, void* stream) {
+  if (!plan || !coef) { cbg_set_error("null plan/coef"); return 1; }
+  if (plan->rcache) { cbg_set_error("DiffSBDD moves the pocket every step: the plan must not carry an R-cache"); return 1; }
+  if (coef->mode != 0 && coef->mode != 1) { cbg_set_error("cbg_sbdd_coef.mode must be 0 or 1"); return 1; }
+  Workspace ws;
+  if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = plan->num_classes;
+  if (K < 1 || K > CBG_MAXCLS) { cbg_set_error("num_classes=%d outside [1,%d]", K, CBG_MAXCLS); return 1; }
+  if (int rc = cbg_launch_step_init(x_t, c_t, plan->lig_node, plan->n_lig, K, plan->emb_wt, plan->h_lig_bias,
+                                    plan->h_static, plan->n_nodes, ws.x4, ws.h, st)) return rc;
+  if (int rc = run_core(plan->blob, plan->num_layers, ws, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes,
+                        plan->n_nodes, plan->gen_node, plan->n_gen, plan->mode, plan->k, plan->r_max, nullptr,
+                        plan->lig_node, plan->n_lig, plan->prune != 0 && prune_enabled(), st)) return rc;
+  float* lg = logits ? logits : ws.w;
+  if (int rc = cbg_launch_classifier(plan->blob, ws.h, plan->lig_node, plan->n_lig, K, lg, st)) return rc;
+  if (x_pred) {
+    if (int rc = cbg_launch_gather_x(ws.x4, plan->lig_node, plan->n_lig, x_pred, st)) return rc;
+  }
+  SbddArgs r{};
+  r.x4 = ws.x4; r.graph_ptr = plan->graph_ptr; r.lig_node = plan->lig_node; r.n_lig = plan->n_lig;
+  r.num_classes = K; r.n_graphs = plan->n_graphs; r.logits = lg; r.x_t = x_t; r.c_t = c_t;
+  r.x_noise = x_noise; r.c_noise = c_noise; r.a = coef->a; r.b = coef->b; r.s = coef->s; r.mode = coef->mode;
+  r.x_next = x_next; r.c_next = c_next;
+  return cbg_launch_sbdd_reverse(r, st);
+}
+
 int32_t cbg_reverse_step_f32(const cbg_step_coef* coef, const float* x0_pred, const float* logits, const float* x_t,
                              const float* c_t, const uint8_t* gen, const float* pos_noise, const float* type_uniform,
                              int32_t n, int32_t num_classes, float* x_next, float* c_next, int64_t* v_next,

@@ -104,3 +104,27 @@ struct ReverseArgs {
 };
 // logvar = posterior_logvar[t]; nonzero = 0 at t == 0 else 1
 int cbg_launch_reverse(const ReverseArgs& a, float logvar, float nonzero, cudaStream_t st);
+
+// DiffSBDD reverse step: one CTA per graph.
+//   mode 0  zs = z_t / a - b * eps_pred + s * noise              (sample_p_zs_given_zt, diffusion_scheduler.py:1005-1039)
+//   mode 1  zs = a * (z_t - b * eps_pred) + s * noise            (sample_p_xh_given_z0, diffsbdd.py:323-360; a = 1/alpha_0)
+// for the coordinates (eps_pred = the denoiser's output coordinates of the ligand atoms, read from x4) followed by
+// the COM projection remove_mean_batch (diffusion_scheduler.py:706-710): the mean of zs over the graph's ligand
+// atoms is subtracted from zs AND from the pocket atoms of the graph (x4 rows without the ligand bit).
+// Types: mode 0 the same update without projection (eps_pred = logits), mode 1 c_next = 4 * c_t.
+struct SbddArgs {
+  float4* x4;               // [N] node coordinates + flags (pocket rows are shifted in place)
+  const int* graph_ptr;     // [B+1]
+  const int* lig_node;      // [n_lig] ascending composed index of every ligand atom
+  int n_lig, num_classes, n_graphs;
+  const float* logits;      // [n_lig,K]
+  const float* x_t;         // [n_lig,3]
+  const float* c_t;         // [n_lig,K]
+  const float* x_noise;     // [n_lig,3]
+  const float* c_noise;     // [n_lig,K]
+  float a, b, s;
+  int mode;
+  float* x_next;            // [n_lig,3]
+  float* c_next;            // [n_lig,K]
+};
+int cbg_launch_sbdd_reverse(const SbddArgs& a, cudaStream_t st);

@@ -171,7 +171,85 @@ __global__ void __launch_bounds__(128) reverse_kernel(ReverseArgs p, float logva
   for (int c = 0; c < K; ++c) p.c_next[(size_t)a * K + c] = (c == v) ? 1.f : 0.f;
 }
 
+// DiffSBDD reverse step + COM projection, one CTA per graph (see SbddArgs)
+__device__ __forceinline__ int lower_bound_i32(const int* __restrict__ a, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(128) sbdd_reverse_kernel(SbddArgs p) {
+  __shared__ int s_rng[2];
+  __shared__ float s_red[4][3];
+  __shared__ float s_mean[3];
+  const int g = blockIdx.x;
+  const int ns = p.graph_ptr[g], ne = p.graph_ptr[g + 1];
+  if (threadIdx.x == 0) {
+    s_rng[0] = lower_bound_i32(p.lig_node, p.n_lig, ns);
+    s_rng[1] = lower_bound_i32(p.lig_node, p.n_lig, ne);
+  }
+  __syncthreads();
+  const int lo = s_rng[0], hi = s_rng[1];
+  float sum[3] = {0.f, 0.f, 0.f};
+  for (int a = lo + threadIdx.x; a < hi; a += blockDim.x) {
+    const float4 pr = p.x4[p.lig_node[a]];
+    const float pred[3] = {pr.x, pr.y, pr.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float zt = p.x_t[3 * a + c], nz = __fmul_rn(p.s, p.x_noise[3 * a + c]);
+      const float mu = p.mode == 0 ? __fsub_rn(__fdiv_rn(zt, p.a), __fmul_rn(p.b, pred[c]))
+                                   : __fmul_rn(p.a, __fsub_rn(zt, __fmul_rn(p.b, pred[c])));
+      const float zs = __fadd_rn(mu, nz);
+      p.x_next[3 * a + c] = zs;
+      sum[c] += zs;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) sum[c] = warp_sum(sum[c]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) s_red[threadIdx.x >> 5][c] = sum[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const float t = (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
+    const int cnt = hi - lo;
+    s_mean[threadIdx.x] = __fdiv_rn(t, (float)(cnt > 0 ? cnt : 1));     // scatter_mean: sum / max(count, 1)
+  }
+  __syncthreads();
+  const float m[3] = {s_mean[0], s_mean[1], s_mean[2]};
+  for (int a = lo + threadIdx.x; a < hi; a += blockDim.x) {          // same thread wrote these entries
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p.x_next[3 * a + c] = __fsub_rn(p.x_next[3 * a + c], m[c]);
+  }
+  for (int i = ns + threadIdx.x; i < ne; i += blockDim.x) {
+    float4 v = p.x4[i];
+    if ((node_flags(v) & 1) == 0) {                                    // pocket atom
+      v.x = __fsub_rn(v.x, m[0]); v.y = __fsub_rn(v.y, m[1]); v.z = __fsub_rn(v.z, m[2]);
+      p.x4[i] = v;
+    }
+  }
+  const int K = p.num_classes;
+  for (long long e = (long long)lo * K + threadIdx.x; e < (long long)hi * K; e += blockDim.x) {
+    const float ct = p.c_t[e];
+    p.c_next[e] = p.mode == 0
+        ? __fadd_rn(__fsub_rn(__fdiv_rn(ct, p.a), __fmul_rn(p.b, p.logits[e])), __fmul_rn(p.s, p.c_noise[e]))
+        : __fmul_rn(ct, 4.f);
+  }
+}
+
 }  // namespace
+
+int cbg_launch_sbdd_reverse(const SbddArgs& a, cudaStream_t st) {
+  if (a.n_graphs <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_REVERSE, st);
+  sbdd_reverse_kernel<<<a.n_graphs, 128, 0, st>>>(a);
+  CBG_LAUNCHED(CBG_K_REVERSE, st);
+  return 0;
+}
 
 int cbg_launch_pack_x4(const float* x, const unsigned char* lig_flag, const unsigned char* gen_flag,
                        long long n, float4* x4, cudaStream_t st) {

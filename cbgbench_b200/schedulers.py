@@ -94,3 +94,74 @@ class TypeVPTables(VPTables):
         self.log_one_minus_alphas_v = _frozen(one_minus(log_a))
         self.log_alphas_cumprod_v = _frozen(log_acp)
         self.log_one_minus_alphas_cumprod_v = _frozen(one_minus(log_acp))
+
+
+# ---- DiffSBDD: variational gamma schedule ---------------------------------------
+
+def polynomial_gamma(timesteps, power=2.0, precision=5e-4):
+    """gamma[T+1] of the 'polynomial_<power>' schedule, float64
+    (repo/models/diffusion/schedule_utils.py:7-21 clip_noise_schedule, :45-59 polynomial_schedule, :80-92)."""
+    grid = np.linspace(0, timesteps + 1, timesteps + 1)
+    a2 = (1 - np.power(grid / (timesteps + 1), power)) ** 2
+    ratio = np.clip(np.concatenate([np.ones(1), a2])[1:] / np.concatenate([np.ones(1), a2])[:-1], a_min=0.001, a_max=1.0)
+    a2 = (1 - 2 * precision) * np.cumprod(ratio, axis=0) + precision
+    return -(np.log(a2) - np.log(1 - a2))
+
+
+class PredefinedNoiseScheduleTable(nn.Module):
+    """Lookup table ``gamma`` (PredefinedNoiseSchedule, schedule_utils.py:62-96); state-dict key ``gamma``."""
+
+    def __init__(self, noise_schedule, timesteps, precision):
+        super().__init__()
+        self.timesteps = timesteps
+        parts = noise_schedule.split('_')
+        if parts[0] != 'polynomial' or len(parts) != 2:
+            # the reference's 'cosine' branch returns None (schedule_utils.py:25-41) and cannot be constructed
+            raise NotImplementedError(f"noise schedule '{noise_schedule}': only 'polynomial_<power>' exists")
+        self.gamma = _frozen(polynomial_gamma(timesteps, power=float(parts[1]), precision=precision))
+
+
+class DiffsbddVariationalTables(nn.Module):
+    """DiffsbddVariationalScheduler (diffusion_scheduler.py:575-584, 670-672) as a table container plus the
+    host-side scalars of one reverse step.  All graphs of a batch share (s, t) during sampling
+    (diffsbdd.py:283-287), so sample_p_zs_given_zt (:1005-1039) needs three numbers per step; they are computed
+    with the reference's own fp32 torch expressions on the CPU copy of the table."""
+
+    def __init__(self, num_timestep, type='polynomial_2'):
+        super().__init__()
+        if type == 'learned':
+            raise NotImplementedError("'learned' gamma network (GammaNetwork) is not used by any shipped config")
+        self.num_timestep = num_timestep
+        self.gamma = PredefinedNoiseScheduleTable(type, timesteps=num_timestep, precision=5e-4)
+
+    def _gamma_host(self):
+        p = self.gamma.gamma
+        key = (p.data_ptr(), p._version)
+        if self.__dict__.get('_host_key') != key:
+            self.__dict__['_host_gamma'] = p.detach().to('cpu', torch.float32).clone()
+            self.__dict__['_host_key'] = key
+        return self.__dict__['_host_gamma']
+
+    def gamma_at(self, t):
+        """PredefinedNoiseSchedule.forward (schedule_utils.py:94-96) on a CPU tensor t in [0, 1]."""
+        return self._gamma_host()[torch.round(t * self.num_timestep).long()]
+
+    def step_scalars(self, t_idx):
+        """(alpha_t|s, sigma2_t|s / alpha_t|s / sigma_t, sigma_t|s * sigma_s / sigma_t) for s = t_idx / T,
+        t = (t_idx + 1) / T  (diffusion_scheduler.py:978-1003, 1008-1024)."""
+        import torch.nn.functional as F
+        T = self.num_timestep
+        s = torch.tensor([t_idx], dtype=torch.int64) / T
+        t = (torch.tensor([t_idx], dtype=torch.int64) + 1) / T
+        g_s, g_t = self.gamma_at(s), self.gamma_at(t)
+        sigma2_ts = -torch.expm1(F.softplus(g_s) - F.softplus(g_t))
+        alpha_ts = torch.exp(0.5 * (F.logsigmoid(-g_t) - F.logsigmoid(-g_s)))
+        sigma_s, sigma_t = torch.sqrt(torch.sigmoid(g_s)), torch.sqrt(torch.sigmoid(g_t))
+        return (float(alpha_ts[0]), float((sigma2_ts / alpha_ts / sigma_t)[0]),
+                float((torch.sqrt(sigma2_ts) * sigma_s / sigma_t)[0]))
+
+    def final_scalars(self):
+        """(1 / alpha_0, sigma_0, exp(0.5 gamma_0)) of sample_p_xh_given_z0 / compute_pred (diffsbdd.py:326-360)."""
+        g0 = self.gamma_at(torch.zeros(1))
+        alpha0 = torch.sqrt(torch.sigmoid(-g0))
+        return float((1.0 / alpha0)[0]), float(torch.sqrt(torch.sigmoid(g0))[0]), float(torch.exp(0.5 * g0)[0])

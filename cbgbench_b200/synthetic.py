@@ -55,6 +55,27 @@ def targetdiff_config(num_steps=1000, num_layers=9, num_atomtype=13, k=None, cut
         embedder=dict(emb_dim=128, atom=dict(type='linear'), residue=dict(type='linear'))))
 
 
+def diffsbdd_config(num_steps=1000, num_layers=9, num_atomtype=13, k=None):
+    """configs/denovo/train/diffsbdd.yml:1-22 (+ num_atomtype)."""
+    enc = dict(type='unitransformer', node_feat_dim=128, n_heads=16, num_layers=num_layers)
+    if k is not None:
+        enc['k'] = k
+    return Cfg(dict(
+        type='diffsbdd', num_atomtype=num_atomtype, encoder=enc,
+        generator=dict(pos_schedule=dict(type='polynomial_2'), atom_schedule=dict(type='polynomial_2'),
+                       num_diffusion_timesteps=num_steps, time_sampler='random'),
+        embedder=dict(emb_dim=128, atom=dict(type='linear'), residue=dict(type='linear'))))
+
+
+def make_sbdd_noise(num_steps, n_lig, num_classes=13, seed=7):
+    """Injected normal draws of one DiffSBDD.sample call (order of the reference: x then c)."""
+    rs = np.random.RandomState(seed)
+    f = lambda *shape: torch.from_numpy(rs.normal(size=shape).astype(np.float32))
+    return {'init_x': f(n_lig, 3), 'init_c': f(n_lig, num_classes),
+            'step_x': f(num_steps, n_lig, 3), 'step_c': f(num_steps, n_lig, num_classes),
+            'final_x': f(n_lig, 3), 'final_c': f(n_lig, num_classes)}
+
+
 def make_batch(n_prot, n_lig, seed=2024, num_classes=13, gen_mode='denovo', protein_sigma=8.0):
     """Flat ragged batch with the reference's keys.
 
@@ -137,4 +158,4 @@ def seeded_state_dict(model, seed=0, skip_prefixes=('pos_scheduler.', 'type_sche
     return out
 
 
-__all__ = ['Cfg', 'targetdiff_config', 'make_batch', 'make_noise', 'seeded_state_dict', 'cfg_get']
+__all__ = ['Cfg', 'targetdiff_config', 'diffsbdd_config', 'make_sbdd_noise', 'make_batch', 'make_noise', 'seeded_state_dict', 'cfg_get']

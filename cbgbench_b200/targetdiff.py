@@ -78,8 +78,13 @@ class PLContextEmbedderB200(nn.Module):
         return h_rec, h_lig_bias.contiguous()
 
 
-@register_model('targetdiff')
-class TargetDiffB200(nn.Module):
+class BaseDiffB200(nn.Module):
+    """What the samplers built on the denoiser share (mirror of repo/models/diffusion/_base.py:4-11 plus the
+    hoisting of everything step-invariant): generator flags, context embedder, denoiser, device workspaces and
+    ``prepare`` (batch -> device plan)."""
+
+    allow_rcache = True      # samplers whose pocket atoms move between steps (DiffSBDD) turn the R-cache off
+
     def __init__(self, cfg):
         super().__init__()
         self.cfg = cfg
@@ -91,42 +96,45 @@ class TargetDiffB200(nn.Module):
         if not (self.denoise_structure and self.denoise_atom):
             raise NotImplementedError('denoise_structure / denoise_atom = False is not implemented')
         self.num_classes = cfg.num_atomtype
-        ps = gen.pos_schedule
-        self.pos_scheduler = CTNVPTables(self.num_diffusion_timesteps, beta_start=ps.beta_start,
-                                         beta_end=ps.beta_end, type=ps.type)
-        at = gen.atom_schedule
-        self.type_scheduler = TypeVPTables(self.num_diffusion_timesteps, num_classes=self.num_classes,
-                                           type=at.type, cosine_s=at.cosine_s)
-        cfg.embedder.num_atomtype = cfg.num_atomtype
-        self.context_embedder = PLContextEmbedderB200(cfg.embedder)
-        self.denoiser = get_e3_gnn(cfg.encoder, num_classes=self.num_classes)
         self._ws = _Workspace()
         self._rc = _Workspace()
         self.last_launches = 0
         # R-cache: step-invariant first-Linear terms of edges between non-generated atoms are computed
         # once per batch and streamed from HBM (2*L*N*16 KB).  CBG_RCACHE=0 / use_rcache=False turns it off.
-        self.use_rcache = os.environ.get('CBG_RCACHE', '1') != '0'
+        self.use_rcache = self.allow_rcache and os.environ.get('CBG_RCACHE', '1') != '0'
         # receptive-field pruning of the per-step denoiser (exact for the sampled ligand rows)
         self.use_prune = os.environ.get('CBG_PRUNE', '1') != '0'
 
+    def _build_networks(self, cfg):
+        """context_embedder + denoiser, registered AFTER the schedulers like the reference constructors do
+        (state-dict order: targetdiff.py:22-38, diffsbdd.py:32-44, diffbp.py:111-128)."""
+        cfg.embedder.num_atomtype = cfg.num_atomtype
+        self.context_embedder = PLContextEmbedderB200(cfg.embedder)
+        self.denoiser = get_e3_gnn(cfg.encoder, num_classes=self.num_classes)
+
     def forward(self, batch):
-        raise NotImplementedError('TargetDiffB200 is a forward-only sampling build: the training / '
-                                  'validation loss (targetdiff.py:41-124) is out of scope (DESIGN.md)')
+        raise NotImplementedError(f'{type(self).__name__} is a forward-only sampling build: the training / '
+                                  'validation losses of the reference models are out of scope (DESIGN.md)')
 
     # ---- setup of the step-invariant state ------------------------------------------------
     @torch.no_grad()
-    def prepare(self, batch, device=None):
+    def prepare(self, batch, device=None, protein_feature_scale=None, protein_pos=None):
         """Move the batch to the device and hoist everything that does not change over the
-        T steps.  Returns a dict holding device tensors (kept alive) and the ctypes plan."""
+        T steps.  Returns a dict holding device tensors (kept alive) and the ctypes plan.
+
+        ``protein_feature_scale`` divides protein_atom_feature (DiffSBDD's normalize_type) and
+        ``protein_pos`` replaces batch['protein_pos'] (DiffSBDD starts from a COM-shifted pocket)."""
         dev = torch.device(device) if device is not None else next(self.parameters()).device
         if dev.type != 'cuda':
-            raise RuntimeError('TargetDiffB200.sample needs the model on a CUDA device (no CPU fallback)')
+            raise RuntimeError(f'{type(self).__name__}.sample needs the model on a CUDA device (no CPU fallback)')
         g = lambda k, d=None: batch.get(k, d) if hasattr(batch, 'get') else (batch[k] if k in batch else d)
         to = lambda t: t.to(dev, non_blocking=True)
         x_lig = to(batch['ligand_pos']).float().contiguous()
         v_lig = to(batch['ligand_atom_type'])
-        x_rec = to(batch['protein_pos']).float()
+        x_rec = to(batch['protein_pos'] if protein_pos is None else protein_pos).float()
         v_rec = to(batch['protein_atom_feature'])
+        if protein_feature_scale is not None:
+            v_rec = v_rec.float() / protein_feature_scale
         aa_rec = to(batch['protein_aa_type'])
         lig_flag = to(batch['ligand_lig_flag']).bool()
         rec_flag = to(batch['protein_lig_flag']).bool()
@@ -166,7 +174,7 @@ class TargetDiffB200(nn.Module):
         ws_ptr, ws_have = self._ws.get(ws_bytes, dev)
         den = self.denoiser
         rc_ptr, rc_bytes = None, 0
-        if self.use_rcache:
+        if self.use_rcache and self.allow_rcache:
             rc_bytes = L.cbg_rcache_bytes(N, den.num_layers)
             have = self._rc.buf.numel() if self._rc.buf is not None and self._rc.buf.device == dev else 0
             free_b, _ = torch.cuda.mem_get_info(dev)
@@ -190,7 +198,21 @@ class TargetDiffB200(nn.Module):
                     lig_nodes=lig_nodes, gen_nodes_flag=gen_nodes_flag)
         c_lig = F.one_hot(v_lig, num_classes=self.num_classes).float().contiguous()
         return dict(plan=plan, keep=keep, device=dev, x_lig=x_lig, c_lig=c_lig, batch_idx_lig=bl,
-                    n_lig=n_lig, n_nodes=N)
+                    batch_idx_rec=br, n_lig=n_lig, n_nodes=N, n_graphs=B)
+
+
+@register_model('targetdiff')
+class TargetDiffB200(BaseDiffB200):
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        gen = cfg.generator
+        ps = gen.pos_schedule
+        self.pos_scheduler = CTNVPTables(self.num_diffusion_timesteps, beta_start=ps.beta_start,
+                                         beta_end=ps.beta_end, type=ps.type)
+        at = gen.atom_schedule
+        self.type_scheduler = TypeVPTables(self.num_diffusion_timesteps, num_classes=self.num_classes,
+                                           type=at.type, cosine_s=at.cosine_s)
+        self._build_networks(cfg)
 
     def step_coef(self, t_idx):
         ps, ts = self.pos_scheduler, self.type_scheduler

@@ -188,6 +188,26 @@ int32_t cbg_reverse_step_f32(const cbg_step_coef* coef, const float* x0_pred /*[
                              int32_t n, int32_t num_classes,
                              float* x_next, float* c_next, int64_t* v_next, void* stream);
 
+/* ---- the other diffusion samplers that drive the same denoiser -------------------
+ *
+ * DiffSBDD (diffsbdd.py:240-321): every step is embed -> denoiser -> sample_p_zs_given_zt
+ * (diffusion_scheduler.py:1005-1039) for coordinates and (continuous) type features, with the COM projection
+ * remove_mean_batch (:706-710) that also translates the pocket.  All graphs share (s, t), so the schedule enters as
+ * three host scalars.  mode 1 is the final stage sample_p_xh_given_z0 (diffsbdd.py:323-360).
+ * The plan is the one of cbg_sample_begin_f32 WITHOUT an R-cache (the pocket is not static here). */
+typedef struct cbg_sbdd_coef {
+  float a;       /* mode 0: alpha_t|s                      mode 1: 1 / alpha_0            */
+  float b;       /* mode 0: sigma2_t|s / alpha_t|s / sigma_t   mode 1: sigma_0            */
+  float s;       /* mode 0: sigma_t|s * sigma_s / sigma_t  mode 1: exp(0.5 * gamma_0)     */
+  int32_t mode;  /* 0: z_s = z_t / a - b * eps + s * noise;  1: z = a * (z_t - b * eps) + s * noise, c_next = 4 c_t */
+} cbg_sbdd_coef;
+
+int32_t cbg_sbdd_step_f32(const cbg_sample_plan* plan, const cbg_sbdd_coef* coef,
+                          const float* x_t /*[n_lig,3]*/, const float* c_t /*[n_lig,K]*/,
+                          const float* x_noise /*[n_lig,3]*/, const float* c_noise /*[n_lig,K]*/,
+                          float* x_next /*[n_lig,3]*/, float* c_next /*[n_lig,K]*/,
+                          float* x_pred /*[n_lig,3] or NULL*/, float* logits /*[n_lig,K] or NULL*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
