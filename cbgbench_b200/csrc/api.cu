@@ -566,6 +566,74 @@ int32_t cbg_sbdd_step_f32(const cbg_sample_plan* plan, const cbg_sbdd_coef* coef
   return cbg_launch_sbdd_reverse(r, st);
 }
 
+int32_t cbg_bp_step_f32(const cbg_sample_plan* plan, const float* com_blob, int32_t com_layers, const cbg_bp_coef* coef,
+                        const float* x_t, const float* c_t, const float* pos_noise, const float* type_uniform,
+                        float* x_next, float* c_next, int64_t* v_next, float* eps_out, float* logits, void* stream) {
+  if (!plan || !coef || !com_blob) { cbg_set_error("null plan/coef/com_blob"); return 1; }
+  if (com_layers < 0 || com_layers > 16) { cbg_set_error("com_layers=%d outside [0,16]", com_layers); return 1; }
+  Workspace ws;
+  if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int K = plan->num_classes;
+  if (K < 1 || K > CBG_MAXCLS) { cbg_set_error("num_classes=%d outside [1,%d]", K, CBG_MAXCLS); return 1; }
+  const long long n_nodes = plan->n_nodes;
+  const int n_gen = plan->n_gen, n_lig = plan->n_lig;
+  if (int rc = cbg_launch_step_init(x_t, c_t, plan->lig_node, n_lig, K, plan->emb_wt, plan->h_lig_bias,
+                                    plan->h_static, n_nodes, ws.x4, ws.h, st)) return rc;
+  const bool prune = plan->prune != 0 && prune_enabled();
+  if (int rc = run_core(plan->blob, plan->num_layers, ws, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes,
+                        n_nodes, plan->gen_node, n_gen, plan->mode, plan->k, plan->r_max, plan->rcache,
+                        plan->lig_node, n_lig, prune, st)) return rc;
+  // scratch in the attention-weight buffer (free after the layers): logits | denoiser output coordinates
+  float* lg = logits ? logits : ws.w;
+  float* xp = ws.w + align256((size_t)n_lig * K * 4) / 4;
+  if (int rc = cbg_launch_classifier(plan->blob, ws.h, plan->lig_node, n_lig, K, lg, st)) return rc;
+  if (int rc = cbg_launch_gather_x(ws.x4, plan->lig_node, n_lig, xp, st)) return rc;
+  // ---- CoM head (diffbp.py:80-101): same graph, own gate, H2X stack on the final h, starting from the INPUT x
+  if (int rc = cbg_launch_scatter_x(x_t, plan->lig_node, n_lig, ws.x4, st)) return rc;
+  if (n_gen > 0 && com_layers > 0) {
+    if (int rc = cbg_launch_edge_gate_rows(com_blob, ws.x4, ws.nbr, plan->gen_node, n_gen, ws.ew, st)) return rc;
+    const bool pruned = prune && plan->num_layers > 0;      // run_core built ws.order / ws.cnt
+    const float* layers = com_blob + cbg_layout::kGlobalFloats;
+    for (int l = 0; l < com_layers; ++l) {
+      const float* L = layers + (size_t)l * cbg_layout::kLayerFloats;
+      NodeGemmArgs gj{};
+      gj.a = ws.h; gj.row_idx = nullptr; gj.n_rows = (int)n_nodes;
+      gj.wt = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_WT);
+      gj.bias = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_B);
+      gj.ldw = 640; gj.n_planes = 2; gj.has_q = 0;
+      gj.out[0] = ws.hplane[0]; gj.out[1] = ws.hplane[1];
+      gj.tc_planes = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_TC); gj.tc_first_plane = 0;
+      if (pruned) { gj.row_idx = ws.order; gj.n_rows_dev = ws.cnt + plan->num_layers; }   // generated atoms + neighbours
+      if (int rc = launch_node_gemm(gj, st)) return rc;
+      NodeGemmArgs gi{};
+      gi.a = ws.h; gi.row_idx = plan->gen_node; gi.n_rows = n_gen;
+      gi.wt = gj.wt + 256; gi.bias = gj.bias + 256;
+      gi.ldw = 640; gi.n_planes = 3; gi.has_q = 1;
+      gi.out[0] = ws.hplane[2]; gi.out[1] = ws.hplane[3]; gi.out[2] = nullptr;
+      gi.q_ln = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_LN);
+      gi.q_w1t = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_W1T);
+      gi.q_b1 = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_B1);
+      gi.out_q = ws.hplane[4];
+      gi.tc_planes = gj.tc_planes; gi.tc_first_plane = 2;
+      if (int rc = launch_node_gemm(gi, st)) return rc;
+      EdgeArgs x{};
+      x.x4 = ws.x4; x.nbr = ws.nbr; x.ew = ws.ew;
+      x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
+      x.layer = L; x.w = nullptr; x.h = ws.h; x.node_idx = plan->gen_node; x.n_nodes = n_gen; x.dx = ws.dx;
+      if (int rc = cbg_launch_h2x(x, st)) return rc;
+      if (int rc = cbg_launch_apply_dx(ws.x4, plan->gen_node, ws.dx, n_gen, st)) return rc;
+    }
+  }
+  BpArgs r{};
+  r.x4 = ws.x4; r.graph_ptr = plan->graph_ptr; r.lig_node = plan->lig_node; r.n_lig = n_lig; r.num_classes = K;
+  r.n_graphs = plan->n_graphs; r.x_pred = xp; r.logits = lg; r.x_t = x_t; r.c_t = c_t; r.gen = plan->gen_lig;
+  r.pos_noise = pos_noise; r.type_u = type_uniform; r.abar = coef->alpha_cumprod; r.beta = coef->beta;
+  r.nonzero = coef->nonzero; r.prob = coef->change_prob; r.x_next = x_next; r.c_next = c_next;
+  r.v_next = (long long*)v_next; r.eps_out = eps_out;
+  return cbg_launch_bp_reverse(r, st);
+}
+
 int32_t cbg_reverse_step_f32(const cbg_step_coef* coef, const float* x0_pred, const float* logits, const float* x_t,
                              const float* c_t, const uint8_t* gen, const float* pos_noise, const float* type_uniform,
                              int32_t n, int32_t num_classes, float* x_next, float* c_next, int64_t* v_next,

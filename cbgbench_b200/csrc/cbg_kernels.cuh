@@ -128,3 +128,34 @@ struct SbddArgs {
   float* c_next;            // [n_lig,K]
 };
 int cbg_launch_sbdd_reverse(const SbddArgs& a, cudaStream_t st);
+
+// DiffBP (row f2).  x4[idx[a]].xyz = x[a] (flags kept): puts the step's INPUT ligand coordinates back before the
+// CoM head runs on them (diffbp.py:80-97 works on x_composed, not on the denoiser's output)
+int cbg_launch_scatter_x(const float* x /*[n,3]*/, const int* idx, int n, float4* x4, cudaStream_t st);
+// edge gate of the listed rows only (the CoM head needs it for the generated atoms' edges)
+int cbg_launch_edge_gate_rows(const float* blob_global, const float4* x4, const int* nbr, const int* row_idx,
+                              int n_rows, float* ew, cudaStream_t st);
+// Fused DiffBP reverse step, one CTA per graph:
+//   eps  = (x_pred - x_t) - mean_g(x_pred - x_t) + mean_g(x_com - x_t)          CoMPredictor.forward diffbp.py:80-101
+//   x_s  = (x_t + beta * (-eps / sqrt(1 - abar))) / sqrt(1 - beta) + nonzero * sqrt(beta) * noise, gen-masked
+//                                                  CTNVPScheduler.backward_remove_noise('score') diffusion_scheduler.py:144-165
+//   v_s  = (u < prob) & gen & (v_t == 0) ? argmax softmax(logits) : v_t   MaskTypeSchedule.backward_remove_noise :474-498
+struct BpArgs {
+  const float4* x4;         // ligand rows hold x_com (output of the CoM head's H2X stack)
+  const int* graph_ptr;
+  const int* lig_node;
+  int n_lig, num_classes, n_graphs;
+  const float* x_pred;      // [n_lig,3] denoiser output coordinates
+  const float* logits;      // [n_lig,K]
+  const float* x_t;         // [n_lig,3]
+  const float* c_t;         // [n_lig,K]
+  const unsigned char* gen; // [n_lig]
+  const float* pos_noise;   // [n_lig,3]
+  const float* type_u;      // [n_lig]
+  float abar, beta, nonzero, prob;
+  float* x_next;            // [n_lig,3]
+  float* c_next;            // [n_lig,K]
+  long long* v_next;        // [n_lig]
+  float* eps_out;           // optional [n_lig,3]
+};
+int cbg_launch_bp_reverse(const BpArgs& a, cudaStream_t st);

@@ -174,6 +174,23 @@ __global__ void __launch_bounds__(128) edge_gate_list_kernel(const float* __rest
   ew[idx] = gate_value(sm, x4[idx / CBG_KMAX], x4[nbr[idx]]);
 }
 
+// gates of the listed rows (DiffBP CoM head: generated atoms only); 4 rows per CTA
+__global__ void __launch_bounds__(128) edge_gate_rows_kernel(const float* __restrict__ gw,
+                                                             const float4* __restrict__ x4,
+                                                             const int* __restrict__ nbr,
+                                                             const int* __restrict__ row_idx, int n_rows,
+                                                             float* __restrict__ ew) {
+  __shared__ __align__(16) float sm[kGateSmemFloats];
+  block_copy_f4(sm, gw, kGateSmemFloats);
+  __syncthreads();
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int i = row_idx[r];
+  const size_t idx = (size_t)i * CBG_KMAX + (threadIdx.x & 31);
+  const int j = nbr[idx];
+  ew[idx] = j >= 0 ? gate_value(sm, x4[i], x4[j]) : 0.f;
+}
+
 __device__ __forceinline__ float gate_value(const float* sm, const float4 xi, const float4 xj) {
   const float* w0t = sm;                 // [20][160]
   const float* b0 = sm + 3200;
@@ -327,6 +344,16 @@ int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max
   CBG_PROF_BEGIN(CBG_K_KNN, st);
   knn_kernel<<<grid, 256, smem, st>>>(x4, graph_ptr, k, mode, r_max * r_max, static_only, snbr, nbr);
   CBG_LAUNCHED(CBG_K_KNN, st);
+  return 0;
+}
+
+int cbg_launch_edge_gate_rows(const float* blob_global, const float4* x4, const int* nbr, const int* row_idx,
+                              int n_rows, float* ew, cudaStream_t st) {
+  if (n_rows <= 0) return 0;
+  const float* gw = blob_global + cbg_layout::global_offset(CBG_GF_GATE_W0T);
+  CBG_PROF_BEGIN(CBG_K_GATE, st);
+  edge_gate_rows_kernel<<<(n_rows + 3) / 4, 128, 0, st>>>(gw, x4, nbr, row_idx, n_rows, ew);
+  CBG_LAUNCHED(CBG_K_GATE, st);
   return 0;
 }
 

@@ -241,7 +241,104 @@ __global__ void __launch_bounds__(128) sbdd_reverse_kernel(SbddArgs p) {
   }
 }
 
+__global__ void scatter_x_kernel(const float* __restrict__ x, const int* __restrict__ idx, int n,
+                                 float4* __restrict__ x4) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  float4 v = x4[idx[a]];
+  v.x = x[3 * a]; v.y = x[3 * a + 1]; v.z = x[3 * a + 2];
+  x4[idx[a]] = v;
+}
+
+// DiffBP reverse step, one CTA per graph (see BpArgs)
+__global__ void __launch_bounds__(128) bp_reverse_kernel(BpArgs p) {
+  __shared__ int s_rng[2];
+  __shared__ float s_red[4][6];
+  __shared__ float s_mean[6];
+  const int g = blockIdx.x;
+  if (threadIdx.x == 0) {
+    s_rng[0] = lower_bound_i32(p.lig_node, p.n_lig, p.graph_ptr[g]);
+    s_rng[1] = lower_bound_i32(p.lig_node, p.n_lig, p.graph_ptr[g + 1]);
+  }
+  __syncthreads();
+  const int lo = s_rng[0], hi = s_rng[1];
+  float sum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int a = lo + threadIdx.x; a < hi; a += blockDim.x) {
+    const float4 xc = p.x4[p.lig_node[a]];
+    const float com[3] = {xc.x, xc.y, xc.z};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xt = p.x_t[3 * a + c];
+      sum[c] += __fsub_rn(p.x_pred[3 * a + c], xt);
+      sum[3 + c] += __fsub_rn(com[c], xt);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) sum[c] = warp_sum(sum[c]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) s_red[threadIdx.x >> 5][c] = sum[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const float t = (s_red[0][threadIdx.x] + s_red[1][threadIdx.x]) + (s_red[2][threadIdx.x] + s_red[3][threadIdx.x]);
+    const int cnt = hi - lo;
+    s_mean[threadIdx.x] = __fdiv_rn(t, (float)(cnt > 0 ? cnt : 1));
+  }
+  __syncthreads();
+  const int K = p.num_classes;
+  const float sigma = __fsqrt_rn(__fsub_rn(1.f, p.abar));
+  const float denom = __fsqrt_rn(__fsub_rn(1.f, p.beta));
+  const float nscale = __fmul_rn(p.nonzero, __fsqrt_rn(p.beta));
+  for (int a = lo + threadIdx.x; a < hi; a += blockDim.x) {
+    const bool gen = p.gen[a] != 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xt = p.x_t[3 * a + c];
+      const float eps = __fadd_rn(__fsub_rn(__fsub_rn(p.x_pred[3 * a + c], xt), s_mean[c]), s_mean[3 + c]);
+      const float score = -__fdiv_rn(eps, sigma);
+      float xs = __fdiv_rn(__fadd_rn(xt, __fmul_rn(p.beta, score)), denom);
+      xs = __fadd_rn(xs, __fmul_rn(nscale, p.pos_noise[3 * a + c]));
+      p.x_next[3 * a + c] = gen ? xs : xt;
+      if (p.eps_out) p.eps_out[3 * a + c] = eps;
+    }
+    // types: argmax of the softmax probabilities (first maximum), change only absorbing-state atoms
+    float mx = -INFINITY;
+    for (int c = 0; c < K; ++c) mx = fmaxf(mx, p.logits[(size_t)a * K + c]);
+    float se = 0.f;
+    for (int c = 0; c < K; ++c) se += expf(p.logits[(size_t)a * K + c] - mx);
+    int v_pred = 0, vt = 0;
+    float best = -INFINITY, best_ct = -INFINITY;
+    for (int c = 0; c < K; ++c) {
+      const float pr = __fdiv_rn(expf(p.logits[(size_t)a * K + c] - mx), se);
+      if (pr > best) { best = pr; v_pred = c; }
+      const float ctv = p.c_t[(size_t)a * K + c];
+      if (ctv > best_ct) { best_ct = ctv; vt = c; }
+    }
+    const bool change = (p.type_u[a] < p.prob) && gen && vt == 0;
+    const int v = change ? v_pred : vt;
+    p.v_next[a] = v;
+    for (int c = 0; c < K; ++c) p.c_next[(size_t)a * K + c] = (c == v) ? 1.f : 0.f;
+  }
+}
+
 }  // namespace
+
+int cbg_launch_scatter_x(const float* x, const int* idx, int n, float4* x4, cudaStream_t st) {
+  if (n <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_MISC, st);
+  scatter_x_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, idx, n, x4);
+  CBG_LAUNCHED(CBG_K_MISC, st);
+  return 0;
+}
+
+int cbg_launch_bp_reverse(const BpArgs& a, cudaStream_t st) {
+  if (a.n_graphs <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_REVERSE, st);
+  bp_reverse_kernel<<<a.n_graphs, 128, 0, st>>>(a);
+  CBG_LAUNCHED(CBG_K_REVERSE, st);
+  return 0;
+}
 
 int cbg_launch_sbdd_reverse(const SbddArgs& a, cudaStream_t st) {
   if (a.n_graphs <= 0) return 0;

@@ -125,8 +125,12 @@ def tc_weight_plane(w):
     return torch.from_numpy(out.reshape(-1)).to(torch.float64)
 
 
-def pack_denoiser_blob(sd, prefix, num_layers, num_classes):
-    """Pack a (reference-keyed) state dict into the flat fp32 blob of csrc/cbg_layout.h."""
+def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
+    """Pack a (reference-keyed) state dict into the flat fp32 blob of csrc/cbg_layout.h.
+
+    ``com_head=True`` packs DiffBP's CoMPredictor (diffbp.py:30-57: its own ``dist_emb`` and ``num_layers`` x
+    H2XAttention under ``h2xattentions.<l>.``) into the same layout: the gate fields of the global block and the
+    H2X fields of every layer block are filled, classifier and X2H fields stay zero."""
     lay = _lib.blob_layout()
     total = lay['global_floats'] + num_layers * lay['layer_floats']
     blob = torch.zeros(total, dtype=torch.float64)
@@ -163,19 +167,22 @@ def pack_denoiser_blob(sd, prefix, num_layers, num_classes):
     put(0, g, 'GATE_LN', torch.cat([_t(sd[p + 'dist_emb.1.net.1.weight']), _t(sd[p + 'dist_emb.1.net.1.bias'])]))
     put(0, g, 'GATE_W1', _t(sd[p + 'dist_emb.1.net.3.weight']).reshape(-1))
     put(0, g, 'GATE_RBF', rbf_field(sd[p + 'dist_emb.0.offset'], float(sd[p + 'dist_emb.1.net.3.bias'].reshape(-1)[0])))
-    put(0, g, 'CLS_W0T', _t(sd[p + 'classifier.0.weight']).t().contiguous())
-    put(0, g, 'CLS_B0', _t(sd[p + 'classifier.0.bias']))
-    w1 = _t(sd[p + 'classifier.2.weight'])
-    assert w1.shape == (num_classes, HIDDEN) and num_classes <= 16
-    put(0, g, 'CLS_W1', w1)
-    put(0, g, 'CLS_B1', _t(sd[p + 'classifier.2.bias']))
+    if not com_head:
+        put(0, g, 'CLS_W0T', _t(sd[p + 'classifier.0.weight']).t().contiguous())
+        put(0, g, 'CLS_B0', _t(sd[p + 'classifier.0.bias']))
+        w1 = _t(sd[p + 'classifier.2.weight'])
+        assert w1.shape == (num_classes, HIDDEN) and num_classes <= 16
+        put(0, g, 'CLS_W1', w1)
+        put(0, g, 'CLS_B1', _t(sd[p + 'classifier.2.bias']))
 
     lf = lay['layer']
     inv_sqrt_dh = 1.0 / math.sqrt(HIDDEN // N_HEADS)
     for l in range(num_layers):
         base = lay['global_floats'] + l * lay['layer_floats']
-        for tag, sub, kname, vname, qname in (('X2H', f'blocks.{l}.x2h_layers.0.', 'hk_func', 'hv_func', 'hq_func'),
-                                              ('H2X', f'blocks.{l}.h2x_layers.0.', 'xk_func', 'xv_func', 'xq_func')):
+        subs = ((('H2X', f'h2xattentions.{l}.', 'xk_func', 'xv_func', 'xq_func'),) if com_head else
+                (('X2H', f'blocks.{l}.x2h_layers.0.', 'hk_func', 'hv_func', 'hq_func'),
+                 ('H2X', f'blocks.{l}.h2x_layers.0.', 'xk_func', 'xv_func', 'xq_func')))
+        for tag, sub, kname, vname, qname in subs:
             sp = p + sub
             wrf_k, c_k, wi_k, wj_k = first_layer_split(sd[sp + kname + '.net.0.weight'])
             wrf_v, c_v, wi_v, wj_v = first_layer_split(sd[sp + vname + '.net.0.weight'])

@@ -67,6 +67,29 @@ def diffsbdd_config(num_steps=1000, num_layers=9, num_atomtype=13, k=None):
         embedder=dict(emb_dim=128, atom=dict(type='linear'), residue=dict(type='linear'))))
 
 
+def diffbp_config(num_steps=1000, num_layers=9, num_atomtype=13, k=None, num_layers_com=None):
+    """configs/denovo/train/diffbp.yml:1-26 (+ num_atomtype)."""
+    enc = dict(type='unitransformer', node_feat_dim=128, n_heads=16, num_layers=num_layers)
+    if k is not None:
+        enc['k'] = k
+    if num_layers_com is not None:
+        enc['num_layers_com'] = num_layers_com
+    return Cfg(dict(
+        type='diffbp', num_atomtype=num_atomtype, encoder=enc,
+        generator=dict(pos_schedule=dict(type='sigmoid', beta_start=1.e-7, beta_end=2.e-3),
+                       atom_schedule=dict(type='uniform'), num_diffusion_timesteps=num_steps, time_sampler='symmetric',
+                       com_schedule=dict(type='log', sigma_min=1.e-7, sigma_max=5.0)),
+        embedder=dict(emb_dim=128, atom=dict(type='linear'), residue=dict(type='linear'))))
+
+
+def make_bp_noise(num_steps, n_lig, seed=7):
+    """Injected draws of one DiffBP.sample call: positions N(0,1) [T,n_lig,3], type change mask U[0,1) [T,n_lig]."""
+    rs = np.random.RandomState(seed)
+    pn = torch.from_numpy(rs.normal(size=(num_steps, n_lig, 3)).astype(np.float32))
+    tu = torch.from_numpy(rs.random_sample(size=(num_steps, n_lig)).astype(np.float32))
+    return pn, tu
+
+
 def make_sbdd_noise(num_steps, n_lig, num_classes=13, seed=7):
     """Injected normal draws of one DiffSBDD.sample call (order of the reference: x then c)."""
     rs = np.random.RandomState(seed)
@@ -158,4 +181,4 @@ def seeded_state_dict(model, seed=0, skip_prefixes=('pos_scheduler.', 'type_sche
     return out
 
 
-__all__ = ['Cfg', 'targetdiff_config', 'diffsbdd_config', 'make_sbdd_noise', 'make_batch', 'make_noise', 'seeded_state_dict', 'cfg_get']
+__all__ = ['Cfg', 'targetdiff_config', 'diffsbdd_config', 'make_sbdd_noise', 'diffbp_config', 'make_bp_noise', 'make_batch', 'make_noise', 'seeded_state_dict', 'cfg_get']

@@ -208,6 +208,25 @@ int32_t cbg_sbdd_step_f32(const cbg_sample_plan* plan, const cbg_sbdd_coef* coef
                           float* x_next /*[n_lig,3]*/, float* c_next /*[n_lig,K]*/,
                           float* x_pred /*[n_lig,3] or NULL*/, float* logits /*[n_lig,K] or NULL*/, void* stream);
 
+/* DiffBP (diffbp.py:240-299): embed -> denoiser -> CoM head (CoMPredictor, diffbp.py:30-101: the step's kNN graph,
+ * its own edge gate, com_layers x H2X on the denoiser's final h starting from the step's input coordinates) ->
+ * CTNVPScheduler.backward_remove_noise(type='score') (diffusion_scheduler.py:144-165) on eps + eps_com and
+ * MaskTypeSchedule.backward_remove_noise (:474-498).  com_blob packs the CoM head in the denoiser's blob layout
+ * (gate fields of the global block, H2X fields of com_layers layer blocks).  type_uniform is [n_lig]. */
+typedef struct cbg_bp_coef {
+  float alpha_cumprod;   /* pos_scheduler.alphas_cumprod[t] */
+  float beta;            /* pos_scheduler.betas[t] */
+  float nonzero;         /* 0 if t == 0 else 1 */
+  float change_prob;     /* clamp((T - t) / T, 0, 1) */
+} cbg_bp_coef;
+
+int32_t cbg_bp_step_f32(const cbg_sample_plan* plan, const float* com_blob, int32_t com_layers,
+                        const cbg_bp_coef* coef, const float* x_t /*[n_lig,3]*/, const float* c_t /*[n_lig,K]*/,
+                        const float* pos_noise /*[n_lig,3]*/, const float* type_uniform /*[n_lig]*/,
+                        float* x_next /*[n_lig,3]*/, float* c_next /*[n_lig,K]*/, int64_t* v_next /*[n_lig]*/,
+                        float* eps_out /*[n_lig,3] or NULL: eps + eps_com*/, float* logits /*[n_lig,K] or NULL*/,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

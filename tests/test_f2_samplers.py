@@ -12,8 +12,9 @@ import torch
 
 from cbgbench_b200 import synthetic
 from cbgbench_b200.diffsbdd import DiffSBDDB200
+from cbgbench_b200.diffbp import DiffBPB200
 from cbgbench_b200.schedulers import DiffsbddVariationalTables
-from oracle import diffusion_sbdd as OS
+from oracle import diffusion_sbdd as OS, diffusion_bp as OB
 from helpers import GOLDEN, WEIGHT_SEED, golden, rel_err
 
 torch.set_grad_enabled(False)
@@ -160,3 +161,137 @@ def test_sbdd_rejects_rcache_plan():
     rc = _lib.lib().cbg_sbdd_step_f32(C.byref(state['plan']), C.byref(coef), z.data_ptr(), z.data_ptr(), z.data_ptr(),
                                       z.data_ptr(), z.data_ptr(), z.data_ptr(), None, None, None)
     assert rc != 0 and b'R-cache' in _lib.lib().cbg_last_error()
+
+
+# =============================================================================================================
+# DiffBP
+# =============================================================================================================
+
+def bp_model(num_steps=10, device=None, **kw):
+    model = DiffBPB200(synthetic.diffbp_config(num_steps=num_steps, **kw))
+    sd = synthetic.seeded_state_dict(model, seed=WEIGHT_SEED)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    return (model.to(device) if device is not None else model), sd
+
+
+def bp_batch(n_prot, n_lig, seed, gen_mode='denovo'):
+    """Ligand types start at the absorbing state 0, every 5th atom keeps a random type (= make_golden_f2.bp_batch)."""
+    batch = synthetic.make_batch(n_prot, n_lig, seed=seed, gen_mode=gen_mode)
+    v = batch['ligand_atom_type'].clone()
+    keep = torch.arange(v.numel()) % 5 == 4
+    batch['ligand_atom_type'] = torch.where(keep, v, torch.zeros_like(v))
+    return batch
+
+
+def test_bp_state_dict_keys_match_reference():
+    with open(os.path.join(GOLDEN, 'bp_state_keys.json')) as f:
+        want = json.load(f)
+    model, _ = bp_model(10)
+    have = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert list(have.keys()) == list(want.keys())
+    assert have == want
+
+
+def test_bp_oracle_trajectory_matches_reference():
+    g = golden('bp_trajectory.npz')
+    T = 10
+    _, sd = bp_model(T)
+    batch = bp_batch([150, 60], [20, 9], seed=41)
+    pn, tu = synthetic.make_bp_noise(T, 29, seed=13)
+    traj = OB.sample(sd, batch, T, pn, tu)
+    for t in range(-1, T):
+        assert np.array_equal(traj[t][1].argmax(-1).numpy(), g[f'v{t}']), t
+        assert rel_err(traj[t][0], g[f'x{t}']) < 1e-5, t
+    eps, eps_com, _ = OB.denoise(sd, batch, batch['ligand_pos'].float(),
+                                 torch.nn.functional.one_hot(batch['ligand_atom_type'], 13).float())
+    assert rel_err(eps + eps_com, g[f'eps{T - 1}']) < 1e-5
+
+
+def test_bp_mask_type_step_properties():
+    """MaskTypeSchedule.backward_remove_noise: only generated absorbing-state atoms may change; prob = (T - t) / T."""
+    rs = np.random.RandomState(0)
+    n, K, T = 50, 13, 20
+    logits = torch.from_numpy(rs.normal(size=(n, K)).astype(np.float32))
+    v = torch.from_numpy(rs.randint(0, 3, size=n))
+    c = torch.nn.functional.one_hot(v, K).float()
+    gen = torch.from_numpy(rs.rand(n) < 0.7)
+    u = torch.from_numpy(rs.random_sample(n).astype(np.float32))
+    for t in (0, 7, 19):
+        cn, vn = OB.mask_type_reverse_step(logits, c, t, T, gen, u, K)
+        changed = vn != v
+        assert not bool((changed & ~(gen & (v == 0))).any())
+        want = gen & (v == 0) & (u < (T - t) / T) & (logits.argmax(-1) != 0)
+        assert torch.equal(changed, want)
+    model, _ = bp_model(T)
+    assert model.type_scheduler.change_prob(0) == 1.0 and abs(model.type_scheduler.change_prob(19) - 0.05) < 1e-7
+
+
+@pytest.mark.gpu
+def test_bp_trajectory_matches_golden_and_oracle():
+    g = golden('bp_trajectory.npz')
+    T = 10
+    model, sd = bp_model(T, device='cuda')
+    batch = bp_batch([150, 60], [20, 9], seed=41)
+    pn, tu = synthetic.make_bp_noise(T, 29, seed=13)
+    eps = {}
+    traj = model.sample(batch, pos_noise=pn, type_uniform=tu, eps_out=eps)
+    assert sorted(traj.keys()) == list(range(-1, T))
+    assert traj[-1][0].is_cuda and not traj[0][0].is_cuda
+    for t in range(-1, T):
+        assert np.array_equal(traj[t][1].argmax(-1).cpu().numpy(), g[f'v{t}']), t
+        assert rel_err(traj[t][0].cpu(), g[f'x{t}']) < TOL, t
+    for t in range(T):
+        assert rel_err(eps[t].cpu(), g[f'eps{t}']) < TOL, t
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('case', [
+    dict(n_prot=[40, 33, 20], n_lig=[9, 6, 4], T=6, layers=3, com=3, gen_mode='denovo'),
+    dict(n_prot=[60, 10], n_lig=[12, 30], T=5, layers=2, com=2, gen_mode='partial'),
+    dict(n_prot=[5, 0, 70], n_lig=[3, 6, 10], T=4, layers=2, com=1, gen_mode='denovo'),
+], ids=['ragged', 'partial_gen', 'no_pocket'])
+def test_bp_sample_matches_oracle(case):
+    T = case['T']
+    model, sd = bp_model(T, device='cuda', num_layers=case['layers'], num_layers_com=case['com'])
+    batch = bp_batch(case['n_prot'], case['n_lig'], seed=19, gen_mode=case['gen_mode'])
+    n_lig = int(sum(case['n_lig']))
+    pn, tu = synthetic.make_bp_noise(T, n_lig, seed=5)
+    want = OB.sample(sd, batch, T, pn, tu)
+    for rcache, prune in ((True, True), (False, False)):
+        model.use_rcache, model.use_prune = rcache, prune
+        traj = model.sample(batch, pos_noise=pn, type_uniform=tu)
+        for t in range(-1, T):
+            assert torch.equal(traj[t][1].argmax(-1).cpu(), want[t][1].argmax(-1)), (t, rcache)
+            assert rel_err(traj[t][0].cpu(), want[t][0]) < TOL, (t, rcache)
+
+
+@pytest.mark.gpu
+def test_bp_com_shift_is_measurable():
+    """The CoM head must matter in the comparison above: eps + eps_com differs from eps alone by more than TOL."""
+    T = 4
+    model, sd = bp_model(T, device='cuda', num_layers=2)
+    batch = bp_batch([40, 30], [9, 7], seed=23)
+    x = batch['ligand_pos'].float()
+    c = torch.nn.functional.one_hot(batch['ligand_atom_type'], 13).float()
+    eps, eps_com, _ = OB.denoise(sd, batch, x, c)
+    assert float(eps_com.abs().max()) > 10 * TOL * float(eps.abs().max())
+    got = {}
+    pn, tu = synthetic.make_bp_noise(T, 16, seed=1)
+    model.sample(batch, pos_noise=pn, type_uniform=tu, num_steps=1, eps_out=got)
+    assert rel_err(got[T - 1].cpu(), eps + eps_com) < TOL
+    assert rel_err(got[T - 1].cpu(), eps) > 10 * TOL
+
+
+@pytest.mark.gpu
+def test_bp_free_running_sample_reproducible():
+    T = 6
+    model, _ = bp_model(T, device='cuda', num_layers=2)
+    batch = bp_batch([50, 40], [10, 8], seed=4)
+    torch.manual_seed(3)
+    a = model.sample(batch, traj_mode='final')
+    torch.manual_seed(3)
+    b = model.sample(batch, traj_mode='final')
+    assert torch.isfinite(a[0][0]).all()
+    assert torch.equal(a[0][0], b[0][0]) and torch.equal(a[0][1], b[0][1])
+    assert torch.equal(a[-1][0], b[-1][0])
