@@ -92,24 +92,12 @@ class DiffBPB200(BaseDiffB200):
                            change_prob=self.type_scheduler.change_prob(t_idx))
 
     @torch.no_grad()
-    def sample(self, batch, pos_noise=None, type_uniform=None, num_steps=None, traj_mode='full', eps_out=None):
-        """DiffBP.sample (diffbp.py:240-299).  Returns ``traj``: {t: (x_lig, c_lig one-hot, batch_idx_lig)}, keys
-        T-1 ... -1, entries >= 0 on the CPU and key -1 on the device like the reference.
-
-        ``pos_noise[t]`` [n_lig,3] / ``type_uniform[t]`` [n_lig] inject the random numbers; ``num_steps`` stops early;
-        ``traj_mode='final'`` keeps only traj[0] and traj[-1]; ``eps_out`` (dict) receives eps + eps_com per step."""
-        T, K = self.num_diffusion_timesteps, self.num_classes
-        state = self.prepare(batch)
+    def run_steps(self, state, t_seq, X, Cc, pos_noise=None, type_uniform=None, eps_out=None):
+        """Enqueue the reverse steps ``t_seq`` (descending t): one ``cbg_bp_step_f32`` call each.  X / Cc as in
+        TargetDiffB200.run_steps (slot t+1 = state entering step t, slot t = its result)."""
         dev, n_lig, plan = state['device'], state['n_lig'], state['plan']
         com_blob = self.com_head.packed_blob(dev)
-        X = torch.empty((T + 1, n_lig, 3), dtype=torch.float32, device=dev)
-        Cc = torch.empty((T + 1, n_lig, K), dtype=torch.float32, device=dev)
-        X[T].copy_(state['x_lig'])
-        Cc[T].copy_(state['c_lig'])
         v_scratch = torch.empty(n_lig, dtype=torch.int64, device=dev)
-        t_seq = list(reversed(range(T)))
-        if num_steps is not None:
-            t_seq = t_seq[:num_steps]
         L = _lib.lib()
         st = _lib.stream_ptr(dev)
         launches0 = L.cbg_launch_count()
@@ -128,6 +116,25 @@ class DiffBPB200(BaseDiffB200):
                                              X[t_idx].data_ptr(), Cc[t_idx].data_ptr(), v_scratch.data_ptr(),
                                              e_buf.data_ptr() if e_buf is not None else None, None, st))
         self.last_launches = L.cbg_launch_count() - launches0
+
+    @torch.no_grad()
+    def sample(self, batch, pos_noise=None, type_uniform=None, num_steps=None, traj_mode='full', eps_out=None):
+        """DiffBP.sample (diffbp.py:240-299).  Returns ``traj``: {t: (x_lig, c_lig one-hot, batch_idx_lig)}, keys
+        T-1 ... -1, entries >= 0 on the CPU and key -1 on the device like the reference.
+
+        ``pos_noise[t]`` [n_lig,3] / ``type_uniform[t]`` [n_lig] inject the random numbers; ``num_steps`` stops early;
+        ``traj_mode='final'`` keeps only traj[0] and traj[-1]; ``eps_out`` (dict) receives eps + eps_com per step."""
+        T, K = self.num_diffusion_timesteps, self.num_classes
+        state = self.prepare(batch)
+        dev, n_lig = state['device'], state['n_lig']
+        X = torch.empty((T + 1, n_lig, 3), dtype=torch.float32, device=dev)
+        Cc = torch.empty((T + 1, n_lig, K), dtype=torch.float32, device=dev)
+        X[T].copy_(state['x_lig'])
+        Cc[T].copy_(state['c_lig'])
+        t_seq = list(reversed(range(T)))
+        if num_steps is not None:
+            t_seq = t_seq[:num_steps]
+        self.run_steps(state, t_seq, X, Cc, pos_noise, type_uniform, eps_out)
         bl = state['batch_idx_lig']
         t_last = t_seq[-1]
         traj = {}

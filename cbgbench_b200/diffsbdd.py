@@ -54,16 +54,10 @@ class DiffSBDDB200(BaseDiffB200):
         return dense.sum(1) / cnt.clamp(min=1).to(x.dtype).unsqueeze(-1)
 
     @torch.no_grad()
-    def sample(self, batch, noise=None, num_steps=None, traj_mode='full'):
-        """DiffSBDD.sample (diffsbdd.py:240-321).
-
-        Returns ``traj``: {t: (x_lig [n_lig,3], c_lig [n_lig,K] continuous, batch_idx_lig)} with keys T-1 ... -1;
-        entries >= 0 on the CPU, key -1 on the device, and traj[0] replaced by the final stage
-        (x_lig, 4 * c_lig) exactly like the reference (:313-320).
-
-        ``noise`` = {'init_x','init_c','step_x'[t],'step_c'[t],'final_x','final_c'} injects the random numbers;
-        ``num_steps`` stops early (testing; the final stage only runs after step t = 0);
-        ``traj_mode='final'`` keeps only traj[0] and traj[-1]."""
+    def begin(self, batch, noise=None):
+        """Initial state (diffsbdd.py:255-262) + device plan.  Ligand ~ N(pocket mean, I) projected to zero ligand
+        COM - the projection translates the pocket as well; type features ~ N(0, I).  Returns the state dict of
+        ``prepare`` plus the trajectory buffers X [T+1,n_lig,3] / C [T+1,n_lig,K] (slot t+1 = state entering step t)."""
         T, K = self.num_diffusion_timesteps, self.num_classes
         dev = next(self.parameters()).device
         if dev.type != 'cuda':
@@ -72,9 +66,7 @@ class DiffSBDDB200(BaseDiffB200):
         bl = batch['ligand_element_batch'].to(dev).long()
         br = batch['protein_element_batch'].to(dev).long()
         n_lig = int(bl.numel())
-        B = int(bl.max()) + 1 if n_lig else (int(br.max()) + 1 if br.numel() else 0)
-        # initial state (diffsbdd.py:255-262): ligand ~ N(pocket mean, I) projected to zero ligand COM - the
-        # projection translates the pocket as well; type features ~ N(0, I)
+        B = max(int(bl.max()) + 1 if n_lig else 0, int(br.max()) + 1 if br.numel() else 0)
         x_rec = batch['protein_pos'].to(dev).float()
         eps_x = to(noise['init_x']) if noise is not None else torch.randn((n_lig, 3), device=dev)
         eps_c = to(noise['init_c']) if noise is not None else torch.randn((n_lig, K), device=dev)
@@ -83,15 +75,19 @@ class DiffSBDDB200(BaseDiffB200):
         x_lig = (x_lig - mean[bl]).contiguous()
         x_rec = x_rec - mean[br]
         state = self.prepare(batch, device=dev, protein_feature_scale=TYPE_NORM, protein_pos=x_rec)
-        plan = state['plan']
-
         X = torch.empty((T + 1, n_lig, 3), dtype=torch.float32, device=dev)
         Cc = torch.empty((T + 1, n_lig, K), dtype=torch.float32, device=dev)
         X[T].copy_(x_lig)
         Cc[T].copy_(eps_c)
-        t_seq = list(reversed(range(T)))
-        if num_steps is not None:
-            t_seq = t_seq[:num_steps]
+        state['X'], state['C'] = X, Cc
+        return state
+
+    @torch.no_grad()
+    def run_steps(self, state, t_seq, noise=None):
+        """Enqueue the reverse steps ``t_seq`` (descending t): one ``cbg_sbdd_step_f32`` call each."""
+        K, dev, n_lig, plan = self.num_classes, state['device'], state['n_lig'], state['plan']
+        X, Cc = state['X'], state['C']
+        to = lambda t: t.to(dev, torch.float32).contiguous()
         L = _lib.lib()
         st = _lib.stream_ptr(dev)
         launches0 = L.cbg_launch_count()
@@ -105,20 +101,51 @@ class DiffSBDDB200(BaseDiffB200):
                 _lib.check(L.cbg_sbdd_step_f32(C.byref(plan), C.byref(coef), x_t.data_ptr(), c_t.data_ptr(),
                                                nx.data_ptr(), nc.data_ptr(), X[t_idx].data_ptr(),
                                                Cc[t_idx].data_ptr(), None, None, st))
-            t_last = t_seq[-1]
-            x_fin = c_fin = None
-            if t_last == 0:
-                # sample_p_xh_given_z0 (diffsbdd.py:323-352): one more denoiser pass at t = 0
-                nx = to(noise['final_x']) if noise is not None else torch.randn((n_lig, 3), device=dev)
-                nc = to(noise['final_c']) if noise is not None else torch.randn((n_lig, K), device=dev)  # drawn, unused
-                a, b, s = self.pos_scheduler.final_scalars()
-                coef = _lib.SbddCoef(a=a, b=b, s=s, mode=1)
-                x_fin = torch.empty((n_lig, 3), dtype=torch.float32, device=dev)
-                c_fin = torch.empty((n_lig, K), dtype=torch.float32, device=dev)
-                _lib.check(L.cbg_sbdd_step_f32(C.byref(plan), C.byref(coef), X[0].data_ptr(), Cc[0].data_ptr(),
-                                               nx.data_ptr(), nc.data_ptr(), x_fin.data_ptr(), c_fin.data_ptr(),
-                                               None, None, st))
         self.last_launches = L.cbg_launch_count() - launches0
+
+    @torch.no_grad()
+    def finish(self, state, noise=None):
+        """sample_p_xh_given_z0 (diffsbdd.py:323-352): one more denoiser pass at t = 0 -> (x_lig, 4 * c_lig)."""
+        K, dev, n_lig, plan = self.num_classes, state['device'], state['n_lig'], state['plan']
+        X, Cc = state['X'], state['C']
+        to = lambda t: t.to(dev, torch.float32).contiguous()
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            nx = to(noise['final_x']) if noise is not None else torch.randn((n_lig, 3), device=dev)
+            nc = to(noise['final_c']) if noise is not None else torch.randn((n_lig, K), device=dev)  # drawn, unused
+            a, b, s = self.pos_scheduler.final_scalars()
+            coef = _lib.SbddCoef(a=a, b=b, s=s, mode=1)
+            x_fin = torch.empty((n_lig, 3), dtype=torch.float32, device=dev)
+            c_fin = torch.empty((n_lig, K), dtype=torch.float32, device=dev)
+            _lib.check(L.cbg_sbdd_step_f32(C.byref(plan), C.byref(coef), X[0].data_ptr(), Cc[0].data_ptr(),
+                                           nx.data_ptr(), nc.data_ptr(), x_fin.data_ptr(), c_fin.data_ptr(),
+                                           None, None, _lib.stream_ptr(dev)))
+        return x_fin, c_fin
+
+    @torch.no_grad()
+    def sample(self, batch, noise=None, num_steps=None, traj_mode='full'):
+        """DiffSBDD.sample (diffsbdd.py:240-321).
+
+        Returns ``traj``: {t: (x_lig [n_lig,3], c_lig [n_lig,K] continuous, batch_idx_lig)} with keys T-1 ... -1;
+        entries >= 0 on the CPU, key -1 on the device, and traj[0] replaced by the final stage
+        (x_lig, 4 * c_lig) exactly like the reference (:313-320).
+
+        ``noise`` = {'init_x','init_c','step_x'[t],'step_c'[t],'final_x','final_c'} injects the random numbers;
+        ``num_steps`` stops early (testing; the final stage only runs after step t = 0);
+        ``traj_mode='final'`` keeps only traj[0] and traj[-1]."""
+        T = self.num_diffusion_timesteps
+        state = self.begin(batch, noise)
+        X, Cc, bl = state['X'], state['C'], state['batch_idx_lig']
+        t_seq = list(reversed(range(T)))
+        if num_steps is not None:
+            t_seq = t_seq[:num_steps]
+        self.run_steps(state, t_seq, noise)
+        launches = self.last_launches
+        t_last = t_seq[-1]
+        x_fin = c_fin = None
+        if t_last == 0:
+            x_fin, c_fin = self.finish(state, noise)
+        self.last_launches = launches
         traj = {}
         bl_cpu = bl.cpu()
         if traj_mode == 'full':

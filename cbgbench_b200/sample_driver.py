@@ -12,6 +12,7 @@ count, each rank samples its share with no communication and ONE all-gather retu
 coordinates / types (``cbgbench_b200.sharding``).
 
     python -m cbgbench_b200.sample_driver --pockets 16 --batch-size 16 --out out.pt
+    python -m cbgbench_b200.sample_driver --model diffsbdd --pockets 16      (row f2: also diffbp)
     torchrun --nproc-per-node 8 -m cbgbench_b200.sample_driver --pockets 512 --batch-size 512
 """
 import argparse
@@ -22,6 +23,12 @@ import torch
 
 from . import sharding, synthetic
 from .targetdiff import TargetDiffB200
+from .diffsbdd import DiffSBDDB200
+from .diffbp import DiffBPB200
+
+MODELS = {'targetdiff': (TargetDiffB200, synthetic.targetdiff_config),
+          'diffsbdd': (DiffSBDDB200, synthetic.diffsbdd_config),
+          'diffbp': (DiffBPB200, synthetic.diffbp_config)}
 
 
 def split_batch_into_samples(x, v, graph_id, n_graphs):
@@ -49,8 +56,8 @@ def run(args):
     torch.cuda.set_device(dev)
     if distributed and not torch.distributed.is_initialized():
         torch.distributed.init_process_group('nccl', device_id=dev)
-    cfg = synthetic.targetdiff_config(num_steps=args.steps, num_layers=args.layers)
-    model = TargetDiffB200(cfg)
+    cls, make_cfg = MODELS[args.model]                                                     # get_model(cfg), sample.py:155
+    model = cls(make_cfg(num_steps=args.steps, num_layers=args.layers))
     if args.ckpt:
         ckpt = torch.load(args.ckpt, map_location='cpu')
         model.load_state_dict(ckpt['model'] if 'model' in ckpt else ckpt, strict=True)     # sample.py:153-157
@@ -65,8 +72,10 @@ def run(args):
         batches = []
         for b0 in range(0, args.pockets, args.batch_size):
             nb = min(args.batch_size, args.pockets - b0)
-            batches.append(synthetic.make_batch([args.n_prot] * nb, [args.n_lig] * nb, seed=args.seed + b0,
-                                                gen_mode=args.gen_mode))
+            b = synthetic.make_batch([args.n_prot] * nb, [args.n_lig] * nb, seed=args.seed + b0, gen_mode=args.gen_mode)
+            if args.model == 'diffbp':        # configs/denovo/test/diffbp.yml:19-21 assign_atomtype: absorbing
+                b['ligand_atom_type'] = torch.zeros_like(b['ligand_atom_type'])
+            batches.append(b)
     results, t0 = [], time.time()
     for batch in batches:
         n_graphs = int(batch['ligand_element_batch'].max()) + 1
@@ -94,6 +103,7 @@ def run(args):
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument('--model', default='targetdiff', choices=sorted(MODELS))
     ap.add_argument('--pockets', type=int, default=16)
     ap.add_argument('--batch-size', type=int, default=16)          # sample.py:108
     ap.add_argument('--n-prot', type=int, default=300)

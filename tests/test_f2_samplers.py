@@ -295,3 +295,19 @@ def test_bp_free_running_sample_reproducible():
     assert torch.isfinite(a[0][0]).all()
     assert torch.equal(a[0][0], b[0][0]) and torch.equal(a[0][1], b[0][1])
     assert torch.equal(a[-1][0], b[-1][0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['diffsbdd', 'diffbp'])
+def test_sample_driver_runs_f2_models(name):
+    """The sample.py-style driver (row f1) with the row-f2 models: per-pocket results, reproducible from the seed."""
+    from cbgbench_b200 import sample_driver
+    argv = ['--model', name, '--pockets', '3', '--batch-size', '2', '--n-prot', '30', '--n-lig', '5', '--steps', '4',
+            '--layers', '2']
+    a = sample_driver.main(argv)
+    b = sample_driver.main(argv)
+    assert len(a) == 3
+    for ra, rb in zip(a, b):
+        assert ra['pos'].shape == (5, 3) and ra['v'].shape == (5,)
+        assert torch.isfinite(ra['pos']).all() and int(ra['v'].max()) < 13
+        assert torch.equal(ra['pos'], rb['pos']) and torch.equal(ra['v'], rb['v'])
