@@ -48,6 +48,7 @@ SIGNATURES = {
     'cbg_version': (_I32, []),
     'cbg_last_error': (C.c_char_p, []),
     'cbg_launch_count': (_I64, []),
+    'cbg_set_edge_impl': (_I32, [_I32, _I32]),
     'cbg_profile_num_families': (_I32, []),
     'cbg_profile_family_name': (C.c_char_p, [_I32]),
     'cbg_profile_enable': (_I32, [_I32]),

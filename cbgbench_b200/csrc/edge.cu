@@ -26,6 +26,7 @@
 // lane-permuted order (physical slot hp <-> head hp ^ (lane >> 1)).
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "cbg_kernels.cuh"
 
 namespace {
@@ -621,14 +622,526 @@ __global__ void __launch_bounds__(256) rcache_kernel(const float* __restrict__ l
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tensor-core variants of the two X2H kernels.
+//
+// The per-edge contractions of X2H are small GEMMs per destination node:
+//   x2h_k:  logits^T[16 heads][32 edges] = U_i^T[16][128] . a^T[128][32]     (M=16, N=32, K=128)
+//   x2h_v:  S[16 heads][128 features]    = w_i^T[16][32]  . a[32][128]       (M=16, N=128, K=32)
+// with a[e][:] = relu(LN(first Linear)) of edge e.  They run on the tensor cores with
+// mma.sync.m16n8k8 TF32 and the 3xTF32 split (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate), which keeps
+// fp32-level accuracy.  The operands differ per node (U_i, w_i), so there is nothing for tcgen05 / TMA to share
+// across a 128-row tile; a warp-level MMA per node is the matching granularity.
+//
+// What changes against the SIMT kernels above is the thread mapping: the MMA fragment layout decides which lane
+// owns which (edge, feature) pairs, so the whole front end (gather, first Linear, LayerNorm) is computed directly in
+// fragment layout and `a` never leaves registers:
+//   x2h_k: lane (g = lane>>2, t = lane&3) owns edges g + 8*nt (nt = 0..3) and the 32 features 16m + 4t + q;
+//          the LayerNorm statistics of an edge are a quad reduction (2 shuffles)
+//   x2h_v: lane (g, t) owns edges 8*kt + t and 8*kt + t + 4 (kt = 0..3) and the 16 features 32c + 4g + q;
+//          the statistics are a reduction over the 8 lanes with the same t (3 shuffles)
+// Edges are processed in their permuted positions (edge_setup); a block of 8 consecutive positions is served from
+// the R-cache when all 8 are static (warp-uniform test), else its RBF mat-vec runs in registers.
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// v = hi + lo exactly, hi = the TF32 the tensor core reads (top 19 bits); lo is read truncated (error 2^-21 |v|)
+__device__ __forceinline__ void split_tf32(const float v, unsigned& hi, unsigned& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+// packed fp32 pairs as opaque 64-bit registers (PTX f32x2): keeps a pair packed across many uses
+__device__ __forceinline__ unsigned long long pack_f32x2(const float lo, const float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(const unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma_f32x2(const unsigned long long a, const unsigned long long b,
+                                                        const unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+template <int N>
+__device__ __forceinline__ void split_frag(const float (&v)[N], unsigned (&hi)[N], unsigned (&lo)[N]) {
+#pragma unroll
+  for (int k = 0; k < N; ++k) split_tf32(v[k], hi[k], lo[k]);
+}
+// c += A.B to fp32 accuracy: the two cross terms first, the leading term last
+__device__ __forceinline__ void mma3(float (&c)[4], const unsigned (&ah)[4], const unsigned (&al)[4],
+                                     const unsigned (&bh)[2], const unsigned (&bl)[2]) {
+  mma_tf32(c, al, bh);
+  mma_tf32(c, ah, bl);
+  mma_tf32(c, ah, bh);
+}
+__device__ __forceinline__ float comp4(const float4 v, const int k) {   // k is a compile-time constant after unrolling
+  return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+}
+
+// Shared-memory images of the two [128][128] second-Linear matrices, laid out so that every operand the kernels
+// need is one LDS.128 that lands in consecutive registers (no register shuffling before an FFMA2 / MMA) and so that
+// the 8 lanes of an LDS.128 phase (two heads g, g+1 x four t) hit disjoint banks (16-byte chunk index XOR (g & 1)).
+//
+// x2h_k: W1k[hd*8+d][f] -> the (g = hd & 7, d) row holds 128 x (f, sel = hd >> 3) interleaved: element
+//   ((g*8+d)*64 + ((f >> 1) ^ (g & 1)))*4 + (f & 1)*2 + sel, so one chunk = {(f,hd g), (f,hd g+8), (f+1,hd g), (f+1,hd g+8)}
+//   = the A fragment (a0..a3) of the k-tile whose slots t / t+4 are the features f / f+1.
+__device__ __forceinline__ void block_copy_w1k_frag(float* dst, const float* __restrict__ src) {
+  for (int idx = threadIdx.x; idx < 128 * 32; idx += blockDim.x) {
+    const int row = idx >> 5, f0 = (idx & 31) * 4;
+    const int hd = row >> 3, d = row & 7, g = hd & 7, sel = hd >> 3;
+    const float4 v = ldg4(src + 4 * idx);
+    float* base = dst + (g * 8 + d) * 256 + sel;
+    const int c0 = (f0 >> 1) ^ (g & 1), c1 = ((f0 >> 1) + 1) ^ (g & 1);
+    base[c0 * 4] = v.x; base[c0 * 4 + 2] = v.y; base[c1 * 4] = v.z; base[c1 * 4 + 2] = v.w;
+  }
+}
+// x2h_v: W1v[row][f], f = 32c + 8t + 4v + q -> element row*128 + 4*((8c + 2t + (q >> 1)) ^ ((row >> 3) & 1)) + 2*(q & 1) + v,
+//   so one chunk = {(q,v=0), (q,v=1), (q+1,v=0), (q+1,v=1)}: pairs over v, matching the accumulator pairs (c0,c1)/(c2,c3).
+__device__ __forceinline__ void block_copy_w1v_frag(float* dst, const float* __restrict__ src) {
+  for (int idx = threadIdx.x; idx < 128 * 32; idx += blockDim.x) {
+    const int row = idx >> 5, f0 = (idx & 31) * 4;       // f0 = 32c + 8t + 4v, q = 0..3
+    const int v = (f0 >> 2) & 1, ct = f0 >> 3;           // ct = 4c + t
+    const float4 x = ldg4(src + 4 * idx);
+    const int sw = (row >> 3) & 1;
+    float* base = dst + row * CBG_H + v;
+    const int c0 = (2 * ct) ^ sw, c1 = (2 * ct + 1) ^ sw;
+    base[c0 * 4] = x.x; base[c0 * 4 + 2] = x.y; base[c1 * 4] = x.z; base[c1 * 4 + 2] = x.w;
+  }
+}
+
+constexpr int x2hk_mma_smem(int w) { return kX2hKFloats * 4 + w * ((int)sizeof(EdgeMeta) + 128 * 4); }
+constexpr int x2hv_mma_smem(int w) { return kX2hVFloats * 4 + w * (int)sizeof(EdgeMeta); }
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int kHead = 4 * 20 * 128 + 4 * 128 + 256;     // WRF | C | LN
+  const float* s_wrf = smem;
+  const float* s_c = s_wrf + 4 * 20 * 128;
+  const float* s_ln = s_c + 4 * 128;
+  const float* s_w1 = s_ln + 256;                          // fragment layout, see block_copy_w1*_frag
+  const float* s_rbf = s_w1 + 128 * 128;
+  EdgeMeta* metas = reinterpret_cast<EdgeMeta*>(smem + kX2hKFloats);
+  {
+    const float* src = p.layer + kOffX2hK;
+    block_copy_f4(smem, src, kHead);
+    block_copy_w1k_frag(smem + kHead, src + kHead);
+    block_copy_f4(smem + kHead + 128 * 128, src + kHead + 128 * 128, 32);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  EdgeMeta& M = metas[warp];
+  float* qst = reinterpret_cast<float*>(metas + kWarps) + warp * 128;   // per-warp staging of q_i
+
+  const int n_list = list_length(p);
+  for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
+    const int i = p.node_idx ? p.node_idx[n] : n;
+    const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    const float* rc = p.rc_k ? p.rc_k + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
+    const int nst = rc ? __popc(__ballot_sync(CBG_FULL, M.slot[lane] >= 0)) : 0;
+    {
+      const int nn = n + gridDim.x * kWarps;
+      if (nn < n_list) prefetch_rc(p.rc_k, p.node_idx ? p.node_idx[nn] : nn, lane);
+    }
+    // query-folded key matrix directly as A fragments: Uf[m][u] = {U[f][g], U[f][g+8], U[f+1][g], U[f+1][g+8]},
+    // f = 16m + 4t + 2u, U[f][hd] = sum_d q[hd*8+d] W1k[hd*8+d][f]
+    float4 Uf[8][2];
+    {
+      // stage q_i through shared memory so that (q of head g, q of head g+8) arrive as adjacent register pairs:
+      // element hd*8+d -> ((hd & 7)*8 + d)*2 + (hd >> 3)
+      {
+        const float4 q4 = ldg4(p.q + (size_t)i * CBG_H + 4 * lane);
+        const int hd = lane >> 1, d0 = 4 * (lane & 1);
+        float* dst = qst + ((hd & 7) * 8 + d0) * 2 + (hd >> 3);
+        dst[0] = q4.x; dst[2] = q4.y; dst[4] = q4.z; dst[6] = q4.w;
+      }
+      __syncwarp();
+      unsigned long long qp[8];
+#pragma unroll
+      for (int dd = 0; dd < 4; ++dd) {
+        const float4 v = ld4(qst + g * 16 + 4 * dd);
+        qp[2 * dd] = pack_f32x2(v.x, v.y);
+        qp[2 * dd + 1] = pack_f32x2(v.z, v.w);
+      }
+      unsigned long long Up[8][2][2];
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) Up[m][u][0] = Up[m][u][1] = 0ull;   // two +0.0f
+      const int sw = g & 1;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const float* row = s_w1 + (g * 8 + d) * 256;
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 w4 = ld4(row + 4 * ((8 * m + 2 * t + u) ^ sw));
+            Up[m][u][0] = fma_f32x2(pack_f32x2(w4.x, w4.y), qp[d], Up[m][u][0]);
+            Up[m][u][1] = fma_f32x2(pack_f32x2(w4.z, w4.w), qp[d], Up[m][u][1]);
+          }
+      }
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          unpack_f32x2(Up[m][u][0], Uf[m][u].x, Uf[m][u].y);
+          unpack_f32x2(Up[m][u][1], Uf[m][u].z, Uf[m][u].w);
+        }
+    }
+    const float* pik = p.pi_k + (size_t)i * CBG_H + 4 * t;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      float4 a[2][8];
+      float rstd[2];
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int nt = 2 * pass + rr;
+        const int e = g + 8 * nt;
+        const float* pj = p.pj_k + (size_t)M.j[e] * CBG_H + 4 * t;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) a[rr][m] = add4(ldg4(pik + 16 * m), ldg4(pj + 16 * m));
+        if (8 * nt + 7 < nst) {                                   // warp-uniform: the whole block is static
+          const float* r = rc + M.slot[e] * CBG_H + 4 * t;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) a[rr][m] = add4(a[rr][m], ldg4(r + 16 * m));
+        } else {
+          const int tt = M.t[e];
+          const float* cc = s_c + tt * CBG_H + 4 * t;
+#pragma unroll
+          for (int m = 0; m < 8; ++m) a[rr][m] = add4(a[rr][m], ld4(cc + 16 * m));
+          const float* w = s_wrf + tt * (CBG_NRBF * CBG_H) + 4 * t;
+#pragma unroll 2
+          for (int mm = 0; mm < CBG_NRBF; ++mm) {
+            const float gv = M.g[mm][e];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) fma4(a[rr][m], ld4(w + mm * CBG_H + 16 * m), gv);
+          }
+        }
+        // LayerNorm statistics: the row lives in the 4 lanes of the quad
+        float s = 0.f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) s += (a[rr][m].x + a[rr][m].y) + (a[rr][m].z + a[rr][m].w);
+        s += __shfl_xor_sync(CBG_FULL, s, 1);
+        s += __shfl_xor_sync(CBG_FULL, s, 2);
+        const float mean = s * (1.f / 128.f);
+        float v = 0.f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) { a[rr][m] = add4s(a[rr][m], -mean); v += dot4(a[rr][m], a[rr][m]); }
+        v += __shfl_xor_sync(CBG_FULL, v, 1);
+        v += __shfl_xor_sync(CBG_FULL, v, 2);
+        rstd[rr] = 1.f / sqrtf(v * (1.f / 128.f) + 1e-5f);
+      }
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float4 gamma = ld4(s_ln + 16 * m + 4 * t), beta = ld4(s_ln + 128 + 16 * m + 4 * t);
+        a[0][m] = ln_relu4(a[0][m], rstd[0], gamma, beta);
+        a[1][m] = ln_relu4(a[1][m], rstd[1], gamma, beta);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          // k-tile 2m+u: slot t <-> feature 16m+4t+2u, slot t+4 <-> feature 16m+4t+2u+1
+          const float af[4] = {Uf[m][u].x, Uf[m][u].y, Uf[m][u].z, Uf[m][u].w};
+          unsigned ah[4], al[4];
+          split_frag(af, ah, al);
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            const float bf[2] = {comp4(a[rr][m], 2 * u), comp4(a[rr][m], 2 * u + 1)};
+            unsigned bh[2], bl[2];
+            split_frag(bf, bh, bl);
+            mma3(acc[2 * pass + rr], ah, al, bh, bl);
+          }
+        }
+      }
+    }
+    // acc[nt][0..1]: head g, edges 8nt + 2t, 8nt + 2t + 1; acc[nt][2..3]: head g + 8.  Softmax over the 32 edges
+    // of a head = 8 values in this lane x the 4 lanes of the quad.
+    float* wout = p.w + (size_t)i * (CBG_KMAX * CBG_HEADS);
+#pragma unroll
+    for (int hs = 0; hs < 2; ++hs) {
+      float l[8];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const bool valid = (vmask >> (8 * nt + 2 * t + v)) & 1u;
+          l[2 * nt + v] = valid ? acc[nt][2 * hs + v] : -INFINITY;
+          mx = fmaxf(mx, l[2 * nt + v]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { l[k] = (mx == -INFINITY) ? 0.f : expf(l[k] - mx); sum += l[k]; }
+      sum += __shfl_xor_sync(CBG_FULL, sum, 1);
+      sum += __shfl_xor_sync(CBG_FULL, sum, 2);
+      const float inv = (sum > 0.f) ? sum : 1.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int e = 8 * nt + 2 * t + v;
+          wout[e * CBG_HEADS + g + 8 * hs] = (l[2 * nt + v] / inv) * M.ew[e];
+        }
+    }
+    __syncwarp();   // M is rewritten by the next node's setup
+  }
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_mma_kernel(EdgeArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int kHead = 4 * 20 * 128 + 4 * 128 + 256;     // WRF | C | LN
+  const float* s_wrf = smem;
+  const float* s_c = s_wrf + 4 * 20 * 128;
+  const float* s_ln = s_c + 4 * 128;
+  const float* s_w1 = s_ln + 256;                          // fragment layout, see block_copy_w1*_frag
+  const float* s_b1 = s_w1 + 128 * 128;
+  const float* s_rbf = s_b1 + 128;
+  EdgeMeta* metas = reinterpret_cast<EdgeMeta*>(smem + kX2hVFloats);
+  {
+    const float* src = p.layer + kOffX2hV;
+    block_copy_f4(smem, src, kHead);
+    block_copy_w1v_frag(smem + kHead, src + kHead);
+    block_copy_f4(smem + kHead + 128 * 128, src + kHead + 128 * 128, 128 + 32);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  EdgeMeta& M = metas[warp];
+
+  const int n_list = list_length(p);
+  for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
+    const int i = p.node_idx ? p.node_idx[n] : n;
+    edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    const float* rc = p.rc_v ? p.rc_v + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
+    const int nst = rc ? __popc(__ballot_sync(CBG_FULL, M.slot[lane] >= 0)) : 0;
+    {
+      const int nn = n + gridDim.x * kWarps;
+      if (nn < n_list) prefetch_rc(p.rc_v, p.node_idx ? p.node_idx[nn] : nn, lane);
+    }
+    // attention weights (alpha * e_w) as A fragments: row = head (g, g+8), column = edge (8kt+t, 8kt+t+4)
+    float wf[4][4];
+    float sw0 = 0.f, sw1 = 0.f;
+    {
+      const float* wsrc = p.w + (size_t)i * (CBG_KMAX * CBG_HEADS);
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt) {
+        const float* r0 = wsrc + (8 * kt + t) * CBG_HEADS + g;
+        wf[kt][0] = r0[0];
+        wf[kt][1] = r0[8];
+        wf[kt][2] = r0[4 * CBG_HEADS];
+        wf[kt][3] = r0[4 * CBG_HEADS + 8];
+        sw0 += wf[kt][0] + wf[kt][2];
+        sw1 += wf[kt][1] + wf[kt][3];
+      }
+      sw0 += __shfl_xor_sync(CBG_FULL, sw0, 1);
+      sw0 += __shfl_xor_sync(CBG_FULL, sw0, 2);
+      sw1 += __shfl_xor_sync(CBG_FULL, sw1, 1);
+      sw1 += __shfl_xor_sync(CBG_FULL, sw1, 2);
+    }
+    float4 pi4[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) pi4[c] = ldg4(p.pi_v + (size_t)i * CBG_H + 4 * (g + 8 * c));
+    // S[head][feature]: acc[c][q][0..1] = head g, features 32c + 8t + q and 32c + 8t + 4 + q; [2..3] = head g + 8
+    float acc[4][4][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[c][q][k] = 0.f;
+
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      // the two edges of this lane (k slots t and t+4 of the k-tile) are kept as packed pairs per feature:
+      // a2[c][q] = (edge e0, edge e1) of feature 32c + 4g + q  ==  the B fragment (b0, b1) of n-tile (c, q)
+      const int e0 = 8 * kt + t, e1 = e0 + 4;
+      float2 a2[4][4];
+      {
+        const float* pj0 = p.pj_v + (size_t)M.j[e0] * CBG_H + 4 * g;
+        const float* pj1 = p.pj_v + (size_t)M.j[e1] * CBG_H + 4 * g;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 x0 = ldg4(pj0 + 32 * c), x1 = ldg4(pj1 + 32 * c);
+          a2[c][0] = make_float2(pi4[c].x + x0.x, pi4[c].x + x1.x);
+          a2[c][1] = make_float2(pi4[c].y + x0.y, pi4[c].y + x1.y);
+          a2[c][2] = make_float2(pi4[c].z + x0.z, pi4[c].z + x1.z);
+          a2[c][3] = make_float2(pi4[c].w + x0.w, pi4[c].w + x1.w);
+        }
+      }
+      if (8 * kt + 7 < nst) {                                   // warp-uniform: the whole block is static
+        const float* r0 = rc + M.slot[e0] * CBG_H + 4 * g;
+        const float* r1 = rc + M.slot[e1] * CBG_H + 4 * g;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 x0 = ldg4(r0 + 32 * c), x1 = ldg4(r1 + 32 * c);
+          a2[c][0].x += x0.x; a2[c][0].y += x1.x;
+          a2[c][1].x += x0.y; a2[c][1].y += x1.y;
+          a2[c][2].x += x0.z; a2[c][2].y += x1.z;
+          a2[c][3].x += x0.w; a2[c][3].y += x1.w;
+        }
+      } else {
+        const int t0 = M.t[e0], t1 = M.t[e1];
+        const float* c0p = s_c + t0 * CBG_H + 4 * g;
+        const float* c1p = s_c + t1 * CBG_H + 4 * g;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 x0 = ld4(c0p + 32 * c), x1 = ld4(c1p + 32 * c);
+          a2[c][0].x += x0.x; a2[c][0].y += x1.x;
+          a2[c][1].x += x0.y; a2[c][1].y += x1.y;
+          a2[c][2].x += x0.z; a2[c][2].y += x1.z;
+          a2[c][3].x += x0.w; a2[c][3].y += x1.w;
+        }
+        const float* w0 = s_wrf + t0 * (CBG_NRBF * CBG_H) + 4 * g;
+        if (t0 == t1) {                                          // same weight rows for both edges: packed FMAs
+#pragma unroll 4
+          for (int mm = 0; mm < CBG_NRBF; ++mm) {
+            const float2 gp = make_float2(M.g[mm][e0], M.g[mm][e1]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 wv = ld4(w0 + mm * CBG_H + 32 * c);
+              a2[c][0] = __ffma2_rn(gp, make_float2(wv.x, wv.x), a2[c][0]);
+              a2[c][1] = __ffma2_rn(gp, make_float2(wv.y, wv.y), a2[c][1]);
+              a2[c][2] = __ffma2_rn(gp, make_float2(wv.z, wv.z), a2[c][2]);
+              a2[c][3] = __ffma2_rn(gp, make_float2(wv.w, wv.w), a2[c][3]);
+            }
+          }
+        } else {
+          const float* w1 = s_wrf + t1 * (CBG_NRBF * CBG_H) + 4 * g;
+#pragma unroll 1
+          for (int mm = 0; mm < CBG_NRBF; ++mm) {
+            const float g0 = M.g[mm][e0], g1 = M.g[mm][e1];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 wa = ld4(w0 + mm * CBG_H + 32 * c), wb = ld4(w1 + mm * CBG_H + 32 * c);
+              a2[c][0].x = fmaf(wa.x, g0, a2[c][0].x); a2[c][0].y = fmaf(wb.x, g1, a2[c][0].y);
+              a2[c][1].x = fmaf(wa.y, g0, a2[c][1].x); a2[c][1].y = fmaf(wb.y, g1, a2[c][1].y);
+              a2[c][2].x = fmaf(wa.z, g0, a2[c][2].x); a2[c][2].y = fmaf(wb.z, g1, a2[c][2].y);
+              a2[c][3].x = fmaf(wa.w, g0, a2[c][3].x); a2[c][3].y = fmaf(wb.w, g1, a2[c][3].y);
+            }
+          }
+        }
+      }
+      // LayerNorm statistics of both edges at once; a row lives in the 8 lanes with the same t
+      float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        s2 = __fadd2_rn(s2, __fadd2_rn(__fadd2_rn(a2[c][0], a2[c][1]), __fadd2_rn(a2[c][2], a2[c][3])));
+#pragma unroll
+      for (int sh = 4; sh <= 16; sh <<= 1) {
+        s2.x += __shfl_xor_sync(CBG_FULL, s2.x, sh);
+        s2.y += __shfl_xor_sync(CBG_FULL, s2.y, sh);
+      }
+      const float2 nmean = make_float2(-s2.x * (1.f / 128.f), -s2.y * (1.f / 128.f));
+      float2 v2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a2[c][q] = __fadd2_rn(a2[c][q], nmean);
+          v2 = __ffma2_rn(a2[c][q], a2[c][q], v2);
+        }
+#pragma unroll
+      for (int sh = 4; sh <= 16; sh <<= 1) {
+        v2.x += __shfl_xor_sync(CBG_FULL, v2.x, sh);
+        v2.y += __shfl_xor_sync(CBG_FULL, v2.y, sh);
+      }
+      const float2 rstd2 = make_float2(1.f / sqrtf(v2.x * (1.f / 128.f) + 1e-5f), 1.f / sqrtf(v2.y * (1.f / 128.f) + 1e-5f));
+      unsigned ah[4], al[4];
+      split_frag(wf[kt], ah, al);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 gamma = ld4(s_ln + 32 * c + 4 * g), beta = ld4(s_ln + 128 + 32 * c + 4 * g);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // n-tile (c, q): column g <-> feature 32c + 4g + q ; k slots t, t+4 <-> edges e0, e1
+          const float gq = comp4(gamma, q), bq = comp4(beta, q);
+          const float2 y = __ffma2_rn(__fmul2_rn(a2[c][q], rstd2), make_float2(gq, gq), make_float2(bq, bq));
+          const float bf[2] = {fmaxf(y.x, 0.f), fmaxf(y.y, 0.f)};
+          unsigned bh[2], bl[2];
+          split_frag(bf, bh, bl);
+          mma3(acc[c][q], ah, al, bh, bl);
+        }
+      }
+    }
+    // out[f'] = W1v[f'][:] . S[head(f')][:] : this lane owns heads g, g+8 and the features 32c + 8t + 4v + q,
+    // so it forms 16 partial sums (2 heads x 8 rows of W1v), which are then reduced over the quad.
+    float part[16];
+    const int sw = g & 1;
+#pragma unroll
+    for (int sel = 0; sel < 2; ++sel)
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const float* wrow = s_w1 + ((g + 8 * sel) * 8 + d) * CBG_H;
+        float2 t2 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            // chunk = {(q=2hq, v=0), (q=2hq, v=1), (q=2hq+1, v=0), (q=2hq+1, v=1)}; accumulator pairs are (v=0, v=1)
+            const float4 w4 = ld4(wrow + 4 * ((8 * c + 2 * t + hq) ^ sw));
+            t2 = __ffma2_rn(make_float2(w4.x, w4.y), make_float2(acc[c][2 * hq][2 * sel], acc[c][2 * hq][2 * sel + 1]), t2);
+            t2 = __ffma2_rn(make_float2(w4.z, w4.w), make_float2(acc[c][2 * hq + 1][2 * sel], acc[c][2 * hq + 1][2 * sel + 1]), t2);
+          }
+        part[sel * 8 + d] = t2.x + t2.y;
+      }
+    {   // quad bit 1 <-> head select
+      const bool up = (t & 2) != 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float send = up ? part[k] : part[k + 8];
+        const float keep = up ? part[k + 8] : part[k];
+        part[k] = keep + __shfl_xor_sync(CBG_FULL, send, 2);
+      }
+    }
+    {   // quad bit 0 <-> upper / lower 4 rows of the head
+      const bool up = (t & 1) != 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float send = up ? part[k] : part[k + 4];
+        const float keep = up ? part[k + 4] : part[k];
+        part[k] = keep + __shfl_xor_sync(CBG_FULL, send, 1);
+      }
+    }
+    {
+      const int sel = (t >> 1) & 1;
+      const int f0 = (g + 8 * sel) * 8 + 4 * (t & 1);
+      const float swh = sel ? sw1 : sw0;
+      float* hrow = p.h + (size_t)i * CBG_H + f0;
+      const float4 hin = ld4(hrow), b1 = ld4(s_b1 + f0);
+      st4(hrow, make_float4(hin.x + (part[0] + b1.x * swh), hin.y + (part[1] + b1.y * swh),
+                            hin.z + (part[2] + b1.z * swh), hin.w + (part[3] + b1.w * swh)));
+    }
+    __syncwarp();
+  }
+}
+
 int g_num_sms = 0;
 int g_edge_warps = 12;
+int g_edge_impl = 1;       // 1: tensor-core X2H kernels (default), 0: fp32 SIMT kernels
+int g_edge_mma_warps = 8;
 
 template <int W>
 int set_attrs() {
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(h2x_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_smem(W)));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma_smem(W)));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_mma_smem(W)));
   return 0;
 }
 
@@ -645,6 +1158,21 @@ int launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
   x2h_v_kernel<W><<<grid, W * 32, x2hv_smem(W), st>>>(a);
+  CBG_LAUNCHED(CBG_K_X2H_V, st);
+  return 0;
+}
+
+// impl 1: both kernels on the tensor cores; 2: tensor-core x2h_k + SIMT x2h_v; 3: SIMT x2h_k + tensor-core x2h_v
+// (the two halves agree on the layout of w, so they can be mixed: used by the tests to localise a mismatch)
+template <int W, int WS>
+int launch_x2h_mma(const EdgeArgs& a, cudaStream_t st, int impl) {
+  CBG_PROF_BEGIN(CBG_K_X2H_K, st);
+  if (impl == 3) x2h_k_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hk_smem(WS), st>>>(a);
+  else x2h_k_mma_kernel<W><<<edge_grid(a.n_nodes, W), W * 32, x2hk_mma_smem(W), st>>>(a);
+  CBG_LAUNCHED(CBG_K_X2H_K, st);
+  CBG_PROF_BEGIN(CBG_K_X2H_V, st);
+  if (impl == 2) x2h_v_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hv_smem(WS), st>>>(a);
+  else x2h_v_mma_kernel<W><<<edge_grid(a.n_nodes, W), W * 32, x2hv_mma_smem(W), st>>>(a);
   CBG_LAUNCHED(CBG_K_X2H_V, st);
   return 0;
 }
@@ -669,6 +1197,14 @@ int cbg_edge_init(void) {
   if (const char* e = getenv("CBG_EDGE_WARPS")) {
     const int w = atoi(e);
     if (w == 8 || w == 12 || w == 16) g_edge_warps = w;
+  }
+  if (const char* e = getenv("CBG_EDGE_IMPL")) {
+    if (strcmp(e, "simt") == 0) g_edge_impl = 0;
+    else if (e[0] >= '0' && e[0] <= '3' && e[1] == 0) g_edge_impl = e[0] - '0';
+  }
+  if (const char* e = getenv("CBG_EDGE_MMA_WARPS")) {
+    const int w = atoi(e);
+    if (w == 8 || w == 12 || w == 16) g_edge_mma_warps = w;
   }
   if (int rc = set_attrs<8>()) return rc;
   if (int rc = set_attrs<12>()) return rc;
@@ -697,6 +1233,13 @@ int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, con
 int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
+  if (g_edge_impl >= 1) {
+    switch (g_edge_mma_warps) {
+      case 12: return launch_x2h_mma<12, 12>(a, st, g_edge_impl);
+      case 16: return launch_x2h_mma<16, 12>(a, st, g_edge_impl);
+      default: return launch_x2h_mma<8, 12>(a, st, g_edge_impl);
+    }
+  }
   switch (g_edge_warps) {
     case 8: return launch_x2h<8>(a, st);
     case 16: return launch_x2h<16>(a, st);
@@ -712,4 +1255,14 @@ int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
     case 16: return launch_h2x<16>(a, st);
     default: return launch_h2x<12>(a, st);
   }
+}
+
+// testing / tuning hook (include/cbg_b200.h): pick the X2H edge-kernel implementation and its warps per CTA
+int cbg_edge_set_impl(int impl, int warps) {
+  if (int rc = cbg_edge_init()) return rc;
+  if (impl < 0 || impl > 3) { cbg_set_error("edge impl must be 0 (simt), 1 (mma), 2 (mma k + simt v) or 3 (simt k + mma v)"); return 1; }
+  if (warps != 0 && warps != 8 && warps != 12 && warps != 16) { cbg_set_error("warps per CTA must be 8, 12 or 16"); return 1; }
+  g_edge_impl = impl;
+  if (warps) { if (impl) g_edge_mma_warps = warps; else g_edge_warps = warps; }
+  return 0;
 }

@@ -51,6 +51,13 @@ const char* cbg_profile_family_name(int32_t i);
 int32_t cbg_profile_enable(int32_t on);
 int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family);
 
+/* Tuning / testing hook: implementation of the two fused X2H edge kernels (the dominant kernels of a step).
+ *   impl 1 (default): per-node contractions on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split, fp32 accumulate)
+ *   impl 0: fp32 SIMT kernels;  2 / 3: tensor-core attention-weight kernel + SIMT aggregation kernel / the reverse
+ * warps = CTA size in warps (8, 12, 16; 0 keeps the current value).  Process-wide; also env CBG_EDGE_IMPL,
+ * CBG_EDGE_MMA_WARPS, CBG_EDGE_WARPS.  Needs a current CUDA device. */
+int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);
+
 /* ---- packed weight blob layout (single source of truth: csrc/cbg_layout.h) -------------------
  * blob = [global section][layer 0][layer 1]...; section 0 = global, 1 = per-layer.
  * Replaces the nn.Module parameter tree of UniTransformer (state-dict keys in SURVEY.md section 8b). */

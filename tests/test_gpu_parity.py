@@ -483,3 +483,69 @@ def test_sample_driver_single_gpu(tmp_path):
         assert ra['pos'].shape == (6, 3) and ra['v'].shape == (6,)
         assert torch.equal(ra['pos'], rb['pos']) and torch.equal(ra['v'], rb['v'])
         assert torch.isfinite(ra['pos']).all() and int(ra['v'].max()) < 13
+
+
+# ---------------------------------------------------------------------------------------------
+# the two implementations of the fused X2H edge kernels (tensor-core mma.sync 3xTF32 vs fp32 SIMT)
+EDGE_IMPLS = {0: 'simt', 1: 'mma', 2: 'mma_k+simt_v', 3: 'simt_k+mma_v'}
+
+
+@pytest.fixture
+def edge_impl_reset():
+    yield
+    _lib.check(_lib.lib().cbg_set_edge_impl(1, 8))
+    _lib.check(_lib.lib().cbg_set_edge_impl(0, 12))
+    _lib.check(_lib.lib().cbg_set_edge_impl(1, 0))
+
+
+@pytest.mark.parametrize('case', FORWARD_CASES, ids=[c[0] for c in FORWARD_CASES])
+def test_edge_kernel_implementations_agree(case, edge_impl_reset):
+    """Every implementation of the X2H kernels (and the two mixed pairings, which localise a mismatch to the
+    attention-weight or the aggregation kernel) must match the reference golden and each other."""
+    name, n_prot, n_lig, seed, gen_mode, enc = case
+    gold = golden('forward_cases.npz')
+    model, sd = make_model(10, device=dev(), **enc)
+    batch = synthetic.make_batch(n_prot, n_lig, seed=seed, gen_mode=gen_mode)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    args = [t.to(dev()) for t in (x, h, bidx, lig, gen)]
+    outs, report = {}, []
+    for impl, label in EDGE_IMPLS.items():
+        for warps in ((8, 12) if impl == 1 else (0,)):
+            _lib.check(_lib.lib().cbg_set_edge_impl(impl, warps))
+            h1 = model.denoiser(*args, stop_after_layers=1)[1].cpu()
+            xg, hg, cg = (t.cpu() for t in model.denoiser(*args))
+            outs[(impl, warps)] = (h1, xg, hg, cg)
+            errs = [rel_err(a, gold[f'{name}/{k}']) for a, k in ((xg, 'x'), (hg, 'h'), (cg, 'c'))]
+            report.append(f'{label}/w{warps}: x {errs[0]:.1e} h {errs[1]:.1e} c {errs[2]:.1e}')
+    base = outs[(0, 0)]
+    bad = []
+    for key, o in outs.items():
+        d1, dx, dh = rel_err(o[0], base[0]), rel_err(o[1], base[1]), rel_err(o[2], base[2])
+        report.append(f'{EDGE_IMPLS[key[0]]}/w{key[1]} vs simt: h(1 layer) {d1:.1e} x {dx:.1e} h {dh:.1e}')
+        if not (d1 < 1e-5 and dx < 1e-4 and dh < 1e-4) or not torch.isfinite(o[2]).all():
+            bad.append(key)
+    assert not bad, f'{name}: ' + ' | '.join(report)
+    for (impl, warps), o in outs.items():
+        for a, k in ((o[1], 'x'), (o[2], 'h'), (o[3], 'c')):
+            assert rel_err(a, gold[f'{name}/{k}']) < TOL, f'{name}: ' + ' | '.join(report)
+
+
+def test_edge_kernel_implementations_agree_on_the_sampling_path(edge_impl_reset):
+    """Sampling path (R-cache, static lists, pruning on): tensor-core and SIMT kernels give the same atom types and
+    coordinates equal to rounding; also with the R-cache off (every block takes the in-register RBF path)."""
+    T = 5
+    for gen_mode, sizes in (('denovo', ([140, 60, 20], [20, 9, 5])), ('partial', ([90, 70], [18, 12]))):
+        model, sd = make_model(T, device=dev())
+        batch = synthetic.make_batch(*sizes, seed=131, gen_mode=gen_mode)
+        n_lig = int(batch['ligand_pos'].shape[0])
+        pn, tu = synthetic.make_noise(T, n_lig, 13, seed=19)
+        for rcache in (True, False):
+            model.use_rcache = rcache
+            res = {}
+            for impl in (0, 1):
+                _lib.check(_lib.lib().cbg_set_edge_impl(impl, 0))
+                res[impl] = model.sample(batch, pos_noise=pn, type_uniform=tu)
+            for t in range(-1, T):
+                assert torch.equal(res[0][t][1].cpu().argmax(-1), res[1][t][1].cpu().argmax(-1)), (gen_mode, rcache, t)
+                e = rel_err(res[1][t][0].cpu(), res[0][t][0].cpu())
+                assert e < 1e-5, (gen_mode, rcache, t, e)
