@@ -303,7 +303,6 @@ int32_t cbg_version(void) { return 100; }
 const char* cbg_last_error(void) { return g_err; }
 int64_t cbg_launch_count(void) { return g_cbg_launches; }
 
-int cbg_edge_set_impl(int impl, int warps);
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps) { return cbg_edge_set_impl(impl, warps); }
 
 int32_t cbg_profile_num_families(void) { return CBG_K_COUNT; }
