@@ -652,4 +652,43 @@ int32_t cbg_reverse_step_f32(const cbg_step_coef* coef, const float* x0_pred, co
   return cbg_launch_reverse(r, coef->pos_logvar, coef->pos_nonzero, (cudaStream_t)stream);
 }
 
+// ---- row f3: device-side batch construction ---------------------------------------------------------------------
+int32_t cbg_pocket_stats_f32(const float* prot_pos, const int32_t* prot_ptr, int32_t n_pockets, const float* ctx_pos,
+                             const int32_t* ctx_ptr, int32_t centre_mode, float* space_size, float* centre, void* stream) {
+  if (n_pockets < 0 || (n_pockets > 0 && (!prot_pos || !prot_ptr || !space_size || !centre))) { cbg_set_error("cbg_pocket_stats_f32: null argument"); return 1; }
+  if (centre_mode != 0 && centre_mode != 1) { cbg_set_error("centre_mode must be 0 (pocket mean) or 1 (context mean)"); return 1; }
+  if (centre_mode == 1 && (!ctx_ptr || !ctx_pos)) { cbg_set_error("centre_mode 1 needs ctx_pos and ctx_ptr"); return 1; }
+  return cbg_launch_pocket_stats(prot_pos, prot_ptr, n_pockets, ctx_pos, ctx_ptr, centre_mode, space_size, centre, (cudaStream_t)stream);
+}
+
+int32_t cbg_sample_ligand_sizes(const cbg_size_prior* prior, const float* space_size, int32_t n_pockets, int32_t repeat,
+                                const double* u, const int32_t* ctx_ptr, const int32_t* extra, int32_t* n_lig,
+                                int32_t* lig_ptr, void* stream) {
+  if (!prior || !prior->bounds || !prior->bin_ptr || !prior->values || !prior->cdf || prior->n_bounds < 0) { cbg_set_error("cbg_sample_ligand_sizes: bad size prior"); return 1; }
+  if (n_pockets < 0 || repeat < 0 || !space_size || !u || !n_lig || !lig_ptr) { cbg_set_error("cbg_sample_ligand_sizes: null argument"); return 1; }
+  if (ctx_ptr && !extra) { cbg_set_error("context tasks need the extra[] draws"); return 1; }
+  return cbg_launch_ligand_sizes(prior->bounds, prior->n_bounds, prior->bin_ptr, prior->values, prior->cdf, space_size,
+                                 n_pockets, repeat, u, ctx_ptr, extra, n_lig, lig_ptr, (cudaStream_t)stream);
+}
+
+int32_t cbg_build_batch_f32(const cbg_batch_spec* b, void* stream) {
+  if (!b) { cbg_set_error("cbg_build_batch_f32: null spec"); return 1; }
+  if (!b->prot_pos || !b->prot_element || !b->prot_backbone || !b->prot_aa || !b->prot_ptr || !b->centre || !b->lig_ptr ||
+      !b->pos_noise || !b->protein_pos || !b->protein_atom_feature || !b->protein_aa_type || !b->protein_element_batch ||
+      !b->protein_translation || !b->ligand_pos || !b->ligand_atom_type || !b->ligand_element_batch) {
+    cbg_set_error("cbg_build_batch_f32: null argument"); return 1;
+  }
+  if (b->type_dist != CBG_TYPE_UNIFORM && b->type_dist != CBG_TYPE_ABSORBING) { cbg_set_error("unknown type_dist"); return 1; }
+  if (b->type_dist == CBG_TYPE_UNIFORM && (!b->type_u || b->num_classes <= 0)) { cbg_set_error("uniform types need type_u and num_classes"); return 1; }
+  if (b->pos_dist != CBG_POS_GAUSSIAN && b->pos_dist != CBG_POS_ZERO_MEAN_GAUSSIAN) { cbg_set_error("unknown pos_dist"); return 1; }
+  if (b->ctx_ptr && (!b->ctx_pos || !b->ctx_type)) { cbg_set_error("ctx_ptr needs ctx_pos and ctx_type"); return 1; }
+  if (b->ctx_ptr && b->pos_dist == CBG_POS_ZERO_MEAN_GAUSSIAN) { cbg_set_error("zero_mean_gaussian is a de-novo option"); return 1; }
+  return cbg_launch_build_batch(b->prot_pos, b->prot_element, b->prot_backbone, b->prot_aa, b->prot_ptr, b->n_pockets, b->repeat,
+                                b->centre, b->ctx_pos, b->ctx_type, b->ctx_ptr, b->lig_ptr, b->pos_noise, b->type_u,
+                                b->num_classes, b->type_dist, b->pos_dist, b->protein_pos, b->protein_atom_feature,
+                                (long long*)b->protein_aa_type, (long long*)b->protein_element_batch, b->protein_translation,
+                                b->ligand_pos, (long long*)b->ligand_atom_type, (long long*)b->ligand_element_batch,
+                                b->ligand_ctx_flag, b->ligand_gen_flag, (cudaStream_t)stream);
+}
+
 }  // extern "C"

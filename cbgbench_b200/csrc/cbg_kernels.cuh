@@ -160,3 +160,17 @@ struct BpArgs {
   float* eps_out;           // optional [n_lig,3]
 };
 int cbg_launch_bp_reverse(const BpArgs& a, cudaStream_t st);
+
+// batch.cu (row f3: device-side batch construction)
+int cbg_launch_pocket_stats(const float* prot_pos, const int* prot_ptr, int n_pockets, const float* ctx_pos,
+                            const int* ctx_ptr, int centre_mode, float* space_size, float* centre, cudaStream_t st);
+int cbg_launch_ligand_sizes(const double* bounds, int n_bounds, const int* bin_ptr, const int* values, const double* cdf,
+                            const float* space_size, int n_pockets, int repeat, const double* u, const int* ctx_ptr,
+                            const int* extra, int* n_lig, int* lig_ptr, cudaStream_t st);
+int cbg_launch_build_batch(const float* prot_pos, const int* prot_element, const unsigned char* prot_backbone,
+                           const int* prot_aa, const int* prot_ptr, int n_pockets, int repeat, const float* centre,
+                           const float* ctx_pos, const int* ctx_type, const int* ctx_ptr, const int* lig_ptr,
+                           const float* pos_noise, const float* type_u, int num_classes, int type_dist, int pos_dist,
+                           float* o_prot_pos, float* o_prot_feat, long long* o_prot_aa, long long* o_prot_batch,
+                           float* o_prot_tr, float* o_lig_pos, long long* o_lig_type, long long* o_lig_batch,
+                           unsigned char* o_lig_ctx, unsigned char* o_lig_gen, cudaStream_t st);

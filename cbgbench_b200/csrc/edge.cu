@@ -715,10 +715,12 @@ __device__ __forceinline__ void block_copy_w1v_frag(float* dst, const float* __r
   }
 }
 
-constexpr int x2hk_mma_smem(int w) { return kX2hKFloats * 4 + w * ((int)sizeof(EdgeMeta) + 128 * 4); }
-constexpr int x2hv_mma_smem(int w) { return kX2hVFloats * 4 + w * (int)sizeof(EdgeMeta); }
+constexpr int x2hk_mma_smem(int w) { return kX2hKFloats * 4 + w * ((int)sizeof(EdgeMeta) + 256 * 4); }   // + q_i | Pi_i staging
+constexpr int x2hv_mma_smem(int w) { return kX2hVFloats * 4 + w * ((int)sizeof(EdgeMeta) + 128 * 4); }   // + Pi_i staging
 
-template <int kWarps>
+// RP = edge blocks (rows of this lane) per pass: 2 keeps 64 registers of activations live and splits U once per two
+// rows; 1 halves that (fits 12 warps per CTA) and splits U once per row.
+template <int kWarps, int RP>
 __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int kHead = 4 * 20 * 128 + 4 * 128 + 256;     // WRF | C | LN
@@ -738,7 +740,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   EdgeMeta& M = metas[warp];
-  float* qst = reinterpret_cast<float*>(metas + kWarps) + warp * 128;   // per-warp staging of q_i
+  float* qst = reinterpret_cast<float*>(metas + kWarps) + warp * 256;   // per-warp staging of q_i (fragment order) | Pi_i
+  float* pist = qst + 128;
 
   const int n_list = list_length(p);
   for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
@@ -761,6 +764,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
         const int hd = lane >> 1, d0 = 4 * (lane & 1);
         float* dst = qst + ((hd & 7) * 8 + d0) * 2 + (hd >> 3);
         dst[0] = q4.x; dst[2] = q4.y; dst[4] = q4.z; dst[6] = q4.w;
+        st4(pist + 4 * lane, ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane));   // Pi row: read back per edge block via LDS
       }
       __syncwarp();
       unsigned long long qp[8];
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
           unpack_f32x2(Up[m][u][1], Uf[m][u].z, Uf[m][u].w);
         }
     }
-    const float* pik = p.pi_k + (size_t)i * CBG_H + 4 * t;
+    const float* pik = pist + 4 * t;
     float acc[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -804,16 +808,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
       for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
 
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      float4 a[2][8];
-      float rstd[2];
+    for (int pass = 0; pass < 4 / RP; ++pass) {
+      float4 a[RP][8];
+      float rstd[RP];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int nt = 2 * pass + rr;
+      for (int rr = 0; rr < RP; ++rr) {
+        const int nt = RP * pass + rr;
         const int e = g + 8 * nt;
         const float* pj = p.pj_k + (size_t)M.j[e] * CBG_H + 4 * t;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) a[rr][m] = add4(ldg4(pik + 16 * m), ldg4(pj + 16 * m));
+        for (int m = 0; m < 8; ++m) a[rr][m] = add4(ld4(pik + 16 * m), ldg4(pj + 16 * m));
         if (8 * nt + 7 < nst) {                                   // warp-uniform: the whole block is static
           const float* r = rc + M.slot[e] * CBG_H + 4 * t;
 #pragma unroll
@@ -848,8 +852,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
         const float4 gamma = ld4(s_ln + 16 * m + 4 * t), beta = ld4(s_ln + 128 + 16 * m + 4 * t);
-        a[0][m] = ln_relu4(a[0][m], rstd[0], gamma, beta);
-        a[1][m] = ln_relu4(a[1][m], rstd[1], gamma, beta);
+#pragma unroll
+        for (int rr = 0; rr < RP; ++rr) a[rr][m] = ln_relu4(a[rr][m], rstd[rr], gamma, beta);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           // k-tile 2m+u: slot t <-> feature 16m+4t+2u, slot t+4 <-> feature 16m+4t+2u+1
@@ -857,11 +861,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
           unsigned ah[4], al[4];
           split_frag(af, ah, al);
 #pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {
+          for (int rr = 0; rr < RP; ++rr) {
             const float bf[2] = {comp4(a[rr][m], 2 * u), comp4(a[rr][m], 2 * u + 1)};
             unsigned bh[2], bl[2];
             split_frag(bf, bh, bl);
-            mma3(acc[2 * pass + rr], ah, al, bh, bl);
+            mma3(acc[RP * pass + rr], ah, al, bh, bl);
           }
         }
       }
@@ -922,6 +926,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_mma_kernel(EdgeArgs p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   EdgeMeta& M = metas[warp];
+  float* pist = reinterpret_cast<float*>(metas + kWarps) + warp * 128;   // per-warp staging of Pi_i
 
   const int n_list = list_length(p);
   for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
@@ -953,9 +958,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_mma_kernel(EdgeArgs p) {
       sw1 += __shfl_xor_sync(CBG_FULL, sw1, 1);
       sw1 += __shfl_xor_sync(CBG_FULL, sw1, 2);
     }
-    float4 pi4[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) pi4[c] = ldg4(p.pi_v + (size_t)i * CBG_H + 4 * (g + 8 * c));
+    st4(pist + 4 * lane, ldg4(p.pi_v + (size_t)i * CBG_H + 4 * lane));     // Pi row staged in shared memory, re-read per k-tile
+    __syncwarp();
     // S[head][feature]: acc[c][q][0..1] = head g, features 32c + 8t + q and 32c + 8t + 4 + q; [2..3] = head g + 8
     float acc[4][4][4];
 #pragma unroll
@@ -976,11 +980,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_mma_kernel(EdgeArgs p) {
         const float* pj1 = p.pj_v + (size_t)M.j[e1] * CBG_H + 4 * g;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float4 x0 = ldg4(pj0 + 32 * c), x1 = ldg4(pj1 + 32 * c);
-          a2[c][0] = make_float2(pi4[c].x + x0.x, pi4[c].x + x1.x);
-          a2[c][1] = make_float2(pi4[c].y + x0.y, pi4[c].y + x1.y);
-          a2[c][2] = make_float2(pi4[c].z + x0.z, pi4[c].z + x1.z);
-          a2[c][3] = make_float2(pi4[c].w + x0.w, pi4[c].w + x1.w);
+          const float4 x0 = ldg4(pj0 + 32 * c), x1 = ldg4(pj1 + 32 * c), pi4 = ld4(pist + 4 * g + 32 * c);
+          a2[c][0] = make_float2(pi4.x + x0.x, pi4.x + x1.x);
+          a2[c][1] = make_float2(pi4.y + x0.y, pi4.y + x1.y);
+          a2[c][2] = make_float2(pi4.z + x0.z, pi4.z + x1.z);
+          a2[c][3] = make_float2(pi4.w + x0.w, pi4.w + x1.w);
         }
       }
       if (8 * kt + 7 < nst) {                                   // warp-uniform: the whole block is static
@@ -1132,7 +1136,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_mma_kernel(EdgeArgs p) {
 
 int g_num_sms = 0;
 int g_edge_warps = 12;
-int g_edge_impl = 1;       // 1: tensor-core X2H kernels (default), 0: fp32 SIMT kernels
+int g_edge_impl = 2;       // 2 (default, fastest measured): tensor-core x2h_k + SIMT x2h_v; 1: both tensor-core; 0: both SIMT; 3: SIMT k + tensor-core v
 int g_edge_mma_warps = 8;
 
 template <int W>
@@ -1140,7 +1144,7 @@ int set_attrs() {
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(h2x_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_smem(W)));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma_smem(W)));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma_kernel<W, (W > 8 ? 1 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_mma_smem(W)));
   return 0;
 }
@@ -1168,7 +1172,7 @@ template <int W, int WS>
 int launch_x2h_mma(const EdgeArgs& a, cudaStream_t st, int impl) {
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
   if (impl == 3) x2h_k_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hk_smem(WS), st>>>(a);
-  else x2h_k_mma_kernel<W><<<edge_grid(a.n_nodes, W), W * 32, x2hk_mma_smem(W), st>>>(a);
+  else x2h_k_mma_kernel<W, (W > 8 ? 1 : 2)><<<edge_grid(a.n_nodes, W), W * 32, x2hk_mma_smem(W), st>>>(a);
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
   if (impl == 2) x2h_v_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hv_smem(WS), st>>>(a);

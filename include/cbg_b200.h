@@ -52,8 +52,9 @@ int32_t cbg_profile_enable(int32_t on);
 int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family);
 
 /* Tuning / testing hook: implementation of the two fused X2H edge kernels (the dominant kernels of a step).
- *   impl 1 (default): per-node contractions on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split, fp32 accumulate)
- *   impl 0: fp32 SIMT kernels;  2 / 3: tensor-core attention-weight kernel + SIMT aggregation kernel / the reverse
+ *   impl 1: per-node contractions of both kernels on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split, fp32 accumulate)
+ *   impl 0: fp32 SIMT kernels;  2 (default, fastest measured) / 3: tensor-core attention-weight kernel + SIMT
+ *   aggregation kernel / the reverse pairing
  * warps = CTA size in warps (8, 12, 16; 0 keeps the current value).  Process-wide; also env CBG_EDGE_IMPL,
  * CBG_EDGE_MMA_WARPS, CBG_EDGE_WARPS.  Needs a current CUDA device. */
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);
@@ -233,6 +234,87 @@ int32_t cbg_bp_step_f32(const cbg_sample_plan* plan, const float* com_blob, int3
                         float* x_next /*[n_lig,3]*/, float* c_next /*[n_lig,K]*/, int64_t* v_next /*[n_lig]*/,
                         float* eps_out /*[n_lig,3] or NULL: eps + eps_com*/, float* logits /*[n_lig,K] or NULL*/,
                         void* stream);
+
+/* ---- sampling-time transforms + batch construction on the device ------------------
+ *
+ * The reference builds a sampling batch by evaluating dataset[i] num_samples times (sample.py:177), i.e. by running
+ * the Python transform list of configs/<task>/test/<model>.yml once per sample, and collating with PyG.  The three calls
+ * below produce the same flat batch from the raw pocket arrays on the device.  Pockets are ragged ranges
+ * (prot_ptr[n_pockets+1]); every pocket is sampled `repeat` times; sample s belongs to pocket s / repeat.
+ * Random numbers are the caller's (numpy / torch order of the reference: one uniform per sample for the size prior,
+ * optionally one randint(1, 8), then rand [n, K] for the types and randn [n, 3] for the positions). */
+
+/* Pocket centre and "space size".
+ *   centre_mode 0: centre = mean of the pocket atoms (center_pos(center_flag=protein), translation.py:11-24, and
+ *                  center_whole_pos without a ligand, :36-50); space size measured on the centred coordinates
+ *   centre_mode 1: centre = mean of the pocket's context ligand atoms, 0 if it has none (center_pos(ligand,
+ *                  mask_flag=ctx_flag)); space size measured on the raw coordinates (assign_gensize runs first)
+ * space_size = median of the 10 largest pairwise atom distances (AssignMolSize.get_space_size, init_lig.py:247-250). */
+int32_t cbg_pocket_stats_f32(const float* prot_pos /*[n_atoms,3]*/, const int32_t* prot_ptr /*[n_pockets+1]*/,
+                             int32_t n_pockets, const float* ctx_pos /*[n_ctx,3] or NULL*/,
+                             const int32_t* ctx_ptr /*[n_pockets+1] or NULL*/, int32_t centre_mode,
+                             float* space_size /*[n_pockets] out*/, float* centre /*[n_pockets,3] out*/, void* stream);
+
+/* Size prior (repo/datasets/transforms/_atom_num_dist.npy) as flat device arrays: bin b (b = 0..n_bounds) is chosen by
+ * the first bound greater than the space size (init_lig.py:47-52) and holds values[bin_ptr[b]:bin_ptr[b+1]] with the
+ * cumulative distribution cdf[...] = cumsum(p) / sum(p) that numpy's legacy choice(values, p=p) searches
+ * (side='right') with its uniform draw (sample_atom_num, init_lig.py:27-31). */
+typedef struct cbg_size_prior {
+  const double* bounds;
+  int32_t n_bounds;
+  const int32_t* bin_ptr;   /* [n_bounds + 2] */
+  const int32_t* values;
+  const double* cdf;
+} cbg_size_prior;
+
+/* Ligand atom counts of the n_pockets * repeat samples and their exclusive prefix sum.  With ctx_ptr (context tasks,
+ * AssignGenSize init_lig.py:253-296) a draw that does not exceed the pocket's context atom count is replaced by
+ * context + extra[s] (the reference's torch.randint(1, 8)). */
+int32_t cbg_sample_ligand_sizes(const cbg_size_prior* prior, const float* space_size /*[n_pockets]*/, int32_t n_pockets,
+                                int32_t repeat, const double* u /*[S]*/, const int32_t* ctx_ptr /*or NULL*/,
+                                const int32_t* extra /*[S] or NULL*/, int32_t* n_lig /*[S] out*/,
+                                int32_t* lig_ptr /*[S+1] out*/, void* stream);
+
+#define CBG_TYPE_UNIFORM 0    /* assign_atomtype / assign_genatomtype 'uniform': Gumbel arg-max over zero logits (init_lig.py:22-26) */
+#define CBG_TYPE_ABSORBING 1  /* 'absorbing' (state 0); also used for 'zeros' (the caller allocates the [n,K] zero features) */
+#define CBG_POS_GAUSSIAN 0            /* assign_molpos / assign_genpos 'gaussian' (init_lig.py:404-457) */
+#define CBG_POS_ZERO_MEAN_GAUSSIAN 1  /* 'zero_mean_gaussian': the sample's mean is removed (de-novo only) */
+
+typedef struct cbg_batch_spec {
+  /* raw pockets (protein_featurizer.py:19-30 runs on the device) */
+  const float* prot_pos;          /* [n_atoms,3] */
+  const int32_t* prot_element;    /* [n_atoms] atomic numbers */
+  const uint8_t* prot_backbone;   /* [n_atoms] is_backbone */
+  const int32_t* prot_aa;         /* [n_atoms] atom_to_aa_type */
+  const int32_t* prot_ptr;        /* [n_pockets+1] */
+  int32_t n_pockets;
+  int32_t repeat;
+  const float* centre;            /* [n_pockets,3] from cbg_pocket_stats_f32 */
+  /* context ligand atoms per pocket (NULL / NULL / NULL for de-novo): they come first in every sample, are centred like
+   * the pocket, keep their types and get ctx_flag = 1, gen_flag = 0 */
+  const float* ctx_pos;
+  const int32_t* ctx_type;
+  const int32_t* ctx_ptr;
+  const int32_t* lig_ptr;         /* [S+1] from cbg_sample_ligand_sizes */
+  const float* pos_noise;         /* [n_lig_total,3] standard normal (rows of context atoms are ignored) */
+  const float* type_u;            /* [n_lig_total,K] uniform(0,1) or NULL unless type_dist == CBG_TYPE_UNIFORM */
+  int32_t num_classes;
+  int32_t type_dist;
+  int32_t pos_dist;
+  /* outputs = the flat batch of SURVEY.md section 8b (graph id = sample index) */
+  float* protein_pos;             /* [S_atoms,3] centred */
+  float* protein_atom_feature;    /* [S_atoms,7] */
+  int64_t* protein_aa_type;       /* [S_atoms] */
+  int64_t* protein_element_batch; /* [S_atoms] */
+  float* protein_translation;     /* [S_atoms,3] the centre, per atom (translation.py:19) */
+  float* ligand_pos;              /* [n_lig_total,3] */
+  int64_t* ligand_atom_type;      /* [n_lig_total] */
+  int64_t* ligand_element_batch;  /* [n_lig_total] */
+  uint8_t* ligand_ctx_flag;       /* [n_lig_total] or NULL */
+  uint8_t* ligand_gen_flag;       /* [n_lig_total] or NULL */
+} cbg_batch_spec;
+
+int32_t cbg_build_batch_f32(const cbg_batch_spec* spec, void* stream);
 
 #ifdef __cplusplus
 }

@@ -495,7 +495,7 @@ def edge_impl_reset():
     yield
     _lib.check(_lib.lib().cbg_set_edge_impl(1, 8))
     _lib.check(_lib.lib().cbg_set_edge_impl(0, 12))
-    _lib.check(_lib.lib().cbg_set_edge_impl(1, 0))
+    _lib.check(_lib.lib().cbg_set_edge_impl(2, 0))     # library default
 
 
 @pytest.mark.parametrize('case', FORWARD_CASES, ids=[c[0] for c in FORWARD_CASES])
