@@ -289,10 +289,19 @@ def run_b200(args):
         #   x2h_k: Pj_k + Pi_k + q rows (3 x 512 B) + nbr (128) + e_w (128) + x (16) read, w (2048) written
         #   x2h_v: Pj_v + Pi_v (2 x 512) + nbr + e_w + x (272) + w (2048) + h (512) read, h (512) written
         #   + the node's R-cache block (32 slots x 512 B) streamed for static (non-generated) nodes
-        n_static = N - state['plan'].n_gen
-        rc_bytes = 32 * 512 * n_static if model.use_rcache else 0
+        # rows one launch processes: with receptive-field pruning layer l only updates the nodes that can still reach a
+        # sampled atom, so the per-launch average over the layers is what the measured launch time corresponds to
+        n_layers = state['plan'].num_layers
+        rows = float(N)
+        if model.use_prune:
+            import ctypes
+            cnt = (ctypes.c_int32 * (n_layers + 1))()
+            _lib.check(L.cbg_sample_prune_counts_host(ctypes.byref(state['plan']), cnt, _lib.stream_ptr(dev)))
+            rows = sum(cnt[l + 1] for l in range(n_layers)) / n_layers
+        rows_static = max(rows - state['plan'].n_gen, 0.0)       # generated atoms are in every layer's list
+        rc_bytes = 32 * 512 * rows_static if model.use_rcache else 0
         per_node = {'x2h_k': 3 * 512 + 272 + 2048, 'x2h_v': 2 * 512 + 272 + 2048 + 1024}[dom]
-        alg_bytes = per_node * N + rc_bytes
+        alg_bytes = per_node * rows + rc_bytes
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         # useful fp32 work of the same launch (query-folded / aggregated second Linears; the RBF mat-vec only
         # for the edges that are not served from the R-cache is NOT counted: lower bound of useful FLOPs)
@@ -309,8 +318,9 @@ def run_b200(args):
                     'traffic': traffic, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': dom_ms,
                     'note': 'per-edge k/v tensors are never materialised; the kernel streams node planes + the R-cache '
                             'and is co-limited by fp32 issue rate (see fp32)',
-                    'fp32': {'achieved_tflops': flops_node * N / (dom_ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
-                             'frac': flops_node * N / (dom_ms * 1e-3) / 1e12 / fp32_peak,
+                    'rows_per_launch': rows,
+                    'fp32': {'achieved_tflops': flops_node * rows / (dom_ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
+                             'frac': flops_node * rows / (dom_ms * 1e-3) / 1e12 / fp32_peak,
                              'peak_source': 'nominal 148 SM x 128 FMA x 2 x max SM clock'}}
 
     # ---- end to end through the public API: host batch -> model.sample() -> host trajectory -------

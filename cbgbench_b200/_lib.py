@@ -69,6 +69,7 @@ SIGNATURES = {
                                              _I32, _I32, _F, _P, _P, _P]),
     'cbg_node_proj_f32': (_I32, [_P, _I32, _I32, _P, _P, _I32, _I64, _P, _P]),
     'cbg_sample_begin_f32': (_I32, [C.POINTER(SamplePlan), _P, _P, _P, _P]),
+    'cbg_sample_prune_counts_host': (_I32, [C.POINTER(SamplePlan), _P, _P]),
     'cbg_sample_step_f32': (_I32, [C.POINTER(SamplePlan), C.POINTER(StepCoef), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cbg_sbdd_step_f32': (_I32, [C.POINTER(SamplePlan), C.POINTER(SbddCoef), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'cbg_bp_step_f32': (_I32, [C.POINTER(SamplePlan), _P, _I32, C.POINTER(BpCoef), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -146,7 +146,7 @@ class DeviceBatchBuilder:
         (CPU or device tensors); context (recipe 'context'): list of {'pos' [C,3], 'atom_type' [C]} per pocket.
         Every pocket is sampled ``repeat`` times (sample.py:177: config.sampling.num_samples); graph id = sample index.
         draws (optional, parity tests): {'u_size' [S] f64, 'extra' [S] i32, 'type_u' [n,K] f32, 'pos_noise' [n,3] f32}.
-        Returns the flat batch dict on the device (+ 'space_size', 'n_lig', 'graph_pocket')."""
+        Returns the flat batch dict on the device (+ 'space_size', 'n_lig', 'graph_pocket', 'graph_translation')."""
         L = _lib.lib()
         dev = torch.device(device if device is not None else 'cuda')
         if dev.type != 'cuda':
@@ -235,4 +235,5 @@ class DeviceBatchBuilder:
             out['ligand_atom_type'] = torch.zeros(n_total, K, dtype=torch.int64, device=dev)
         out['space_size'], out['n_lig'] = space, n_lig
         out['graph_pocket'] = torch.arange(S, device=dev) // repeat
+        out['graph_translation'] = centre[out['graph_pocket']]
         return out

@@ -508,6 +508,16 @@ int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, 
   return 0;
 }
 
+int32_t cbg_sample_prune_counts_host(const cbg_sample_plan* plan, int32_t* counts_host, void* stream) {
+  if (!plan || !counts_host) { cbg_set_error("cbg_sample_prune_counts_host: null argument"); return 1; }
+  Workspace ws;
+  if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  CBG_CUDA_OK(cudaMemcpyAsync(counts_host, ws.cnt, sizeof(int32_t) * (size_t)(plan->num_layers + 1), cudaMemcpyDeviceToHost, st));
+  CBG_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* coef, const float* x_t,
                             const float* c_t, const float* pos_noise, const float* type_uniform, float* x_next,
                             float* c_next, int64_t* v_next, float* x0_pred, float* logits, void* stream) {

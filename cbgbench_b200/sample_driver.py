@@ -12,6 +12,9 @@ count, each rank samples its share with no communication and ONE all-gather retu
 coordinates / types (``cbgbench_b200.sharding``).
 
     python -m cbgbench_b200.sample_driver --pockets 16 --batch-size 16 --out out.pt
+    python -m cbgbench_b200.sample_driver --builder device --size-prior <reference>/repo/datasets/transforms/_atom_num_dist.npy \
+        --pockets 2 --num-samples 100 --batch-size 50      (row f3: batches built on the GPU from raw pockets,
+                                                            sample.py:177-183: num_samples per pocket, batch_size per step)
     python -m cbgbench_b200.sample_driver --model diffsbdd --pockets 16      (row f2: also diffbp)
     torchrun --nproc-per-node 8 -m cbgbench_b200.sample_driver --pockets 512 --batch-size 512
 """
@@ -48,6 +51,36 @@ def final_state(model, sub_batch, traj_key=0):
     return x.to(dev), c.argmax(-1).to(dev)
 
 
+def device_built_batches(args, dev):
+    """Row f3: the transform list of configs/denovo/test/<model>.yml evaluated on the GPU (DeviceBatchBuilder) for
+    synthetic RAW pockets: every pocket is sampled --num-samples times in mini-batches of --batch-size samples, like
+    sample.py:177-183 (``data_list_repeat`` + DataLoader).  Generator: torch's CUDA generator (seeded by --seed)."""
+    import numpy as np
+    from .batch_builder import DeviceBatchBuilder, SizePrior
+    if not args.size_prior:
+        raise SystemExit('--builder device needs --size-prior (the reference\'s _atom_num_dist.npy)')
+    prior = SizePrior.from_npy(args.size_prior)
+    recipe = {'targetdiff': dict(type_dist='uniform', pos_dist='gaussian', num_classes=13),
+              'diffbp': dict(type_dist='absorbing', pos_dist='gaussian', num_classes=13),
+              'diffsbdd': dict(type_dist='zeros', pos_dist='zero_mean_gaussian', num_classes=13)}[args.model]
+    builder = DeviceBatchBuilder(prior, recipe='denovo', **recipe)
+    rs = np.random.RandomState(args.seed)
+    batches = []
+    for _ in range(args.pockets):
+        n = args.n_prot
+        pocket = {'pos': torch.from_numpy((rs.normal(0, 5.0, size=(n, 3)) + rs.normal(0, 20, size=3)).astype(np.float32)),
+                  'element': torch.from_numpy(rs.choice([1, 6, 7, 8, 16], size=n, p=[0.05, 0.55, 0.18, 0.2, 0.02])),
+                  'is_backbone': torch.from_numpy(rs.randint(0, 2, size=n).astype(bool)),
+                  'atom_to_aa_type': torch.from_numpy(rs.randint(0, 20, size=n))}
+        for s0 in range(0, args.num_samples, args.batch_size):
+            b = builder.build([pocket], min(args.batch_size, args.num_samples - s0), device=dev)
+            if args.model == 'diffsbdd':          # our DiffSBDD host class takes integer types like the other two
+                b['ligand_atom_type'] = torch.zeros(b['ligand_pos'].shape[0], dtype=torch.int64, device=dev)
+            b['protein_translation'] = b['graph_translation']      # per graph, the driver's convention (sample.py:199 uses row 0)
+            batches.append(b)
+    return batches
+
+
 def run(args):
     distributed = int(os.environ.get('WORLD_SIZE', '1')) > 1
     rank = int(os.environ.get('RANK', '0'))
@@ -66,7 +99,9 @@ def run(args):
     model = model.to(dev).eval()
     torch.manual_seed(args.seed + rank)                                                    # sample.py:106,131-133
 
-    if args.batches:
+    if args.builder == 'device':
+        batches = device_built_batches(args, dev)
+    elif args.batches:
         batches = torch.load(args.batches)
     else:
         batches = []
@@ -115,6 +150,10 @@ def main(argv=None):
     ap.add_argument('--ckpt', default=None, help='reference checkpoint ({"model": state_dict, ...})')
     ap.add_argument('--batches', default=None, help='torch.save()d list of batch dicts with the reference keys')
     ap.add_argument('--out', default=None)
+    ap.add_argument('--builder', default='host', choices=['host', 'device'],
+                    help="'device': build the batches on the GPU from raw pockets (row f3)")
+    ap.add_argument('--size-prior', default=None, help='path of the reference size-prior table (_atom_num_dist.npy)')
+    ap.add_argument('--num-samples', type=int, default=8, help='samples per pocket with --builder device (sampling.num_samples)')
     return run(ap.parse_args(argv))
 
 

@@ -182,6 +182,11 @@ typedef struct cbg_step_coef {  /* scheduler table entries of the current step (
 int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes /*[N,3]*/,
                              const uint8_t* lig_flag /*[N]*/, const uint8_t* gen_flag /*[N]*/, void* stream);
 
+/* Measurement hook (bench.py roofline): node counts of the receptive-field pruning of the LAST step run on this plan,
+ * counts_host[l + 1] = nodes whose X2H output of layer l is still needed (= rows the X2H kernels of layer l process),
+ * counts_host[0] = nodes needed at all; num_layers + 1 entries.  Copies to host memory and synchronises the stream. */
+int32_t cbg_sample_prune_counts_host(const cbg_sample_plan* plan, int32_t* counts_host /*[num_layers+1]*/, void* stream);
+
 int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* coef,
                             const float* x_t /*[n_lig,3]*/, const float* c_t /*[n_lig,K]*/,
                             const float* pos_noise /*[n_lig,3]*/, const float* type_uniform /*[n_lig,K]*/,
