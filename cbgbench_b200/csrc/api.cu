@@ -174,17 +174,25 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
              float r_max, const float* rcache, const int* cls_idx, int n_cls, bool prune, cudaStream_t st) {
   if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
   if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, rcache ? ws.snbr : nullptr, ws.nbr, st)) return rc;
-  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, rcache ? ws.sew : nullptr,
-                                    gate_compact() ? (int*)ws.w : nullptr, ws.ew, st)) return rc;
   const float* layers = blob + cbg_layout::kGlobalFloats;
   // Receptive-field pruning (only when the caller consumes nothing but the generated / classified rows):
   // layer l updates h only for the nodes that can still reach such a row through the remaining layers.
   prune = prune && num_layers > 0 && (n_gen > 0 || n_cls > 0);
+  const bool overlap = (n_gen > 0) && aux_ready();
+  // the edge gate and the pruning BFS both need only the neighbour table: run them side by side
+  const bool fork_depth = prune && overlap;
+  if (fork_depth) {
+    CBG_CUDA_OK(cudaEventRecord(g_aux.ev_h0, st));
+    CBG_CUDA_OK(cudaStreamWaitEvent(g_aux.s3, g_aux.ev_h0, 0));
+  }
   if (prune) {
     if (int rc = cbg_launch_depth(ws.nbr, graph_ptr, n_graphs, max_graph_nodes, n_nodes, gen_idx, n_gen, cls_idx, n_cls,
-                                  num_layers, ws.depth, ws.order, ws.cnt, st)) return rc;
+                                  num_layers, ws.depth, ws.order, ws.cnt, fork_depth ? g_aux.s3 : st)) return rc;
   }
-  const bool overlap = (n_gen > 0) && aux_ready();
+  if (fork_depth) CBG_CUDA_OK(cudaEventRecord(g_aux.ev_p, g_aux.s3));
+  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, rcache ? ws.sew : nullptr,
+                                    gate_compact() ? (int*)ws.w : nullptr, ws.ew, st)) return rc;
+  if (fork_depth) CBG_CUDA_OK(cudaStreamWaitEvent(st, g_aux.ev_p, 0));
   cudaStream_t sx = overlap ? g_aux.s2 : st;       // stream of the H2X chain
   bool x_pending = false;                          // an apply_dx on sx has not been joined yet
   for (int l = 0; l < num_layers; ++l) {
