@@ -49,6 +49,7 @@ SIGNATURES = {
     'cbg_last_error': (C.c_char_p, []),
     'cbg_launch_count': (_I64, []),
     'cbg_set_edge_impl': (_I32, [_I32, _I32]),
+    'cbg_set_option': (_I32, [C.c_char_p, _I32]),
     'cbg_profile_num_families': (_I32, []),
     'cbg_profile_family_name': (C.c_char_p, [_I32]),
     'cbg_profile_enable': (_I32, [_I32]),

@@ -65,6 +65,8 @@ struct Workspace {
   int* cnt;
   float* ew;
   float* dx;
+  int* tickets;                // 64 work counters of the X2H launches of one step (dynamic node scheduling)
+  unsigned char* fstat;        // per node: all 32 in-edges static this step (written by the edge gate when an R-cache is used)
   size_t bytes;
 };
 
@@ -86,6 +88,8 @@ Workspace carve(void* base, long long n_nodes, long long n_gen) {
   ws.cnt = (int*)take(96 * 4);
   ws.ew = (float*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.dx = (float*)take((size_t)(n_gen > 0 ? n_gen : 1) * 16);
+  ws.fstat = (unsigned char*)take((size_t)n_nodes);
+  ws.tickets = (int*)take(64 * sizeof(int));
   ws.bytes = off;
   return ws;
 }
@@ -168,6 +172,19 @@ bool gate_compact() {
   return on != 0;
 }
 
+// fast path of edge_setup for nodes whose 32 in-edges are all static (needs the R-cache): CBG_STATIC_FAST=0 turns it off
+// dynamic node scheduling of the X2H kernels (work counters); CBG_DYN_SCHED=0 keeps the static round-robin
+int g_dyn_sched = -1;
+bool dyn_sched() {
+  if (g_dyn_sched < 0) { const char* e = getenv("CBG_DYN_SCHED"); g_dyn_sched = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  return g_dyn_sched != 0;
+}
+int g_static_fast = -1;
+bool static_fast_path() {
+  if (g_static_fast < 0) { const char* e = getenv("CBG_STATIC_FAST"); g_static_fast = (e && strcmp(e, "0") == 0) ? 0 : 1; }
+  return g_static_fast != 0;
+}
+
 // graph build + gate + layers on an initialised workspace (x4, h valid)
 int run_core(const float* blob, int num_layers, const Workspace& ws, const int* graph_ptr, int n_graphs,
              int max_graph_nodes, long long n_nodes, const int* gen_idx, int n_gen, int mode, int k,
@@ -179,6 +196,8 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
   // layer l updates h only for the nodes that can still reach such a row through the remaining layers.
   prune = prune && num_layers > 0 && (n_gen > 0 || n_cls > 0);
   const bool overlap = (n_gen > 0) && aux_ready();
+  const bool tickets = dyn_sched() && 2 * num_layers <= 64;
+  if (tickets) CBG_CUDA_OK(cudaMemsetAsync(ws.tickets, 0, 64 * sizeof(int), st));
   // the edge gate and the pruning BFS both need only the neighbour table: run them side by side
   const bool fork_depth = prune && overlap;
   if (fork_depth) {
@@ -191,7 +210,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
   }
   if (fork_depth) CBG_CUDA_OK(cudaEventRecord(g_aux.ev_p, g_aux.s3));
   if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, rcache ? ws.sew : nullptr,
-                                    gate_compact() ? (int*)ws.w : nullptr, ws.ew, st)) return rc;
+                                    gate_compact() ? (int*)ws.w : nullptr, ws.ew, st, ws.fstat)) return rc;
   if (fork_depth) CBG_CUDA_OK(cudaStreamWaitEvent(st, g_aux.ev_p, 0));
   cudaStream_t sx = overlap ? g_aux.s2 : st;       // stream of the H2X chain
   bool x_pending = false;                          // an apply_dx on sx has not been joined yet
@@ -237,10 +256,12 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     e.pj_k = ws.plane[0]; e.pj_v = ws.plane[1]; e.pi_k = ws.plane[2]; e.pi_v = ws.plane[3]; e.q = ws.plane[4];
     e.layer = L; e.w = ws.w; e.h = ws.h; e.node_idx = nullptr; e.n_nodes = (int)n_nodes; e.dx = nullptr;
     if (prune) { e.node_idx = ws.order; e.n_nodes_dev = ws.cnt + l + 1; }
+    if (tickets) e.ticket = ws.tickets + 2 * l;
     if (rcache) {
       const size_t per = (size_t)n_nodes * (CBG_KMAX * CBG_H);
       e.rc_k = rcache + (size_t)(2 * l) * per;
       e.rc_v = rcache + (size_t)(2 * l + 1) * per;
+      e.fstat = static_fast_path() ? ws.fstat : nullptr;
     }
     if (int rc = cbg_launch_x2h(e, st)) return rc;
     if (n_gen <= 0) continue;   // nothing moves: H2X output is multiplied by gen_flag == 0
@@ -276,7 +297,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     }
     EdgeArgs x = e;
     x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
-    x.node_idx = gen_idx; x.n_nodes = n_gen; x.n_nodes_dev = nullptr; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr;
+    x.node_idx = gen_idx; x.n_nodes = n_gen; x.n_nodes_dev = nullptr; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr; x.fstat = nullptr; x.ticket = nullptr;
     if (int rc = cbg_launch_h2x(x, sx)) return rc;
     if (int rc = cbg_launch_apply_dx(ws.x4, gen_idx, ws.dx, n_gen, sx)) return rc;
     if (overlap) { CBG_CUDA_OK(cudaEventRecord(g_aux.ev_x, sx)); x_pending = true; }
@@ -312,6 +333,12 @@ const char* cbg_last_error(void) { return g_err; }
 int64_t cbg_launch_count(void) { return g_cbg_launches; }
 
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps) { return cbg_edge_set_impl(impl, warps); }
+int32_t cbg_set_option(const char* key, int32_t value) {
+  if (key && strcmp(key, "static_fast") == 0) { g_static_fast = value ? 1 : 0; return 0; }
+  if (key && strcmp(key, "dyn_sched") == 0) { g_dyn_sched = value ? 1 : 0; return 0; }
+  cbg_set_error("cbg_set_option: unknown key '%s'", key ? key : "(null)");
+  return 1;
+}
 
 int32_t cbg_profile_num_families(void) { return CBG_K_COUNT; }
 const char* cbg_profile_family_name(int32_t i) { return (i >= 0 && i < CBG_K_COUNT) ? kFamilyNames[i] : nullptr; }

@@ -14,8 +14,10 @@ int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max
 // ew_static (optional): gates of the static-only neighbour lists, reused for static edges
 // glist (optional, with ew_static): scratch of 64 + 32*n_nodes ints; the moving edges are compacted into it
 // and their gates computed by a second, dense launch
+// full_static (optional, with ew_static): per node, 1 when all 32 slots hold static edges (fast path of edge_setup)
 int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
-                         const float* ew_static, int* glist, float* ew, cudaStream_t st);
+                         const float* ew_static, int* glist, float* ew, cudaStream_t st,
+                         unsigned char* full_static = nullptr);
 
 // Receptive-field pruning (sampling path): depth[i] = last layer whose X2H output of node i can still
 // influence a generated / classified atom (-2: never).  order[] lists nodes by decreasing depth,
@@ -67,6 +69,8 @@ struct EdgeArgs {
   const int* n_nodes_dev; // optional device-side length of node_idx (x2h with a pruned node list)
   const float* rc_k;     // x2h: R-cache of this layer's hk / hv MLP ([N][32][128]) or nullptr
   const float* rc_v;
+  int* ticket;           // x2h: optional work counter (zeroed by the caller) for dynamic node scheduling; k uses ticket[0], v ticket[1]
+  const unsigned char* fstat;  // x2h with an R-cache: 1 = all 32 in-edges of the node are static (nbr row == its static list)
 };
 int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, const int* snbr, int n_nodes,
                       float* rcache, cudaStream_t st);

@@ -60,9 +60,19 @@ struct MlpSmem {                  // first-layer weights of one edge MLP in shar
 // diffusion steps (their endpoints never move), which is what the R-cache below exploits; the p-th
 // static edge of the list is the p-th entry of the node's static-only kNN list (prefix property).
 // Returns the validity mask in permuted positions.
+// fstat (optional): per-node flag "all 32 slots hold static edges" (written by the edge gate once per step when the
+// R-cache is on).  For such a node the permutation is the identity and every edge is served from the R-cache, so only
+// j, e_w and the slot index are ever read: the coordinate gathers, the RBF and the type computation are skipped.
 __device__ __forceinline__ unsigned edge_setup(EdgeMeta& M, int i, int lane, const float4* __restrict__ x4,
                                                const int* __restrict__ nbr, const float* __restrict__ ew,
-                                               const float* s_rbf) {
+                                               const float* s_rbf, const unsigned char* __restrict__ fstat = nullptr) {
+  if (fstat != nullptr && fstat[i]) {                     // warp-uniform
+    M.j[lane] = nbr[(size_t)i * CBG_KMAX + lane];
+    M.ew[lane] = ew[(size_t)i * CBG_KMAX + lane];
+    M.slot[lane] = lane;
+    __syncwarp();
+    return 0xffffffffu;
+  }
   const float4 xi = x4[i];
   const int jn = nbr[(size_t)i * CBG_KMAX + lane];
   const bool valid = jn >= 0;
@@ -109,6 +119,30 @@ __device__ __forceinline__ int list_length(const EdgeArgs& p) {
   if (p.n_nodes_dev) { const int nd = *p.n_nodes_dev; n = nd < n ? nd : n; }
   return n;
 }
+
+// Node scheduling of the X2H kernels.  With a ticket counter (EdgeArgs::ticket, zeroed before the launch) every warp
+// draws its next node from a global counter: nodes differ in cost (generated atoms and their neighbourhood run the RBF
+// path, static nodes only stream the R-cache), so a static round-robin leaves SMs idle at the end of a launch.  The
+// draw for the following node is issued before the current one is processed, which hides the atomic's latency.
+struct NodeSched {
+  int* ticket;
+  int stride, pending, nn;
+  __device__ __forceinline__ int first(const EdgeArgs& p, int warp_global, int total_warps, int lane) {
+    ticket = p.ticket; stride = total_warps; pending = 0; nn = 0;
+    if (ticket == nullptr) return warp_global;
+    int v = 0;
+    if (lane == 0) v = atomicAdd(ticket, 1);
+    return __shfl_sync(CBG_FULL, v, 0);
+  }
+  __device__ __forceinline__ void draw(int n, int lane) {            // request the node that follows n
+    if (ticket != nullptr) { if (lane == 0) pending = atomicAdd(ticket, 1); }
+    else pending = n + stride;
+  }
+  __device__ __forceinline__ int next(int lane) {                    // first use waits for the atomic
+    nn = ticket != nullptr ? __shfl_sync(CBG_FULL, pending, 0) : pending;
+    return nn;
+  }
+};
 
 // All-lane sums of 4 per-lane values, result in every lane: transposed butterfly (each step halves
 // the number of live values), three plain steps, four broadcasts: 10 SHFL instead of 20.
@@ -343,12 +377,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_kernel(EdgeArgs p) {
   const float4 gamma = ld4(s_ln + 4 * lane), beta = ld4(s_ln + 128 + 4 * lane);
 
   const int n_list = list_length(p);
-  for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
+  NodeSched sch;
+  for (int n = sch.first(p, blockIdx.x * kWarps + warp, gridDim.x * kWarps, lane); n < n_list; n = sch.nn) {
+    sch.draw(n, lane);
     const int i = p.node_idx ? p.node_idx[n] : n;
-    const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf, p.fstat);
     const float* rc = p.rc_k ? p.rc_k + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
     {
-      const int nn = n + gridDim.x * kWarps;
+      const int nn = sch.next(lane);
       if (nn < n_list) prefetch_rc(p.rc_k, p.node_idx ? p.node_idx[nn] : nn, lane);
     }
     float U[4][CBG_HEADS];
@@ -403,12 +439,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_kernel(EdgeArgs p) {
   const float4 gamma = ld4(s_ln + 4 * lane), beta = ld4(s_ln + 128 + 4 * lane);
 
   const int n_list = list_length(p);
-  for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
+  NodeSched sch;
+  for (int n = sch.first(p, blockIdx.x * kWarps + warp, gridDim.x * kWarps, lane); n < n_list; n = sch.nn) {
+    sch.draw(n, lane);
     const int i = p.node_idx ? p.node_idx[n] : n;
-    edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf, p.fstat);
     const float* rc = p.rc_v ? p.rc_v + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
     {
-      const int nn = n + gridDim.x * kWarps;
+      const int nn = sch.next(lane);
       if (nn < n_list) prefetch_rc(p.rc_v, p.node_idx ? p.node_idx[nn] : nn, lane);
     }
     {
@@ -527,7 +565,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) h2x_kernel(EdgeArgs p) {
 
   for (int n = blockIdx.x * kWarps + warp; n < p.n_nodes; n += gridDim.x * kWarps) {
     const int i = p.node_idx[n];
-    const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf, p.fstat);
     float U[4][CBG_HEADS];
     build_u(p.q + (size_t)i * CBG_H, k_w1, lane, U);
     const float4 pik = ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane);
@@ -744,13 +782,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma_kernel(EdgeArgs p) {
   float* pist = qst + 128;
 
   const int n_list = list_length(p);
-  for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
+  NodeSched sch;
+  for (int n = sch.first(p, blockIdx.x * kWarps + warp, gridDim.x * kWarps, lane); n < n_list; n = sch.nn) {
+    sch.draw(n, lane);
     const int i = p.node_idx ? p.node_idx[n] : n;
-    const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf, p.fstat);
     const float* rc = p.rc_k ? p.rc_k + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
     const int nst = rc ? __popc(__ballot_sync(CBG_FULL, M.slot[lane] >= 0)) : 0;
     {
-      const int nn = n + gridDim.x * kWarps;
+      const int nn = sch.next(lane);
       if (nn < n_list) prefetch_rc(p.rc_k, p.node_idx ? p.node_idx[nn] : nn, lane);
     }
     // query-folded key matrix directly as A fragments: Uf[m][u] = {U[f][g], U[f][g+8], U[f+1][g], U[f+1][g+8]},
@@ -929,13 +969,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_mma_kernel(EdgeArgs p) {
   float* pist = reinterpret_cast<float*>(metas + kWarps) + warp * 128;   // per-warp staging of Pi_i
 
   const int n_list = list_length(p);
-  for (int n = blockIdx.x * kWarps + warp; n < n_list; n += gridDim.x * kWarps) {
+  NodeSched sch;
+  for (int n = sch.first(p, blockIdx.x * kWarps + warp, gridDim.x * kWarps, lane); n < n_list; n = sch.nn) {
+    sch.draw(n, lane);
     const int i = p.node_idx ? p.node_idx[n] : n;
-    edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+    edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf, p.fstat);
     const float* rc = p.rc_v ? p.rc_v + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
     const int nst = rc ? __popc(__ballot_sync(CBG_FULL, M.slot[lane] >= 0)) : 0;
     {
-      const int nn = n + gridDim.x * kWarps;
+      const int nn = sch.next(lane);
       if (nn < n_list) prefetch_rc(p.rc_v, p.node_idx ? p.node_idx[nn] : nn, lane);
     }
     // attention weights (alpha * e_w) as A fragments: row = head (g, g+8), column = edge (8kt+t, 8kt+t+4)
@@ -1157,11 +1199,13 @@ int edge_grid(int n_nodes, int warps) {
 template <int W>
 int launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   const int grid = edge_grid(a.n_nodes, W);
+  EdgeArgs av = a;
+  if (av.ticket) av.ticket += 1;          // the second kernel has its own work counter
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
   x2h_k_kernel<W><<<grid, W * 32, x2hk_smem(W), st>>>(a);
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
-  x2h_v_kernel<W><<<grid, W * 32, x2hv_smem(W), st>>>(a);
+  x2h_v_kernel<W><<<grid, W * 32, x2hv_smem(W), st>>>(av);
   CBG_LAUNCHED(CBG_K_X2H_V, st);
   return 0;
 }
@@ -1170,13 +1214,15 @@ int launch_x2h(const EdgeArgs& a, cudaStream_t st) {
 // (the two halves agree on the layout of w, so they can be mixed: used by the tests to localise a mismatch)
 template <int W, int WS>
 int launch_x2h_mma(const EdgeArgs& a, cudaStream_t st, int impl) {
+  EdgeArgs av = a;
+  if (av.ticket) av.ticket += 1;          // the second kernel has its own work counter
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
   if (impl == 3) x2h_k_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hk_smem(WS), st>>>(a);
   else x2h_k_mma_kernel<W, (W > 8 ? 1 : 2)><<<edge_grid(a.n_nodes, W), W * 32, x2hk_mma_smem(W), st>>>(a);
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
-  if (impl == 2) x2h_v_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hv_smem(WS), st>>>(a);
-  else x2h_v_mma_kernel<W><<<edge_grid(a.n_nodes, W), W * 32, x2hv_mma_smem(W), st>>>(a);
+  if (impl == 2) x2h_v_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hv_smem(WS), st>>>(av);
+  else x2h_v_mma_kernel<W><<<edge_grid(a.n_nodes, W), W * 32, x2hv_mma_smem(W), st>>>(av);
   CBG_LAUNCHED(CBG_K_X2H_V, st);
   return 0;
 }

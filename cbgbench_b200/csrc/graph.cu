@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
                                                         const int* __restrict__ nbr, long long n_slots,
                                                         const float* __restrict__ ew_static,
                                                         int* __restrict__ glist,
-                                                        float* __restrict__ ew) {
+                                                        float* __restrict__ ew,
+                                                        unsigned char* __restrict__ full_static) {
   __shared__ __align__(16) float sm[kGateSmemFloats];
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one warp = one node's 32 slots
   const bool in_range = idx < n_slots;   // n_slots is a multiple of 32: whole warps are in or out
@@ -132,6 +133,7 @@ __global__ void __launch_bounds__(128) edge_gate_kernel(const float* __restrict_
       // current list is the p-th entry of that list (prefix property, see edge.cu: edge_setup)
       const bool is_static = j >= 0 && ((node_flags(xi) | node_flags(xj)) & 2) == 0;
       const unsigned sm_mask = __ballot_sync(CBG_FULL, is_static);
+      if (full_static != nullptr && (threadIdx.x & 31) == 0) full_static[i] = sm_mask == 0xffffffffu;
       if (is_static) {
         ew[idx] = ew_static[(size_t)i * CBG_KMAX + __popc(sm_mask & ((1u << (threadIdx.x & 31)) - 1u))];
         need = false;
@@ -358,7 +360,7 @@ int cbg_launch_edge_gate_rows(const float* blob_global, const float4* x4, const 
 }
 
 int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* nbr, long long n_nodes,
-                         const float* ew_static, int* glist, float* ew, cudaStream_t st) {
+                         const float* ew_static, int* glist, float* ew, cudaStream_t st, unsigned char* full_static) {
   const long long n_slots = n_nodes * CBG_KMAX;
   if (n_slots == 0) return 0;
   const float* gw = blob_global + cbg_layout::global_offset(CBG_GF_GATE_W0T);
@@ -366,7 +368,7 @@ int cbg_launch_edge_gate(const float* blob_global, const float4* x4, const int* 
   const unsigned grid = (unsigned)((n_slots + 127) / 128);
   if (ew_static == nullptr) glist = nullptr;
   if (glist) CBG_CUDA_OK(cudaMemsetAsync(glist, 0, sizeof(int), st));
-  edge_gate_kernel<<<grid, 128, 0, st>>>(gw, x4, nbr, n_slots, ew_static, glist, ew);
+  edge_gate_kernel<<<grid, 128, 0, st>>>(gw, x4, nbr, n_slots, ew_static, glist, ew, ew_static ? full_static : nullptr);
   if (glist) {
     edge_gate_list_kernel<<<grid, 128, 0, st>>>(gw, x4, nbr, glist, ew);
     g_cbg_launches += 1;

@@ -58,6 +58,11 @@ int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family)
  * warps = CTA size in warps (8, 12, 16; 0 keeps the current value).  Process-wide; also env CBG_EDGE_IMPL,
  * CBG_EDGE_MMA_WARPS, CBG_EDGE_WARPS.  Needs a current CUDA device. */
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);
+/* Other process-wide switches (testing): "static_fast" = 1 (default; env CBG_STATIC_FAST) lets the X2H kernels skip the
+ * coordinate gathers / RBF set-up of nodes whose 32 in-edges are all served from the R-cache (bit-identical results);
+ * "dyn_sched" = 1 (default; env CBG_DYN_SCHED): warps of the X2H kernels draw their next node from a work counter instead
+ * of a static round-robin (bit-identical results, better balance). */
+int32_t cbg_set_option(const char* key, int32_t value);
 
 /* ---- packed weight blob layout (single source of truth: csrc/cbg_layout.h) -------------------
  * blob = [global section][layer 0][layer 1]...; section 0 = global, 1 = per-layer.

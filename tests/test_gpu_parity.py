@@ -549,3 +549,31 @@ def test_edge_kernel_implementations_agree_on_the_sampling_path(edge_impl_reset)
                 assert torch.equal(res[0][t][1].cpu().argmax(-1), res[1][t][1].cpu().argmax(-1)), (gen_mode, rcache, t)
                 e = rel_err(res[1][t][0].cpu(), res[0][t][0].cpu())
                 assert e < 1e-5, (gen_mode, rcache, t, e)
+
+
+def test_static_fast_path_and_dynamic_scheduling_are_bit_identical(edge_impl_reset):
+    """Nodes whose 32 in-edges are all static skip the coordinate gathers / RBF set-up of the X2H kernels, and warps draw
+    nodes from a work counter instead of a round-robin; neither may change a single bit of the sampled coordinates and
+    types, for every implementation of the kernels."""
+    T = 4
+    L = _lib.lib()
+    try:
+        for gen_mode, sizes in (('denovo', ([300, 120, 40], [24, 10, 6])), ('partial', ([200, 150], [18, 12]))):
+            model, sd = make_model(T, device=dev())
+            batch = synthetic.make_batch(*sizes, seed=141, gen_mode=gen_mode)
+            n_lig = int(batch['ligand_pos'].shape[0])
+            pn, tu = synthetic.make_noise(T, n_lig, 13, seed=23)
+            for impl in (0, 1, 2):
+                _lib.check(L.cbg_set_edge_impl(impl, 0))
+                res = {}
+                for fast, dyn in ((1, 1), (0, 1), (1, 0), (0, 0)):
+                    _lib.check(L.cbg_set_option(b'static_fast', fast))
+                    _lib.check(L.cbg_set_option(b'dyn_sched', dyn))      # work-counter vs round-robin node scheduling
+                    res[(fast, dyn)] = model.sample(batch, pos_noise=pn, type_uniform=tu)
+                for key in ((0, 1), (1, 0), (0, 0)):
+                    for t in range(-1, T):
+                        assert torch.equal(res[key][t][0].cpu(), res[(1, 1)][t][0].cpu()), (gen_mode, impl, key, t)
+                        assert torch.equal(res[key][t][1].cpu(), res[(1, 1)][t][1].cpu()), (gen_mode, impl, key, t)
+    finally:
+        _lib.check(L.cbg_set_option(b'static_fast', 1))
+        _lib.check(L.cbg_set_option(b'dyn_sched', 1))
