@@ -1180,6 +1180,7 @@ int g_num_sms = 0;
 int g_edge_warps = 12;
 int g_edge_impl = 2;       // 2 (default, fastest measured): tensor-core x2h_k + SIMT x2h_v; 1: both tensor-core; 0: both SIMT; 3: SIMT k + tensor-core v
 int g_edge_mma_warps = 8;
+int g_h2x_warps = 12;
 
 template <int W>
 int set_attrs() {
@@ -1252,6 +1253,10 @@ int cbg_edge_init(void) {
     if (strcmp(e, "simt") == 0) g_edge_impl = 0;
     else if (e[0] >= '0' && e[0] <= '3' && e[1] == 0) g_edge_impl = e[0] - '0';
   }
+  if (const char* e = getenv("CBG_H2X_WARPS")) {
+    const int w = atoi(e);
+    if (w == 8 || w == 12 || w == 16) g_h2x_warps = w;
+  }
   if (const char* e = getenv("CBG_EDGE_MMA_WARPS")) {
     const int w = atoi(e);
     if (w == 8 || w == 12 || w == 16) g_edge_mma_warps = w;
@@ -1300,7 +1305,7 @@ int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
-  switch (g_edge_warps) {
+  switch (g_h2x_warps) {
     case 8: return launch_h2x<8>(a, st);
     case 16: return launch_h2x<16>(a, st);
     default: return launch_h2x<12>(a, st);
