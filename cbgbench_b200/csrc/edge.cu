@@ -1176,9 +1176,258 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_v_mma_kernel(EdgeArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// x2h_k, second tensor-core variant: the RBF mat-vec of the non-cached edges runs on the tensor cores as well.
+//
+// Per pass of 16 edges (positions 16p .. 16p+15; lane (g, t) owns e0 = 16p + g and e1 = e0 + 8) the first Linear is
+//     pre[e][f] = Pi[f] + Pj[j_e][f] + (static e ? R[e][f] : c[type_e][f] + sum_m g_m(d_e) Wrf[type_e][m][f])
+// The last term is the GEMM  G[16 edges x 24] . Wrf[type][24 x 128]  (20 RBFs padded to 3 k-tiles): one m16n8k8 tile per
+// 8 features, with the rows of edges of another type (or static / padded edges) zeroed in G, once per edge type present.
+// Its accumulator fragment {(e0,f), (e0,f+1), (e1,f), (e1,f+1)} IS the register layout of the activations (act[m][h][4],
+// f = 16m + 4t + 2h), so the MMA accumulates straight into them; the same registers are then the B fragments of the
+// head contraction.  Static edges are decided per lane (no more "whole block dynamic because of one edge").
+// Wrf lives in shared memory as B fragments: img[type][kt][n-tile (m,h)][lane][2] (see block_copy_wrf_frag).
+constexpr int kWimgFloats = 4 * 3 * 16 * 32 * 2;                                  // 12288 floats = 48 KB
+constexpr int kX2hK2Floats = kWimgFloats + 4 * 128 + 256 + 128 * 128 + 32;        // WIMG | C | LN | W1 (fragments) | RBF
+constexpr int x2hk_mma2_smem(int w) { return kX2hK2Floats * 4 + w * ((int)sizeof(EdgeMeta) + 256 * 4); }
+
+// B fragments of the RBF GEMM: b_j (j = 0, 1) of lane (g', t') for k-tile kt and n-tile (m, h) is
+// Wrf[type][8kt + t' + 4j][16m + 4(g' >> 1) + 2h + (g' & 1)]  (0 for the padded RBF rows 20..23)
+__device__ __forceinline__ void block_copy_wrf_frag(float* dst, const float* __restrict__ wrf /*[4][20][128]*/) {
+  for (int idx = threadIdx.x; idx < kWimgFloats; idx += blockDim.x) {
+    const int j = idx & 1, ln = (idx >> 1) & 31, nt = (idx >> 6) & 15, kt = (idx >> 10) % 3, ty = idx / (3 << 10);
+    const int gp = ln >> 2, tp = ln & 3, m = nt >> 1, h = nt & 1;
+    const int rbf = 8 * kt + tp + 4 * j, f = 16 * m + 4 * (gp >> 1) + 2 * h + (gp & 1);
+    dst[idx] = rbf < CBG_NRBF ? __ldg(wrf + (ty * CBG_NRBF + rbf) * CBG_H + f) : 0.f;
+  }
+}
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma2_kernel(EdgeArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  const float* s_wimg = smem;
+  const float* s_c = s_wimg + kWimgFloats;
+  const float* s_ln = s_c + 4 * 128;
+  const float* s_w1 = s_ln + 256;                          // fragment layout, see block_copy_w1k_frag
+  const float* s_rbf = s_w1 + 128 * 128;
+  EdgeMeta* metas = reinterpret_cast<EdgeMeta*>(smem + kX2hK2Floats);
+  {
+    const float* src = p.layer + kOffX2hK;                 // blob: WRF | C | LN | W1 | RBF
+    block_copy_wrf_frag(smem, src);
+    block_copy_f4(smem + kWimgFloats, src + 4 * 20 * 128, 4 * 128 + 256);
+    block_copy_w1k_frag(smem + kWimgFloats + 4 * 128 + 256, src + 4 * 20 * 128 + 4 * 128 + 256);
+    block_copy_f4(smem + kWimgFloats + 4 * 128 + 256 + 128 * 128, src + 4 * 20 * 128 + 4 * 128 + 256 + 128 * 128, 32);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  EdgeMeta& M = metas[warp];
+  float* qst = reinterpret_cast<float*>(metas + kWarps) + warp * 256;   // per-warp staging of q_i (fragment order) | Pi_i
+  float* pist = qst + 128;
+
+  const int n_list = list_length(p);
+  NodeSched sch;
+  for (int n = sch.first(p, blockIdx.x * kWarps + warp, gridDim.x * kWarps, lane); n < n_list; n = sch.nn) {
+    sch.draw(n, lane);
+    const int i = p.node_idx ? p.node_idx[n] : n;
+    const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf, p.fstat);
+    const float* rc = p.rc_k ? p.rc_k + (size_t)i * (CBG_KMAX * CBG_H) : nullptr;
+    const int nst = rc ? __popc(__ballot_sync(CBG_FULL, M.slot[lane] >= 0)) : 0;   // static edges occupy positions 0 .. nst-1
+    {
+      const int nn = sch.next(lane);
+      if (nn < n_list) prefetch_rc(p.rc_k, p.node_idx ? p.node_idx[nn] : nn, lane);
+    }
+    // query-folded key matrix as A fragments (same as x2h_k_mma_kernel)
+    float4 Uf[8][2];
+    {
+      {
+        const float4 q4 = ldg4(p.q + (size_t)i * CBG_H + 4 * lane);
+        const int hd = lane >> 1, d0 = 4 * (lane & 1);
+        float* dst = qst + ((hd & 7) * 8 + d0) * 2 + (hd >> 3);
+        dst[0] = q4.x; dst[2] = q4.y; dst[4] = q4.z; dst[6] = q4.w;
+        st4(pist + 4 * lane, ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane));
+      }
+      __syncwarp();
+      unsigned long long qp[8];
+#pragma unroll
+      for (int dd = 0; dd < 4; ++dd) {
+        const float4 v = ld4(qst + g * 16 + 4 * dd);
+        qp[2 * dd] = pack_f32x2(v.x, v.y);
+        qp[2 * dd + 1] = pack_f32x2(v.z, v.w);
+      }
+      unsigned long long Up[8][2][2];
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) Up[m][u][0] = Up[m][u][1] = 0ull;
+      const int sw = g & 1;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const float* row = s_w1 + (g * 8 + d) * 256;
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float4 w4 = ld4(row + 4 * ((8 * m + 2 * t + u) ^ sw));
+            Up[m][u][0] = fma_f32x2(pack_f32x2(w4.x, w4.y), qp[d], Up[m][u][0]);
+            Up[m][u][1] = fma_f32x2(pack_f32x2(w4.z, w4.w), qp[d], Up[m][u][1]);
+          }
+      }
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          unpack_f32x2(Up[m][u][0], Uf[m][u].x, Uf[m][u].y);
+          unpack_f32x2(Up[m][u][1], Uf[m][u].z, Uf[m][u].w);
+        }
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int e0 = 16 * pass + g, e1 = e0 + 8;
+      const bool st0 = e0 < nst, st1 = e1 < nst;
+      // act[m][h] = {(e0,f), (e0,f+1), (e1,f), (e1,f+1)}, f = 16m + 4t + 2h
+      float act[8][2][4];
+      {
+        const float* pj0 = p.pj_k + (size_t)M.j[e0] * CBG_H + 4 * t;
+        const float* pj1 = p.pj_k + (size_t)M.j[e1] * CBG_H + 4 * t;
+        // third term: the R-cache row of a static edge, the type constant of any other edge
+        const float* r0 = st0 ? rc + M.slot[e0] * CBG_H + 4 * t : nullptr;
+        const float* r1 = st1 ? rc + M.slot[e1] * CBG_H + 4 * t : nullptr;
+        const float* c0 = s_c + (st0 ? 0 : M.t[e0]) * CBG_H + 4 * t;     // (M.t is not written by the static fast path)
+        const float* c1 = s_c + (st1 ? 0 : M.t[e1]) * CBG_H + 4 * t;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const float4 pi4 = ld4(pist + 4 * t + 16 * m);
+          const float4 x0 = ldg4(pj0 + 16 * m), x1 = ldg4(pj1 + 16 * m);
+          const float4 y0 = st0 ? ldg4(r0 + 16 * m) : ld4(c0 + 16 * m);
+          const float4 y1 = st1 ? ldg4(r1 + 16 * m) : ld4(c1 + 16 * m);
+          act[m][0][0] = (pi4.x + x0.x) + y0.x; act[m][0][1] = (pi4.y + x0.y) + y0.y;
+          act[m][0][2] = (pi4.x + x1.x) + y1.x; act[m][0][3] = (pi4.y + x1.y) + y1.y;
+          act[m][1][0] = (pi4.z + x0.z) + y0.z; act[m][1][1] = (pi4.w + x0.w) + y0.w;
+          act[m][1][2] = (pi4.z + x1.z) + y1.z; act[m][1][3] = (pi4.w + x1.w) + y1.w;
+        }
+      }
+      if (__any_sync(CBG_FULL, !st0 || !st1)) {          // warp-uniform: some edge of this pass needs the RBF term
+        const int t0 = st0 ? -1 : M.t[e0], t1 = st1 ? -1 : M.t[e1];
+#pragma unroll 1
+        for (int ty = 0; ty < CBG_NTYPE; ++ty) {
+          if (!__any_sync(CBG_FULL, t0 == ty || t1 == ty)) continue;
+          const float m0 = t0 == ty ? 1.f : 0.f, m1 = t1 == ty ? 1.f : 0.f;
+          unsigned gh[3][4], gl[3][4];
+#pragma unroll
+          for (int kt = 0; kt < 3; ++kt) {
+            const int ra = 8 * kt + t, rb = ra + 4;        // rb >= 20 only for kt == 2: padded rows
+            const float gf[4] = {M.g[ra][e0] * m0, M.g[ra][e1] * m1,
+                                 kt < 2 ? M.g[kt < 2 ? rb : 0][e0] * m0 : 0.f, kt < 2 ? M.g[kt < 2 ? rb : 0][e1] * m1 : 0.f};
+            split_frag(gf, gh[kt], gl[kt]);
+          }
+          const float* img = s_wimg + ty * (3 * 16 * 64) + 2 * lane;
+#pragma unroll
+          for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int kt = 0; kt < 3; ++kt) {
+                const float2 wv = *reinterpret_cast<const float2*>(img + (kt * 16 + 2 * m + h) * 64);
+                const float bf[2] = {wv.x, wv.y};
+                unsigned bh[2], bl[2];
+                split_frag(bf, bh, bl);
+                mma3(act[m][h], gh[kt], gl[kt], bh, bl);
+              }
+        }
+      }
+      // LayerNorm statistics of both edges; a row lives in the 4 lanes of the quad
+      float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          s01 = __fadd2_rn(s01, make_float2(act[m][h][0], act[m][h][1]));
+          s23 = __fadd2_rn(s23, make_float2(act[m][h][2], act[m][h][3]));
+        }
+      float sa = s01.x + s01.y, sb = s23.x + s23.y;
+      sa += __shfl_xor_sync(CBG_FULL, sa, 1); sb += __shfl_xor_sync(CBG_FULL, sb, 1);
+      sa += __shfl_xor_sync(CBG_FULL, sa, 2); sb += __shfl_xor_sync(CBG_FULL, sb, 2);
+      const float na = -sa * (1.f / 128.f), nb = -sb * (1.f / 128.f);
+      float2 v01 = make_float2(0.f, 0.f), v23 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 d01 = __fadd2_rn(make_float2(act[m][h][0], act[m][h][1]), make_float2(na, na));
+          const float2 d23 = __fadd2_rn(make_float2(act[m][h][2], act[m][h][3]), make_float2(nb, nb));
+          act[m][h][0] = d01.x; act[m][h][1] = d01.y; act[m][h][2] = d23.x; act[m][h][3] = d23.y;
+          v01 = __ffma2_rn(d01, d01, v01);
+          v23 = __ffma2_rn(d23, d23, v23);
+        }
+      float va = v01.x + v01.y, vb = v23.x + v23.y;
+      va += __shfl_xor_sync(CBG_FULL, va, 1); vb += __shfl_xor_sync(CBG_FULL, vb, 1);
+      va += __shfl_xor_sync(CBG_FULL, va, 2); vb += __shfl_xor_sync(CBG_FULL, vb, 2);
+      const float ra_ = 1.f / sqrtf(va * (1.f / 128.f) + 1e-5f), rb_ = 1.f / sqrtf(vb * (1.f / 128.f) + 1e-5f);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const float4 gamma = ld4(s_ln + 16 * m + 4 * t), beta = ld4(s_ln + 128 + 16 * m + 4 * t);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 gm = h ? make_float2(gamma.z, gamma.w) : make_float2(gamma.x, gamma.y);
+          const float2 bt = h ? make_float2(beta.z, beta.w) : make_float2(beta.x, beta.y);
+          const float2 y0 = __ffma2_rn(__fmul2_rn(make_float2(act[m][h][0], act[m][h][1]), make_float2(ra_, ra_)), gm, bt);
+          const float2 y1 = __ffma2_rn(__fmul2_rn(make_float2(act[m][h][2], act[m][h][3]), make_float2(rb_, rb_)), gm, bt);
+          const float af[4] = {h ? Uf[m][1].x : Uf[m][0].x, h ? Uf[m][1].y : Uf[m][0].y, h ? Uf[m][1].z : Uf[m][0].z, h ? Uf[m][1].w : Uf[m][0].w};
+          unsigned ah[4], al[4];
+          split_frag(af, ah, al);
+          const float b0[2] = {fmaxf(y0.x, 0.f), fmaxf(y0.y, 0.f)}, b1[2] = {fmaxf(y1.x, 0.f), fmaxf(y1.y, 0.f)};
+          unsigned bh[2], bl[2];
+          split_frag(b0, bh, bl);
+          mma3(acc[2 * pass], ah, al, bh, bl);
+          split_frag(b1, bh, bl);
+          mma3(acc[2 * pass + 1], ah, al, bh, bl);
+        }
+      }
+    }
+    // softmax + store: identical to x2h_k_mma_kernel
+    float* wout = p.w + (size_t)i * (CBG_KMAX * CBG_HEADS);
+#pragma unroll
+    for (int hs = 0; hs < 2; ++hs) {
+      float l[8];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const bool valid = (vmask >> (8 * nt + 2 * t + v)) & 1u;
+          l[2 * nt + v] = valid ? acc[nt][2 * hs + v] : -INFINITY;
+          mx = fmaxf(mx, l[2 * nt + v]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { l[k] = (mx == -INFINITY) ? 0.f : expf(l[k] - mx); sum += l[k]; }
+      sum += __shfl_xor_sync(CBG_FULL, sum, 1);
+      sum += __shfl_xor_sync(CBG_FULL, sum, 2);
+      const float inv = (sum > 0.f) ? sum : 1.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int e = 8 * nt + 2 * t + v;
+          wout[e * CBG_HEADS + g + 8 * hs] = (l[2 * nt + v] / inv) * M.ew[e];
+        }
+    }
+    __syncwarp();
+  }
+}
+
 int g_num_sms = 0;
 int g_edge_warps = 12;
-int g_edge_impl = 2;       // 2 (default, fastest measured): tensor-core x2h_k + SIMT x2h_v; 1: both tensor-core; 0: both SIMT; 3: SIMT k + tensor-core v
+int g_edge_impl = 4;       // 4 (default, fastest measured): x2h_k_mma2 (contraction + RBF on the tensor cores) + SIMT x2h_v; see launch_x2h_mma
 int g_edge_mma_warps = 8;
 int g_h2x_warps = 12;
 
@@ -1189,6 +1438,7 @@ int set_attrs() {
   CBG_CUDA_OK(cudaFuncSetAttribute(h2x_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma_kernel<W, (W > 8 ? 1 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_mma_smem(W)));
+  if (W == 8) CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma2_smem(8)));
   return 0;
 }
 
@@ -1211,7 +1461,8 @@ int launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   return 0;
 }
 
-// impl 1: both kernels on the tensor cores; 2: tensor-core x2h_k + SIMT x2h_v; 3: SIMT x2h_k + tensor-core x2h_v
+// impl 1: both kernels on the tensor cores; 2: tensor-core x2h_k + SIMT x2h_v; 3: SIMT x2h_k + tensor-core x2h_v;
+// 4 / 5: x2h_k with the RBF mat-vec on the tensor cores as well (x2h_k_mma2_kernel) + SIMT / tensor-core x2h_v
 // (the two halves agree on the layout of w, so they can be mixed: used by the tests to localise a mismatch)
 template <int W, int WS>
 int launch_x2h_mma(const EdgeArgs& a, cudaStream_t st, int impl) {
@@ -1219,10 +1470,11 @@ int launch_x2h_mma(const EdgeArgs& a, cudaStream_t st, int impl) {
   if (av.ticket) av.ticket += 1;          // the second kernel has its own work counter
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
   if (impl == 3) x2h_k_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hk_smem(WS), st>>>(a);
+  else if (impl >= 4) x2h_k_mma2_kernel<8><<<edge_grid(a.n_nodes, 8), 8 * 32, x2hk_mma2_smem(8), st>>>(a);
   else x2h_k_mma_kernel<W, (W > 8 ? 1 : 2)><<<edge_grid(a.n_nodes, W), W * 32, x2hk_mma_smem(W), st>>>(a);
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
-  if (impl == 2) x2h_v_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hv_smem(WS), st>>>(av);
+  if (impl == 2 || impl == 4) x2h_v_kernel<WS><<<edge_grid(a.n_nodes, WS), WS * 32, x2hv_smem(WS), st>>>(av);
   else x2h_v_mma_kernel<W><<<edge_grid(a.n_nodes, W), W * 32, x2hv_mma_smem(W), st>>>(av);
   CBG_LAUNCHED(CBG_K_X2H_V, st);
   return 0;
@@ -1251,7 +1503,7 @@ int cbg_edge_init(void) {
   }
   if (const char* e = getenv("CBG_EDGE_IMPL")) {
     if (strcmp(e, "simt") == 0) g_edge_impl = 0;
-    else if (e[0] >= '0' && e[0] <= '3' && e[1] == 0) g_edge_impl = e[0] - '0';
+    else if (e[0] >= '0' && e[0] <= '5' && e[1] == 0) g_edge_impl = e[0] - '0';
   }
   if (const char* e = getenv("CBG_H2X_WARPS")) {
     const int w = atoi(e);
@@ -1315,7 +1567,7 @@ int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
 // testing / tuning hook (include/cbg_b200.h): pick the X2H edge-kernel implementation and its warps per CTA
 int cbg_edge_set_impl(int impl, int warps) {
   if (int rc = cbg_edge_init()) return rc;
-  if (impl < 0 || impl > 3) { cbg_set_error("edge impl must be 0 (simt), 1 (mma), 2 (mma k + simt v) or 3 (simt k + mma v)"); return 1; }
+  if (impl < 0 || impl > 5) { cbg_set_error("edge impl must be 0 (simt), 1 (mma), 2 (mma k + simt v), 3 (simt k + mma v), 4 (mma2 k + simt v) or 5 (mma2 k + mma v)"); return 1; }
   if (warps != 0 && warps != 8 && warps != 12 && warps != 16) { cbg_set_error("warps per CTA must be 8, 12 or 16"); return 1; }
   g_edge_impl = impl;
   if (warps) { if (impl) g_edge_mma_warps = warps; else g_edge_warps = warps; }

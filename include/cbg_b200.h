@@ -52,9 +52,11 @@ int32_t cbg_profile_enable(int32_t on);
 int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family);
 
 /* Tuning / testing hook: implementation of the two fused X2H edge kernels (the dominant kernels of a step).
- *   impl 1: per-node contractions of both kernels on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split, fp32 accumulate)
- *   impl 0: fp32 SIMT kernels;  2 (default, fastest measured) / 3: tensor-core attention-weight kernel + SIMT
- *   aggregation kernel / the reverse pairing
+ *   impl 4 (default, fastest measured): attention-weight kernel with the per-node head contraction AND the RBF mat-vec of
+ *           the non-cached edges on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split, fp32 accumulate) + SIMT
+ *           aggregation kernel;  5: the same + tensor-core aggregation kernel
+ *   impl 1 / 2 / 3: first tensor-core generation (contraction only): both kernels / attention-weight kernel only /
+ *           aggregation kernel only;  impl 0: fp32 SIMT kernels
  * warps = CTA size in warps (8, 12, 16; 0 keeps the current value).  Process-wide; also env CBG_EDGE_IMPL,
  * CBG_EDGE_MMA_WARPS, CBG_EDGE_WARPS.  Needs a current CUDA device. */
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);

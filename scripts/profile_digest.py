@@ -25,7 +25,7 @@ def raw_metrics(rep):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else 'vX'
     traffic = {'_source': f'ncu --set full --clock-control none, one launch each, bench.py c2 shape (profiles/r01_ncu_*_{tag}.txt)'}
-    for kernel, fam in (('x2h_k_mma_kernel', 'x2h_k'), ('x2h_v_kernel', 'x2h_v'), ('node_gemm_ws_kernel', None), ('h2x_kernel', None)):
+    for kernel, fam in (('x2h_k_mma2_kernel', 'x2h_k'), ('x2h_v_kernel', 'x2h_v'), ('node_gemm_ws_kernel', None), ('h2x_kernel', None)):
         rep = os.path.join(OUT, f'prof3_{kernel}.ncu-rep')
         if not os.path.exists(rep):
             continue
@@ -66,13 +66,13 @@ def main():
             f.write(f'total {total:.1f} us over {sum(cnt.values())} launches\n')
             for name, v in tot.most_common():
                 f.write(f'{name:44s} n={cnt[name]:3d} total {v:9.1f} us  avg {v / cnt[name]:7.1f}  {100 * v / total:5.1f}%\n')
-    for src, dst in (('bench_full.log', f'r01_bench_{tag}_full.json'), ('bench_f3.log', f'r01_bench_{tag}_f3.json'),
+    for src, dst in (('bench_full.log', f'r01_bench_{tag}_full.json'), ('bench_f3.log', f'r01_bench_{tag}_f3.json'), ('bench_f2.log', f'r01_bench_{tag}_f2.jsonl'),
                      ('pytest_gpu.log', f'r01_pytest_gpu_{tag}.log')):
         p = os.path.join(OUT, src)
         if os.path.exists(p):
             lines = open(p).read().strip().splitlines()
             with open(os.path.join(PROF, dst), 'w') as f:
-                f.write((lines[-1] if dst.endswith('.json') else '\n'.join(lines[-6:])) + '\n')
+                f.write((lines[-1] if dst.endswith('.json') else '\n'.join(l for l in lines[-6:] if not dst.endswith('.jsonl') or l.startswith('{'))) + '\n')
     print('profiles updated for', tag)
 
 

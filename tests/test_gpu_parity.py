@@ -487,7 +487,7 @@ def test_sample_driver_single_gpu(tmp_path):
 
 # ---------------------------------------------------------------------------------------------
 # the two implementations of the fused X2H edge kernels (tensor-core mma.sync 3xTF32 vs fp32 SIMT)
-EDGE_IMPLS = {0: 'simt', 1: 'mma', 2: 'mma_k+simt_v', 3: 'simt_k+mma_v'}
+EDGE_IMPLS = {0: 'simt', 1: 'mma', 2: 'mma_k+simt_v', 3: 'simt_k+mma_v', 4: 'mma2_k+simt_v', 5: 'mma2_k+mma_v'}
 
 
 @pytest.fixture
@@ -495,7 +495,7 @@ def edge_impl_reset():
     yield
     _lib.check(_lib.lib().cbg_set_edge_impl(1, 8))
     _lib.check(_lib.lib().cbg_set_edge_impl(0, 12))
-    _lib.check(_lib.lib().cbg_set_edge_impl(2, 0))     # library default
+    _lib.check(_lib.lib().cbg_set_edge_impl(4, 0))     # library default
 
 
 @pytest.mark.parametrize('case', FORWARD_CASES, ids=[c[0] for c in FORWARD_CASES])
@@ -542,13 +542,14 @@ def test_edge_kernel_implementations_agree_on_the_sampling_path(edge_impl_reset)
         for rcache in (True, False):
             model.use_rcache = rcache
             res = {}
-            for impl in (0, 1):
+            for impl in (0, 1, 4):
                 _lib.check(_lib.lib().cbg_set_edge_impl(impl, 0))
                 res[impl] = model.sample(batch, pos_noise=pn, type_uniform=tu)
-            for t in range(-1, T):
-                assert torch.equal(res[0][t][1].cpu().argmax(-1), res[1][t][1].cpu().argmax(-1)), (gen_mode, rcache, t)
-                e = rel_err(res[1][t][0].cpu(), res[0][t][0].cpu())
-                assert e < 1e-5, (gen_mode, rcache, t, e)
+            for impl in (1, 4):
+                for t in range(-1, T):
+                    assert torch.equal(res[0][t][1].cpu().argmax(-1), res[impl][t][1].cpu().argmax(-1)), (gen_mode, rcache, impl, t)
+                    e = rel_err(res[impl][t][0].cpu(), res[0][t][0].cpu())
+                    assert e < 1e-5, (gen_mode, rcache, impl, t, e)
 
 
 def test_static_fast_path_and_dynamic_scheduling_are_bit_identical(edge_impl_reset):
@@ -563,7 +564,7 @@ def test_static_fast_path_and_dynamic_scheduling_are_bit_identical(edge_impl_res
             batch = synthetic.make_batch(*sizes, seed=141, gen_mode=gen_mode)
             n_lig = int(batch['ligand_pos'].shape[0])
             pn, tu = synthetic.make_noise(T, n_lig, 13, seed=23)
-            for impl in (0, 1, 2):
+            for impl in (0, 1, 2, 4):
                 _lib.check(L.cbg_set_edge_impl(impl, 0))
                 res = {}
                 for fast, dyn in ((1, 1), (0, 1), (1, 0), (0, 0)):
