@@ -336,6 +336,7 @@ int32_t cbg_set_edge_impl(int32_t impl, int32_t warps) { return cbg_edge_set_imp
 int32_t cbg_set_option(const char* key, int32_t value) {
   if (key && strcmp(key, "static_fast") == 0) { g_static_fast = value ? 1 : 0; return 0; }
   if (key && strcmp(key, "dyn_sched") == 0) { g_dyn_sched = value ? 1 : 0; return 0; }
+  if (key && strcmp(key, "h2x_impl") == 0) return cbg_edge_set_h2x_impl(value);
   cbg_set_error("cbg_set_option: unknown key '%s'", key ? key : "(null)");
   return 1;
 }

@@ -78,6 +78,7 @@ int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st);
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st);
 int cbg_edge_init(void);  // sets max-dynamic-smem attributes once
 int cbg_edge_set_impl(int impl, int warps);  // X2H implementation switch (cbg_set_edge_impl)
+int cbg_edge_set_h2x_impl(int impl);         // H2X implementation switch (cbg_set_option "h2x_impl")
 
 // misc.cu
 int cbg_launch_pack_x4(const float* x, const unsigned char* lig_flag, const unsigned char* gen_flag,

@@ -1425,11 +1425,315 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma2_kernel(EdgeArgs p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// H2X on the tensor cores, two warps per generated node.
+//
+// Every in-edge of a generated node is "dynamic" (its end point moves), so both edge MLPs of H2X take the RBF path for
+// all 32 edges; with one warp per node the launch is one long latency chain (1 536 nodes on 1 776 warp slots at c2).
+// Here a node is handled by a PAIR of warps of the same CTA:
+//   K warp: edge_setup, query folding, k-MLP (two 16-edge passes exactly like x2h_k_mma2_kernel: RBF mat-vec and head
+//           contraction as MMAs), softmax -> alpha * e_w into the pair's shared buffer
+//   V warp: v-MLP with the same pass code (A fragments = xv_func's second Linear [16 heads x 128], from shared memory),
+//           then dx_i = 1/16 sum_{e,hd} alpha e_w (W1xv a + b1)[e][hd] (x_i - x_j)
+// The two meet at named barriers (one id per pair): M ready -> alpha ready -> node done.
+constexpr int kH2xPairK = kWimgFloats + 4 * 128 + 256 + 128 * 128;          // K: WIMG | C | LN | W1 (U fragments)
+constexpr int kH2xPairV = kWimgFloats + 4 * 128 + 256 + 16 * 128 + 32;      // V: WIMG | C | LN | W1 (A fragments) | B1
+constexpr int kH2xPairFloats = kH2xPairK + kH2xPairV + 32;                  // + RBF
+constexpr int kPairScratchFloats = 128 + 128 + 128 + 32 * 16;               // q (fragment order) | Pi_k | Pi_v | alpha * e_w
+constexpr int h2x_pair_smem(int pairs) { return kH2xPairFloats * 4 + pairs * ((int)sizeof(EdgeMeta) + kPairScratchFloats * 4); }
+
+// A fragments of xv_func's second Linear: frag[(m*2+h)*32 + lane] = {W[g][f], W[g+8][f], W[g][f+1], W[g+8][f+1]}, f = 16m+4t+2h
+__device__ __forceinline__ void block_copy_w1xv_frag(float* dst, const float* __restrict__ w /*[16][128]*/) {
+  for (int idx = threadIdx.x; idx < 16 * 32; idx += blockDim.x) {
+    const int ln = idx & 31, mh = idx >> 5, gp = ln >> 2, tp = ln & 3;
+    const int f = 16 * (mh >> 1) + 4 * tp + 2 * (mh & 1);
+    st4(dst + 4 * idx, make_float4(__ldg(w + gp * CBG_H + f), __ldg(w + (gp + 8) * CBG_H + f),
+                                   __ldg(w + gp * CBG_H + f + 1), __ldg(w + (gp + 8) * CBG_H + f + 1)));
+  }
+}
+
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+struct RegFrag {          // A fragments held in registers (query-folded key matrix)
+  const float4 (&U)[8][2];
+  __device__ __forceinline__ float4 get(int m, int h) const { return h ? U[m][1] : U[m][0]; }
+};
+struct SmemFrag {         // A fragments in shared memory, one LDS.128 per k-tile
+  const float* img;
+  int lane;
+  __device__ __forceinline__ float4 get(int m, int h) const { return ld4(img + ((m * 2 + h) * 32 + lane) * 4); }
+};
+
+// One 16-edge pass of an edge MLP whose edges are all non-cached (see x2h_k_mma2_kernel for the layout):
+// acc0 / acc1 += A . relu(LN(Pi + Pj[j] + c[type] + Wrf[type] g))^T for the edge blocks 2*pass and 2*pass + 1.
+template <class AFrag>
+__device__ __forceinline__ void mlp_pass16_dynamic(const EdgeMeta& M, int pass, int g, int t, int lane,
+                                                   const float* pist, const float* __restrict__ pj_plane,
+                                                   const float* s_c, const float* s_wimg, const float* s_ln,
+                                                   const AFrag& A, float (&acc0)[4], float (&acc1)[4]) {
+  const int e0 = 16 * pass + g, e1 = e0 + 8;
+  const int t0 = M.t[e0], t1 = M.t[e1];
+  float act[8][2][4];
+  {
+    const float* pj0 = pj_plane + (size_t)M.j[e0] * CBG_H + 4 * t;
+    const float* pj1 = pj_plane + (size_t)M.j[e1] * CBG_H + 4 * t;
+    const float* c0 = s_c + t0 * CBG_H + 4 * t;
+    const float* c1 = s_c + t1 * CBG_H + 4 * t;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const float4 pi4 = ld4(pist + 4 * t + 16 * m);
+      const float4 x0 = ldg4(pj0 + 16 * m), x1 = ldg4(pj1 + 16 * m);
+      const float4 y0 = ld4(c0 + 16 * m), y1 = ld4(c1 + 16 * m);
+      act[m][0][0] = (pi4.x + x0.x) + y0.x; act[m][0][1] = (pi4.y + x0.y) + y0.y;
+      act[m][0][2] = (pi4.x + x1.x) + y1.x; act[m][0][3] = (pi4.y + x1.y) + y1.y;
+      act[m][1][0] = (pi4.z + x0.z) + y0.z; act[m][1][1] = (pi4.w + x0.w) + y0.w;
+      act[m][1][2] = (pi4.z + x1.z) + y1.z; act[m][1][3] = (pi4.w + x1.w) + y1.w;
+    }
+  }
+#pragma unroll 1
+  for (int ty = 0; ty < CBG_NTYPE; ++ty) {
+    if (!__any_sync(CBG_FULL, t0 == ty || t1 == ty)) continue;
+    const float m0 = t0 == ty ? 1.f : 0.f, m1 = t1 == ty ? 1.f : 0.f;
+    unsigned gh[3][4], gl[3][4];
+#pragma unroll
+    for (int kt = 0; kt < 3; ++kt) {
+      const int ra = 8 * kt + t;
+      const float gf[4] = {M.g[ra][e0] * m0, M.g[ra][e1] * m1,
+                           kt < 2 ? M.g[kt < 2 ? ra + 4 : 0][e0] * m0 : 0.f, kt < 2 ? M.g[kt < 2 ? ra + 4 : 0][e1] * m1 : 0.f};
+      split_frag(gf, gh[kt], gl[kt]);
+    }
+    const float* img = s_wimg + ty * (3 * 16 * 64) + 2 * lane;
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+          const float2 wv = *reinterpret_cast<const float2*>(img + (kt * 16 + 2 * m + h) * 64);
+          const float bf[2] = {wv.x, wv.y};
+          unsigned bh[2], bl[2];
+          split_frag(bf, bh, bl);
+          mma3(act[m][h], gh[kt], gl[kt], bh, bl);
+        }
+  }
+  float2 s01 = make_float2(0.f, 0.f), s23 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      s01 = __fadd2_rn(s01, make_float2(act[m][h][0], act[m][h][1]));
+      s23 = __fadd2_rn(s23, make_float2(act[m][h][2], act[m][h][3]));
+    }
+  float sa = s01.x + s01.y, sb = s23.x + s23.y;
+  sa += __shfl_xor_sync(CBG_FULL, sa, 1); sb += __shfl_xor_sync(CBG_FULL, sb, 1);
+  sa += __shfl_xor_sync(CBG_FULL, sa, 2); sb += __shfl_xor_sync(CBG_FULL, sb, 2);
+  const float na = -sa * (1.f / 128.f), nb = -sb * (1.f / 128.f);
+  float2 v01 = make_float2(0.f, 0.f), v23 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 d01 = __fadd2_rn(make_float2(act[m][h][0], act[m][h][1]), make_float2(na, na));
+      const float2 d23 = __fadd2_rn(make_float2(act[m][h][2], act[m][h][3]), make_float2(nb, nb));
+      act[m][h][0] = d01.x; act[m][h][1] = d01.y; act[m][h][2] = d23.x; act[m][h][3] = d23.y;
+      v01 = __ffma2_rn(d01, d01, v01);
+      v23 = __ffma2_rn(d23, d23, v23);
+    }
+  float va = v01.x + v01.y, vb = v23.x + v23.y;
+  va += __shfl_xor_sync(CBG_FULL, va, 1); vb += __shfl_xor_sync(CBG_FULL, vb, 1);
+  va += __shfl_xor_sync(CBG_FULL, va, 2); vb += __shfl_xor_sync(CBG_FULL, vb, 2);
+  const float ra_ = 1.f / sqrtf(va * (1.f / 128.f) + 1e-5f), rb_ = 1.f / sqrtf(vb * (1.f / 128.f) + 1e-5f);
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const float4 gamma = ld4(s_ln + 16 * m + 4 * t), beta = ld4(s_ln + 128 + 16 * m + 4 * t);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 gm = h ? make_float2(gamma.z, gamma.w) : make_float2(gamma.x, gamma.y);
+      const float2 bt = h ? make_float2(beta.z, beta.w) : make_float2(beta.x, beta.y);
+      const float2 y0 = __ffma2_rn(__fmul2_rn(make_float2(act[m][h][0], act[m][h][1]), make_float2(ra_, ra_)), gm, bt);
+      const float2 y1 = __ffma2_rn(__fmul2_rn(make_float2(act[m][h][2], act[m][h][3]), make_float2(rb_, rb_)), gm, bt);
+      const float4 a4 = A.get(m, h);
+      const float af[4] = {a4.x, a4.y, a4.z, a4.w};
+      unsigned ah[4], al[4];
+      split_frag(af, ah, al);
+      const float b0[2] = {fmaxf(y0.x, 0.f), fmaxf(y0.y, 0.f)}, b1[2] = {fmaxf(y1.x, 0.f), fmaxf(y1.y, 0.f)};
+      unsigned bh[2], bl[2];
+      split_frag(b0, bh, bl);
+      mma3(acc0, ah, al, bh, bl);
+      split_frag(b1, bh, bl);
+      mma3(acc1, ah, al, bh, bl);
+    }
+  }
+}
+
+template <int kPairs>
+__global__ void __launch_bounds__(kPairs * 64, 1) h2x_pair_kernel(EdgeArgs p) {
+  extern __shared__ __align__(16) float smem[];
+  float* k_wimg = smem;
+  float* k_c = k_wimg + kWimgFloats;
+  float* k_ln = k_c + 4 * 128;
+  float* k_w1 = k_ln + 256;
+  float* v_wimg = k_w1 + 128 * 128;
+  float* v_c = v_wimg + kWimgFloats;
+  float* v_ln = v_c + 4 * 128;
+  float* v_w1 = v_ln + 256;               // A fragments of xv_func.net.3
+  float* v_b1 = v_w1 + 16 * 128;
+  float* s_rbf = v_b1 + 32;
+  EdgeMeta* metas = reinterpret_cast<EdgeMeta*>(smem + kH2xPairFloats);
+  float* scratch = reinterpret_cast<float*>(metas + kPairs);
+  {
+    // blob (cbg_layout.h): K_WRF | K_C | K_LN | K_W1 | V_WRF | V_C | V_LN | V_W1 [16][128] | V_B1 (32) | RBF (32)
+    const float* src = p.layer + kOffH2x;
+    constexpr int kWrf = 4 * 20 * 128, kCL = 4 * 128 + 256;
+    block_copy_wrf_frag(k_wimg, src);
+    block_copy_f4(k_c, src + kWrf, kCL);
+    block_copy_w1k_frag(k_w1, src + kWrf + kCL);
+    const float* vsrc = src + kWrf + kCL + 128 * 128;
+    block_copy_wrf_frag(v_wimg, vsrc);
+    block_copy_f4(v_c, vsrc + kWrf, kCL);
+    block_copy_w1xv_frag(v_w1, vsrc + kWrf + kCL);
+    block_copy_f4(v_b1, vsrc + kWrf + kCL + 16 * 128, 32 + 32);       // V_B1 | RBF
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = warp >> 1, role = warp & 1;
+  const int g = lane >> 2, t = lane & 3;
+  EdgeMeta& M = metas[pair];
+  float* qst = scratch + pair * kPairScratchFloats;
+  float* pik = qst + 128;
+  float* piv = pik + 128;
+  float* alpha = piv + 128;                 // [32 edges][16 heads]: softmax * e_w
+  const int bar = 1 + pair;
+
+  for (int n = blockIdx.x * kPairs + pair; n < p.n_nodes; n += gridDim.x * kPairs) {
+    const int i = p.node_idx[n];
+    if (role == 0) {
+      // ---------------- K warp ----------------
+      const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
+      pair_barrier(bar);                                            // (1) M ready
+      float4 Uf[8][2];
+      {
+        {
+          const float4 q4 = ldg4(p.q + (size_t)i * CBG_H + 4 * lane);
+          const int hd = lane >> 1, d0 = 4 * (lane & 1);
+          float* dst = qst + ((hd & 7) * 8 + d0) * 2 + (hd >> 3);
+          dst[0] = q4.x; dst[2] = q4.y; dst[4] = q4.z; dst[6] = q4.w;
+          st4(pik + 4 * lane, ldg4(p.pi_k + (size_t)i * CBG_H + 4 * lane));
+        }
+        __syncwarp();
+        unsigned long long qp[8];
+#pragma unroll
+        for (int dd = 0; dd < 4; ++dd) {
+          const float4 v = ld4(qst + g * 16 + 4 * dd);
+          qp[2 * dd] = pack_f32x2(v.x, v.y);
+          qp[2 * dd + 1] = pack_f32x2(v.z, v.w);
+        }
+        unsigned long long Up[8][2][2];
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) Up[m][u][0] = Up[m][u][1] = 0ull;
+        const int sw = g & 1;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          const float* row = k_w1 + (g * 8 + d) * 256;
+#pragma unroll
+          for (int m = 0; m < 8; ++m)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const float4 w4 = ld4(row + 4 * ((8 * m + 2 * t + u) ^ sw));
+              Up[m][u][0] = fma_f32x2(pack_f32x2(w4.x, w4.y), qp[d], Up[m][u][0]);
+              Up[m][u][1] = fma_f32x2(pack_f32x2(w4.z, w4.w), qp[d], Up[m][u][1]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            unpack_f32x2(Up[m][u][0], Uf[m][u].x, Uf[m][u].y);
+            unpack_f32x2(Up[m][u][1], Uf[m][u].z, Uf[m][u].w);
+          }
+      }
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+      const RegFrag A{Uf};
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass)
+        mlp_pass16_dynamic(M, pass, g, t, lane, pik, p.pj_k, k_c, k_wimg, k_ln, A, acc[2 * pass], acc[2 * pass + 1]);
+      // softmax over the 32 edges of heads g and g + 8 (see x2h_k_mma_kernel), times e_w
+#pragma unroll
+      for (int hs = 0; hs < 2; ++hs) {
+        float l[8];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const bool valid = (vmask >> (8 * nt + 2 * t + v)) & 1u;
+            l[2 * nt + v] = valid ? acc[nt][2 * hs + v] : -INFINITY;
+            mx = fmaxf(mx, l[2 * nt + v]);
+          }
+        mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 2));
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { l[k] = (mx == -INFINITY) ? 0.f : expf(l[k] - mx); sum += l[k]; }
+        sum += __shfl_xor_sync(CBG_FULL, sum, 1);
+        sum += __shfl_xor_sync(CBG_FULL, sum, 2);
+        const float inv = (sum > 0.f) ? sum : 1.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) {
+            const int e = 8 * nt + 2 * t + v;
+            alpha[e * CBG_HEADS + g + 8 * hs] = (l[2 * nt + v] / inv) * M.ew[e];
+          }
+      }
+      pair_barrier(bar);                                            // (2) alpha ready
+      pair_barrier(bar);                                            // (3) V warp done with M / alpha
+    } else {
+      // ---------------- V warp ----------------
+      st4(piv + 4 * lane, ldg4(p.pi_v + (size_t)i * CBG_H + 4 * lane));
+      pair_barrier(bar);                                            // (1) M ready (also orders the piv writes for this warp)
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[nt][k] = 0.f;
+      const SmemFrag A{v_w1, lane};
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass)
+        mlp_pass16_dynamic(M, pass, g, t, lane, piv, p.pj_v, v_c, v_wimg, v_ln, A, acc[2 * pass], acc[2 * pass + 1]);
+      pair_barrier(bar);                                            // (2) alpha ready
+      // acc[nt][0..1]: head g, edges 8nt + 2t, +1; acc[nt][2..3]: head g + 8
+      const float b1a = v_b1[g], b1b = v_b1[g + 8];
+      float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          const int e = 8 * nt + 2 * t + v;
+          const float coef = alpha[e * CBG_HEADS + g] * (acc[nt][v] + b1a) + alpha[e * CBG_HEADS + g + 8] * (acc[nt][2 + v] + b1b);
+          ax = fmaf(coef, M.rel[0][e], ax);
+          ay = fmaf(coef, M.rel[1][e], ay);
+          az = fmaf(coef, M.rel[2][e], az);
+        }
+      ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+      if (lane == 0) st4(p.dx + 4 * (size_t)n, make_float4(ax * (1.f / 16.f), ay * (1.f / 16.f), az * (1.f / 16.f), 0.f));
+      pair_barrier(bar);                                            // (3) node done
+    }
+  }
+}
+
 int g_num_sms = 0;
 int g_edge_warps = 12;
 int g_edge_impl = 4;       // 4 (default, fastest measured): x2h_k_mma2 (contraction + RBF on the tensor cores) + SIMT x2h_v; see launch_x2h_mma
 int g_edge_mma_warps = 8;
 int g_h2x_warps = 12;
+int g_h2x_impl = 0;        // 0 (default, measured faster at c2: 85 vs 91 us per launch): SIMT kernel; 1: tensor-core pair kernel
 
 template <int W>
 int set_attrs() {
@@ -1438,6 +1742,7 @@ int set_attrs() {
   CBG_CUDA_OK(cudaFuncSetAttribute(h2x_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma_kernel<W, (W > 8 ? 1 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_mma_smem(W)));
+  if (W == 8) CBG_CUDA_OK(cudaFuncSetAttribute(h2x_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_pair_smem(4)));
   if (W == 8) CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma2_smem(8)));
   return 0;
 }
@@ -1505,6 +1810,7 @@ int cbg_edge_init(void) {
     if (strcmp(e, "simt") == 0) g_edge_impl = 0;
     else if (e[0] >= '0' && e[0] <= '5' && e[1] == 0) g_edge_impl = e[0] - '0';
   }
+  if (const char* e = getenv("CBG_H2X_IMPL")) g_h2x_impl = (e[0] == '0') ? 0 : 1;
   if (const char* e = getenv("CBG_H2X_WARPS")) {
     const int w = atoi(e);
     if (w == 8 || w == 12 || w == 16) g_h2x_warps = w;
@@ -1557,6 +1863,14 @@ int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
+  if (g_h2x_impl == 1) {
+    constexpr int kPairs = 4;
+    const int need = (a.n_nodes + kPairs - 1) / kPairs;
+    CBG_PROF_BEGIN(CBG_K_H2X, st);
+    h2x_pair_kernel<kPairs><<<need < g_num_sms ? need : g_num_sms, kPairs * 64, h2x_pair_smem(kPairs), st>>>(a);
+    CBG_LAUNCHED(CBG_K_H2X, st);
+    return 0;
+  }
   switch (g_h2x_warps) {
     case 8: return launch_h2x<8>(a, st);
     case 16: return launch_h2x<16>(a, st);
@@ -1571,5 +1885,12 @@ int cbg_edge_set_impl(int impl, int warps) {
   if (warps != 0 && warps != 8 && warps != 12 && warps != 16) { cbg_set_error("warps per CTA must be 8, 12 or 16"); return 1; }
   g_edge_impl = impl;
   if (warps) { if (impl) g_edge_mma_warps = warps; else g_edge_warps = warps; }
+  return 0;
+}
+
+int cbg_edge_set_h2x_impl(int impl) {
+  if (int rc = cbg_edge_init()) return rc;
+  if (impl != 0 && impl != 1) { cbg_set_error("h2x impl must be 0 (simt) or 1 (tensor-core pair kernel)"); return 1; }
+  g_h2x_impl = impl;
   return 0;
 }

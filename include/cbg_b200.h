@@ -63,7 +63,9 @@ int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);
 /* Other process-wide switches (testing): "static_fast" = 1 (default; env CBG_STATIC_FAST) lets the X2H kernels skip the
  * coordinate gathers / RBF set-up of nodes whose 32 in-edges are all served from the R-cache (bit-identical results);
  * "dyn_sched" = 1 (default; env CBG_DYN_SCHED): warps of the X2H kernels draw their next node from a work counter instead
- * of a static round-robin (bit-identical results, better balance). */
+ * of a static round-robin (bit-identical results, better balance);
+ * "h2x_impl" = 0 (default; env CBG_H2X_IMPL): fp32 SIMT H2X edge kernel (one warp per generated node), 1 = two warps per
+ * node with both edge MLPs on the tensor cores (tested alternative; slower at the c2 shape). */
 int32_t cbg_set_option(const char* key, int32_t value);
 
 /* ---- packed weight blob layout (single source of truth: csrc/cbg_layout.h) -------------------

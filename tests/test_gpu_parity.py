@@ -578,3 +578,38 @@ def test_static_fast_path_and_dynamic_scheduling_are_bit_identical(edge_impl_res
     finally:
         _lib.check(L.cbg_set_option(b'static_fast', 1))
         _lib.check(L.cbg_set_option(b'dyn_sched', 1))
+
+
+def test_h2x_implementations_agree(edge_impl_reset):
+    """H2X edge kernel: tensor-core pair kernel (two warps per generated node) vs the fp32 SIMT kernel - same goldens, equal
+    to rounding, on de-novo, partial-generation, tiny and k=8 graphs; and along a short sampled trajectory."""
+    L = _lib.lib()
+    gold = golden('forward_cases.npz')
+    try:
+        for case in FORWARD_CASES:
+            name, n_prot, n_lig, seed, gen_mode, enc = case
+            model, sd = make_model(10, device=dev(), **enc)
+            batch = synthetic.make_batch(n_prot, n_lig, seed=seed, gen_mode=gen_mode)
+            x, h, bidx, lig, gen = composed_inputs(sd, batch)
+            args = [t.to(dev()) for t in (x, h, bidx, lig, gen)]
+            outs = {}
+            for impl in (0, 1):
+                _lib.check(L.cbg_set_option(b'h2x_impl', impl))
+                outs[impl] = [t.cpu() for t in model.denoiser(*args)]
+                for a, k in zip(outs[impl], ('x', 'h', 'c')):
+                    assert rel_err(a, gold[f'{name}/{k}']) < TOL, (name, impl, k)
+            assert rel_err(outs[1][0], outs[0][0]) < 1e-5 and rel_err(outs[1][1], outs[0][1]) < 1e-5, name
+            assert torch.equal(outs[1][0][~gen], x[~gen])
+        T = 5
+        model, sd = make_model(T, device=dev())
+        batch = synthetic.make_batch([140, 60, 20], [20, 9, 5], seed=151)
+        pn, tu = synthetic.make_noise(T, 34, 13, seed=29)
+        res = {}
+        for impl in (0, 1):
+            _lib.check(L.cbg_set_option(b'h2x_impl', impl))
+            res[impl] = model.sample(batch, pos_noise=pn, type_uniform=tu)
+        for t in range(-1, T):
+            assert torch.equal(res[0][t][1].cpu().argmax(-1), res[1][t][1].cpu().argmax(-1)), t
+            assert rel_err(res[1][t][0].cpu(), res[0][t][0].cpu()) < 1e-5, t
+    finally:
+        _lib.check(L.cbg_set_option(b'h2x_impl', 0))      # library default
