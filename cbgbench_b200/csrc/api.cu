@@ -297,7 +297,8 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     }
     EdgeArgs x = e;
     x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
-    x.node_idx = gen_idx; x.n_nodes = n_gen; x.n_nodes_dev = nullptr; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr; x.fstat = nullptr; x.ticket = nullptr;
+    x.node_idx = gen_idx; x.n_nodes = n_gen; x.n_nodes_dev = nullptr; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr; x.fstat = nullptr;
+    x.ticket = (tickets && num_layers <= 16) ? ws.tickets + 32 + l : nullptr;      // used by the pair kernel only (x2h: 0 .. 2L-1)
     if (int rc = cbg_launch_h2x(x, sx)) return rc;
     if (int rc = cbg_launch_apply_dx(ws.x4, gen_idx, ws.dx, n_gen, sx)) return rc;
     if (overlap) { CBG_CUDA_OK(cudaEventRecord(g_aux.ev_x, sx)); x_pending = true; }

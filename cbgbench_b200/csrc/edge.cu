@@ -1439,7 +1439,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) x2h_k_mma2_kernel(EdgeArgs p) 
 constexpr int kH2xPairK = kWimgFloats + 4 * 128 + 256 + 128 * 128;          // K: WIMG | C | LN | W1 (U fragments)
 constexpr int kH2xPairV = kWimgFloats + 4 * 128 + 256 + 16 * 128 + 32;      // V: WIMG | C | LN | W1 (A fragments) | B1
 constexpr int kH2xPairFloats = kH2xPairK + kH2xPairV + 32;                  // + RBF
-constexpr int kPairScratchFloats = 128 + 128 + 128 + 32 * 16;               // q (fragment order) | Pi_k | Pi_v | alpha * e_w
+constexpr int kPairScratchFloats = 128 + 128 + 128 + 32 * 16 + 4;           // q (fragment order) | Pi_k | Pi_v | alpha * e_w | next node
 constexpr int h2x_pair_smem(int pairs) { return kH2xPairFloats * 4 + pairs * ((int)sizeof(EdgeMeta) + kPairScratchFloats * 4); }
 
 // A fragments of xv_func's second Linear: frag[(m*2+h)*32 + lane] = {W[g][f], W[g+8][f], W[g][f+1], W[g+8][f+1]}, f = 16m+4t+2h
@@ -1604,13 +1604,22 @@ __global__ void __launch_bounds__(kPairs * 64, 1) h2x_pair_kernel(EdgeArgs p) {
   float* piv = pik + 128;
   float* alpha = piv + 128;                 // [32 edges][16 heads]: softmax * e_w
   const int bar = 1 + pair;
-
-  for (int n = blockIdx.x * kPairs + pair; n < p.n_nodes; n += gridDim.x * kPairs) {
+  int* next_slot = reinterpret_cast<int*>(alpha + 32 * 16);
+  // node scheduling: a work counter shared by all pairs (p.ticket) or a static round-robin; the K warp draws, the pair
+  // reads the result after a barrier
+  int n = blockIdx.x * kPairs + pair;
+  if (p.ticket != nullptr) {
+    if (role == 0 && lane == 0) *next_slot = atomicAdd(p.ticket, 1);
+    pair_barrier(bar);
+    n = *next_slot;
+  }
+  while (n < p.n_nodes) {
     const int i = p.node_idx[n];
     if (role == 0) {
       // ---------------- K warp ----------------
       const unsigned vmask = edge_setup(M, i, lane, p.x4, p.nbr, p.ew, s_rbf);
       pair_barrier(bar);                                            // (1) M ready
+      const int nxt = (p.ticket != nullptr && lane == 0) ? atomicAdd(p.ticket, 1) : 0;   // next node: latency hidden behind this one
       float4 Uf[8][2];
       {
         {
@@ -1693,7 +1702,8 @@ __global__ void __launch_bounds__(kPairs * 64, 1) h2x_pair_kernel(EdgeArgs p) {
           }
       }
       pair_barrier(bar);                                            // (2) alpha ready
-      pair_barrier(bar);                                            // (3) V warp done with M / alpha
+      pair_barrier(bar);                                            // (3) V warp done with M / alpha / next_slot
+      if (p.ticket != nullptr && lane == 0) *next_slot = nxt;
     } else {
       // ---------------- V warp ----------------
       st4(piv + 4 * lane, ldg4(p.pi_v + (size_t)i * CBG_H + 4 * lane));
@@ -1725,6 +1735,12 @@ __global__ void __launch_bounds__(kPairs * 64, 1) h2x_pair_kernel(EdgeArgs p) {
       if (lane == 0) st4(p.dx + 4 * (size_t)n, make_float4(ax * (1.f / 16.f), ay * (1.f / 16.f), az * (1.f / 16.f), 0.f));
       pair_barrier(bar);                                            // (3) node done
     }
+    if (p.ticket != nullptr) {
+      pair_barrier(bar);                                            // (4) next node published
+      n = *next_slot;
+    } else {
+      n += gridDim.x * kPairs;
+    }
   }
 }
 
@@ -1733,6 +1749,7 @@ int g_edge_warps = 12;
 int g_edge_impl = 4;       // 4 (default, fastest measured): x2h_k_mma2 (contraction + RBF on the tensor cores) + SIMT x2h_v; see launch_x2h_mma
 int g_edge_mma_warps = 8;
 int g_h2x_warps = 12;
+int g_h2x_pairs = 4;       // node pairs per CTA of the pair kernel (4: 255 registers, 5: 204)
 int g_h2x_impl = 0;        // 0 (default, measured faster at c2: 85 vs 91 us per launch): SIMT kernel; 1: tensor-core pair kernel
 
 template <int W>
@@ -1743,6 +1760,7 @@ int set_attrs() {
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma_kernel<W, (W > 8 ? 1 : 2)>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma_smem(W)));
   CBG_CUDA_OK(cudaFuncSetAttribute(x2h_v_mma_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hv_mma_smem(W)));
   if (W == 8) CBG_CUDA_OK(cudaFuncSetAttribute(h2x_pair_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_pair_smem(4)));
+  if (W == 8) CBG_CUDA_OK(cudaFuncSetAttribute(h2x_pair_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, h2x_pair_smem(5)));
   if (W == 8) CBG_CUDA_OK(cudaFuncSetAttribute(x2h_k_mma2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, x2hk_mma2_smem(8)));
   return 0;
 }
@@ -1811,6 +1829,7 @@ int cbg_edge_init(void) {
     else if (e[0] >= '0' && e[0] <= '5' && e[1] == 0) g_edge_impl = e[0] - '0';
   }
   if (const char* e = getenv("CBG_H2X_IMPL")) g_h2x_impl = (e[0] == '0') ? 0 : 1;
+  if (const char* e = getenv("CBG_H2X_PAIRS")) g_h2x_pairs = (atoi(e) == 5) ? 5 : 4;
   if (const char* e = getenv("CBG_H2X_WARPS")) {
     const int w = atoi(e);
     if (w == 8 || w == 12 || w == 16) g_h2x_warps = w;
@@ -1864,10 +1883,12 @@ int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
   if (g_h2x_impl == 1) {
-    constexpr int kPairs = 4;
-    const int need = (a.n_nodes + kPairs - 1) / kPairs;
+    const int kp = g_h2x_pairs;
+    const int need = (a.n_nodes + kp - 1) / kp;
+    const int grid = need < g_num_sms ? need : g_num_sms;
     CBG_PROF_BEGIN(CBG_K_H2X, st);
-    h2x_pair_kernel<kPairs><<<need < g_num_sms ? need : g_num_sms, kPairs * 64, h2x_pair_smem(kPairs), st>>>(a);
+    if (kp == 5) h2x_pair_kernel<5><<<grid, 5 * 64, h2x_pair_smem(5), st>>>(a);
+    else h2x_pair_kernel<4><<<grid, 4 * 64, h2x_pair_smem(4), st>>>(a);
     CBG_LAUNCHED(CBG_K_H2X, st);
     return 0;
   }
