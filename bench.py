@@ -316,8 +316,9 @@ def run_b200(args):
         roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                     'frac': achieved / peaks['hbm_gbs'], 'peak_source': f'{peak_kind} copy bandwidth (MEASURED_PEAKS.json)',
                     'traffic': traffic, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': dom_ms,
-                    'note': 'per-edge k/v tensors are never materialised; the kernel streams node planes + the R-cache '
-                            'and is co-limited by fp32 issue rate (see fp32)',
+                    'note': 'per-edge k/v tensors are never materialised; the kernel streams node planes + the R-cache; bytes are '
+                            'counted for the rows a launch really processes (receptive-field pruning); the loaded unit is the '
+                            'L1/shared data pipe, not DRAM (DESIGN.md section 5)',
                     'rows_per_launch': rows,
                     'fp32': {'achieved_tflops': flops_node * rows / (dom_ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
                              'frac': flops_node * rows / (dom_ms * 1e-3) / 1e12 / fp32_peak,
