@@ -10,6 +10,7 @@ import os
 from .build import LIB_PATH
 
 _lib = None
+DEFAULT_EDGE_IMPL = 4      # library default of cbg_set_edge_impl (csrc/edge.cu: g_edge_impl)
 
 
 class SamplePlan(C.Structure):
@@ -49,6 +50,7 @@ SIGNATURES = {
     'cbg_last_error': (C.c_char_p, []),
     'cbg_launch_count': (_I64, []),
     'cbg_set_edge_impl': (_I32, [_I32, _I32]),
+    'cbg_selftest_umma_f16': (_I32, [_P, _P, _P, _I32, _P]),
     'cbg_set_option': (_I32, [C.c_char_p, _I32]),
     'cbg_profile_num_families': (_I32, []),
     'cbg_profile_family_name': (C.c_char_p, [_I32]),

@@ -334,6 +334,10 @@ const char* cbg_last_error(void) { return g_err; }
 int64_t cbg_launch_count(void) { return g_cbg_launches; }
 
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps) { return cbg_edge_set_impl(impl, warps); }
+int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_from_smem, void* stream) {
+  if (!a || !b || !d) { cbg_set_error("cbg_selftest_umma_f16: null argument"); return 1; }
+  return cbg_launch_umma_selftest(a, b, d, a_from_smem, (cudaStream_t)stream);
+}
 int32_t cbg_set_option(const char* key, int32_t value) {
   if (key && strcmp(key, "static_fast") == 0) { g_static_fast = value ? 1 : 0; return 0; }
   if (key && strcmp(key, "dyn_sched") == 0) { g_dyn_sched = value ? 1 : 0; return 0; }

@@ -75,6 +75,10 @@ struct EdgeArgs {
 int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, const int* snbr, int n_nodes,
                       float* rcache, cudaStream_t st);
 int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st);
+// x2h_tc.cu: both X2H kernels on tcgen05 (A operands in TMEM, f16 hi/lo split); edge order of w = neighbour-table order
+int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st);
+// hardware self-test of the tcgen05 operand conventions (tests): d[128][128] = a[128][32] * b[128][32]^T, f16 inputs
+int cbg_launch_umma_selftest(const void* a, const void* b, float* d, int a_from_smem, cudaStream_t st);
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st);
 int cbg_edge_init(void);  // sets max-dynamic-smem attributes once
 int cbg_edge_set_impl(int impl, int warps);  // X2H implementation switch (cbg_set_edge_impl)

@@ -64,7 +64,14 @@
   X(H2X_V_LN, 256)                                                                       \
   X(H2X_V_W1, 16 * 128)      /* xv_func.net.3.weight [head][f_in] */                     \
   X(H2X_V_B1, 32)            /* xv_func.net.3.bias[16], zero padded */                   \
-  X(H2X_RBF, 32)
+  X(H2X_RBF, 32)                                                                         \
+  /* tcgen05 X2H kernels (x2h_tc.cu): f16 (hi | lo) operand images in the UMMA canonical K-major layout.        \
+     TCW1 = 64 * W1 [128 n][128 k]; TCWG = [128 n][96 k] with k < 80: 16 * Wrf[t][m] at k = 20 t + m,           \
+     k = 80 + t: 16 * c[t], k >= 84: zero (the kernel writes the tile's Pi rows there).  Sizes in floats. */    \
+  X(X2H_K_TCW1, 2 * 128 * 128 / 2)                                                       \
+  X(X2H_K_TCWG, 2 * 128 * 96 / 2)                                                        \
+  X(X2H_V_TCW1, 2 * 128 * 128 / 2)                                                       \
+  X(X2H_V_TCWG, 2 * 128 * 96 / 2)
 
 // ---- global (per-denoiser) fields -------------------------------------------------------
 #define CBG_GLOBAL_FIELDS(X)                                                             \

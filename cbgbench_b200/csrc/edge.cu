@@ -1826,7 +1826,7 @@ int cbg_edge_init(void) {
   }
   if (const char* e = getenv("CBG_EDGE_IMPL")) {
     if (strcmp(e, "simt") == 0) g_edge_impl = 0;
-    else if (e[0] >= '0' && e[0] <= '5' && e[1] == 0) g_edge_impl = e[0] - '0';
+    else if (e[0] >= '0' && e[0] <= '6' && e[1] == 0) g_edge_impl = e[0] - '0';
   }
   if (const char* e = getenv("CBG_H2X_IMPL")) g_h2x_impl = (e[0] == '0') ? 0 : 1;
   if (const char* e = getenv("CBG_H2X_PAIRS")) g_h2x_pairs = (atoi(e) == 5) ? 5 : 4;
@@ -1865,6 +1865,7 @@ int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, con
 int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
+  if (g_edge_impl == 6) return cbg_launch_x2h_tc(a, st);       // tcgen05 kernels (x2h_tc.cu)
   if (g_edge_impl >= 1) {
     switch (g_edge_mma_warps) {
       case 12: return launch_x2h_mma<12, 12>(a, st, g_edge_impl);
@@ -1902,7 +1903,7 @@ int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
 // testing / tuning hook (include/cbg_b200.h): pick the X2H edge-kernel implementation and its warps per CTA
 int cbg_edge_set_impl(int impl, int warps) {
   if (int rc = cbg_edge_init()) return rc;
-  if (impl < 0 || impl > 5) { cbg_set_error("edge impl must be 0 (simt), 1 (mma), 2 (mma k + simt v), 3 (simt k + mma v), 4 (mma2 k + simt v) or 5 (mma2 k + mma v)"); return 1; }
+  if (impl < 0 || impl > 6) { cbg_set_error("edge impl must be 0 (simt), 1 (mma), 2 (mma k + simt v), 3 (simt k + mma v), 4 (mma2 k + simt v), 5 (mma2 k + mma v) or 6 (tcgen05)"); return 1; }
   if (warps != 0 && warps != 8 && warps != 12 && warps != 16) { cbg_set_error("warps per CTA must be 8, 12 or 16"); return 1; }
   g_edge_impl = impl;
   if (warps) { if (impl) g_edge_mma_warps = warps; else g_edge_warps = warps; }

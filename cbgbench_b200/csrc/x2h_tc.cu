@@ -1,0 +1,565 @@
+// X2H attention on the 5th-generation tensor cores: one CTA tile = 4 destination nodes x 32 in-edges = 128 edge rows.
+//
+// Reference semantics: repo/modules/attention/x2h_attention.py:43-97 (per edge e = (j -> i):
+//   kv = [onehot(type) | onehot(type) (x) g(d) | h_i | h_j], k = MLP_k(kv), v = MLP_v(kv) * e_w,
+//   alpha = softmax_j(<q_i, k_ij>/sqrt(8)) per head, h_i += sum_j alpha_ij v_ij).
+//
+// Both edge MLPs are 340 -> 128 -> LayerNorm -> ReLU -> 128.  Per 128-row tile the kernel runs two GEMMs on tcgen05:
+//   MMA1  pre[128 x 128] = G[128 x 96] * Wg[96 x 128]      G = [onehot(t) (x) g(d) | onehot(t) | onehot(node slot)]
+//                                                           Wg = [Wrf[t] ; c[t] ; Pi rows of the tile's 4 nodes]
+//         (the type-dependent RBF mat-vec, the type bias and the destination-node plane Pi in one K = 96 product;
+//          the source plane Pj[j] is added by the SIMT stage from rows staged in shared memory)
+//   MMA2  out[128 x 128] = relu(LN(pre + Pj)) * W1^T
+// fp32 accuracy comes from the split x = hi + lo into two f16 values (scaled by powers of two so lo stays normal)
+// and the three products hi*hi + hi*lo + lo*hi accumulated in fp32 in TMEM (cbg_tc.cuh): same error class as 3xTF32
+// at twice the tensor-core rate and half the operand bytes.
+//
+// A operands (G and the activations) live in TENSOR MEMORY (tcgen05.mma with A from TMEM: lane = edge row), written
+// by tcgen05.st from the warps that produce them; B operands (weight images, pre-split and pre-laid-out by the host
+// packer) stay resident in shared memory for the whole persistent CTA.  Nothing of size [E, 128] touches HBM and no
+// R-cache is needed: the only per-edge gather is the 512-byte Pj row (cp.async, L2 resident).
+//
+// Warp roles (16 warps x 128 registers):
+//   warps 0-7   S1        thread = (edge row, column half): TMEM(pre) + Pj -> LayerNorm (mean-free: the packer centres
+//                         the first Linear over the feature axis) -> ReLU -> (hi, lo) f16 -> TMEM (in place)
+//   warps 8-11  PROD/EPI  thread = edge row.  PROD(tile t+1): neighbour / coordinates -> d, type, g(d) -> G (TMEM),
+//                         Pi columns of Wg (smem), cp.async of the node's 32 Pj rows into a 6-chunk ring;
+//                         EPI(tile t-1): TMEM(out) -> k: <q_i, k>, softmax over the warp's 32 edges, w = alpha * e_w
+//                                                     v: (v + b1v) * w, sum over the warp's 32 edges, h_i += .
+//   warp 12     MMA       one lane issues every tcgen05.mma / commit
+// Pipelining: TMEM holds two pre/activation buffers and two 64-column output halves, so MMA1 of tile t+1 and MMA2 of
+// tile t-1 run while S1 works on tile t and EPI on tile t-1.
+#include <math.h>
+#include "cbg_kernels.cuh"
+#include "cbg_tc.cuh"
+
+using namespace cbg_tc;
+
+namespace {
+
+// ---- blob fields ------------------------------------------------------------------------------------------------
+constexpr long long kOffKW1 = cbg_layout::layer_offset(CBG_LF_X2H_K_TCW1);
+constexpr long long kOffKWg = cbg_layout::layer_offset(CBG_LF_X2H_K_TCWG);
+constexpr long long kOffVW1 = cbg_layout::layer_offset(CBG_LF_X2H_V_TCW1);
+constexpr long long kOffVWg = cbg_layout::layer_offset(CBG_LF_X2H_V_TCWG);
+constexpr long long kOffKLn = cbg_layout::layer_offset(CBG_LF_X2H_K_LN);
+constexpr long long kOffVLn = cbg_layout::layer_offset(CBG_LF_X2H_V_LN);
+constexpr long long kOffVB1 = cbg_layout::layer_offset(CBG_LF_X2H_V_B1);
+constexpr long long kOffRbf = cbg_layout::layer_offset(CBG_LF_X2H_K_RBF);
+
+// ---- scales (exact powers of two; must match modules.py: tc_f16_image) ----------------------------------------
+constexpr float kScaleG = 1024.f;        // g(d) and the type one-hot in G
+// Wrf, c in Wg are scaled by 16 (packer)                       -> pre accumulates at 2^14
+constexpr float kInvPre = 1.f / 16384.f;
+constexpr uint32_t kHalfTypeOne = 0x6400u;   // f16 1024
+constexpr uint32_t kHalfNodeOne = 0x7400u;   // f16 16384: node one-hot x unscaled Pi = Pi * 2^14
+constexpr float kScaleA = 64.f;          // activations
+constexpr float kInvOut = 1.f / 4096.f;  // W1 image is scaled by 64 -> out accumulates at 2^12
+
+// ---- shapes -----------------------------------------------------------------------------------------------------
+constexpr int KG = 96;                   // K of MMA1 (84 used + 8 node one-hot columns (2 tile parities x 4) + 4 zero)
+constexpr int KG_LO = 80;                // the lo part of G is non-zero only in the RBF columns
+constexpr int NCH = 6;                   // Pj ring: chunks of 32 rows
+constexpr uint32_t PJ_ROW = 528;         // padded row stride: 16-byte row-per-lane reads are bank-conflict free
+constexpr uint32_t PJ_CHUNK = 32 * PJ_ROW;
+constexpr uint32_t W1_IMG = 128 * 128 * 2;            // one (hi | lo) image, bytes
+constexpr uint32_t WG_IMG = 128 * KG * 2;
+constexpr uint32_t W1_SBO = (128 / 8) * 128, WG_SBO = (KG / 8) * 128, LBO = 128;
+constexpr uint32_t SM_W1 = 0;                         // hi | lo
+constexpr uint32_t SM_WG = SM_W1 + 2 * W1_IMG;
+constexpr uint32_t SM_PJ = SM_WG + 2 * WG_IMG;
+constexpr uint32_t SM_LN = SM_PJ + NCH * PJ_CHUNK;    // gamma * 64 [128] | beta * 64 [128]
+constexpr uint32_t SM_B1 = SM_LN + 1024;              // b1v [128]
+constexpr uint32_t SM_XCH = SM_B1 + 512;              // sum-of-squares exchange between the two half-row S1 warps
+constexpr uint32_t SM_BAR = SM_XCH + 2048;              // [tile parity][half][row]
+constexpr int NBAR = 11 + 2 * NCH;
+constexpr uint32_t SM_TOTAL = SM_BAR + 8 * NBAR + 16;
+static_assert(SM_TOTAL <= 232448, "shared memory budget");
+enum { B_WFULL = 0, B_GREADY, B_GFREE, B_ACC1 /*2*/ = 3, B_AREADY /*2*/ = 5, B_ACC2 /*2*/ = 7, B_ACC2FREE /*2*/ = 9,
+       B_PJFULL = 11, B_PJFREE = 11 + NCH };
+// TMEM columns
+constexpr uint32_t TM_BUF = 0;           // 2 x 128: pre (fp32) -> a_hi (64 cols) | a_lo (64 cols)
+constexpr uint32_t TM_OUT = 256;         // 2 x 64 : output halves (features 0-63, 64-127)
+constexpr uint32_t TM_GHI = 384;         // 48 columns = 96 f16
+constexpr uint32_t TM_GLO = 432;         // 40 columns = 80 f16
+constexpr uint32_t TM_COLS = 512;
+constexpr uint32_t IDESC128 = idesc_f16(128), IDESC64 = idesc_f16(64);
+
+__device__ __forceinline__ int list_len(const EdgeArgs& p) {
+  int n = p.n_nodes;
+  if (p.n_nodes_dev) { const int nd = *p.n_nodes_dev; n = nd < n ? nd : n; }
+  return n;
+}
+__device__ __forceinline__ int node_of(const EdgeArgs& p, int n, int n_list) {
+  const int nc = n < n_list ? n : n_list - 1;
+  return p.node_idx ? p.node_idx[nc] : nc;
+}
+
+// =================================================================================================================
+// per-warp state of the producer half of the EPI/PROD warps: everything tile t+1 needs, loaded one stage ahead
+struct TileIn {
+  int i;          // destination node of this warp's slot
+  int jn;         // neighbour of this lane (-1: padded slot)
+};
+
+template <bool IS_V>
+__global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int n_list = list_len(p);
+  const int n_tiles = (n_list + 3) >> 2;
+  if ((int)blockIdx.x >= n_tiles) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bars = sbase + SM_BAR;
+  auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * NBAR);
+  const float* L = p.layer;
+  const int n_my = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;     // tiles of this CTA: blockIdx.x + k * gridDim.x
+
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
+  if (tid == 32) {
+    mbar_init(bar(B_WFULL), 1);
+    mbar_init(bar(B_GREADY), 4);
+    mbar_init(bar(B_GFREE), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar(B_ACC1 + b), 1);
+      mbar_init(bar(B_AREADY + b), 8);
+      mbar_init(bar(B_ACC2 + b), 1);
+      mbar_init(bar(B_ACC2FREE + b), 4);
+    }
+    for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 32); mbar_init(bar(B_PJFREE + c), 2); }
+    fence_mbar_init();
+  }
+  {   // LayerNorm affine (pre-multiplied by the activation scale) and the value bias
+    float* s_ln = reinterpret_cast<float*>(smem + SM_LN);
+    float* s_b1 = reinterpret_cast<float*>(smem + SM_B1);
+    const float* ln = L + (IS_V ? kOffVLn : kOffKLn);
+    if (tid < 256) s_ln[tid] = ln[tid] * kScaleA;
+    else if (tid < 384) s_b1[tid - 256] = IS_V ? L[kOffVB1 + tid - 256] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 8) {
+    // ===================================== S1: LayerNorm + ReLU + split =========================================
+    // thread = (edge row, column half).  The first Linear is centred over the feature axis by the packer (W0 and
+    // b0 minus their column means), so pre has zero mean and LayerNorm needs only the sum of squares.
+    const int wq = warp & 3, hf = warp >> 2;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
+    const float* s_ln = reinterpret_cast<const float*>(smem + SM_LN) + 64 * hf;
+    float* s_x = reinterpret_cast<float*>(smem + SM_XCH);
+    const int row = 32 * wq + lane;
+    for (int k = 0; k < n_my; ++k) {
+      const int b = k & 1;
+      const int idx = 4 * k + wq, c = idx % NCH;
+      mbar_wait(bar(B_PJFULL + c), (uint32_t)((idx / NCH) & 1));
+      mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));
+      tc_fence_after();
+      const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
+      float v[64];
+      {
+        uint32_t r[2][32];
+        tmem_ld32_nowait(t_buf + 64u * hf, r[0]);
+        tmem_ld32_nowait(t_buf + 64u * hf + 32u, r[1]);
+        tmem_wait_ld();
+        const uint8_t* prow = smem + SM_PJ + (uint32_t)c * PJ_CHUNK + (uint32_t)lane * PJ_ROW + 256u * hf;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 pj = *reinterpret_cast<const float4*>(prow + 16 * j);
+          const uint32_t* rv = &r[j >> 3][4 * (j & 7)];
+          const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(rv[0]), __uint_as_float(rv[1])),
+                                       make_float2(kInvPre, kInvPre), make_float2(pj.x, pj.y));
+          const float2 a1 = __ffma2_rn(make_float2(__uint_as_float(rv[2]), __uint_as_float(rv[3])),
+                                       make_float2(kInvPre, kInvPre), make_float2(pj.z, pj.w));
+          v[4 * j] = a0.x; v[4 * j + 1] = a0.y; v[4 * j + 2] = a1.x; v[4 * j + 3] = a1.y;
+        }
+      }
+      float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) q2 = __ffma2_rn(make_float2(v[2 * j], v[2 * j + 1]), make_float2(v[2 * j], v[2 * j + 1]), q2);
+      const float qs = q2.x + q2.y;
+      s_x[256 * b + 128 * hf + row] = qs;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_PJFREE + c));          // this warp is done with the ring chunk
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");   // the two half-row warps of this row quarter
+      const float qo = s_x[256 * b + 128 * (hf ^ 1) + row];
+      const float rstd = 1.f / sqrtf((qs + qo) * (1.f / 128.f) + 1e-5f);
+      const float2 rr = make_float2(rstd, rstd);
+      // relu((pre * rstd) * gamma + beta) * 64 -> (hi, lo) f16 into the buffer's columns: hi 0-63, lo 64-127
+      // (the partner thread has read its accumulator columns before the barrier above)
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 ga = *reinterpret_cast<const float4*>(s_ln + 32 * ch + 4 * j);
+          const float4 be = *reinterpret_cast<const float4*>(s_ln + 128 + 32 * ch + 4 * j);
+          const int e = 32 * ch + 4 * j;
+          float2 y0 = __fmul2_rn(make_float2(v[e], v[e + 1]), rr);
+          float2 y1 = __fmul2_rn(make_float2(v[e + 2], v[e + 3]), rr);
+          y0 = __ffma2_rn(y0, make_float2(ga.x, ga.y), make_float2(be.x, be.y));
+          y1 = __ffma2_rn(y1, make_float2(ga.z, ga.w), make_float2(be.z, be.w));
+          split_pair_relu(y0.x, y0.y, hi[2 * j], lo[2 * j]);
+          split_pair_relu(y1.x, y1.y, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        tmem_st16(t_buf + 32u * hf + 16u * ch, hi);
+        tmem_st16(t_buf + 64u + 32u * hf + 16u * ch, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_AREADY + b));
+    }
+  } else if (warp < 12) {
+    // ===================================== PROD (tile k + 1) then EPI (tile k - 1) ===============================
+    const int wq = warp - 8;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
+    const float* s_b1 = reinterpret_cast<const float*>(smem + SM_B1);
+    const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
+    const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
+    const float* rbf = L + kOffRbf;
+    const float coeff = __ldg(rbf + 20);
+
+    auto load_tile = [&](int kk, TileIn& t) {
+      const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + wq;
+      t.i = node_of(p, n, n_list);
+      t.jn = p.nbr[(size_t)t.i * CBG_KMAX + lane];
+    };
+    // ---- producer half: everything tile kk needs before its first MMA
+    auto produce = [&](int kk, const TileIn& t) {
+      const int i = t.i;
+      const int jj = t.jn >= 0 ? t.jn : i;
+      const float4 xi = p.x4[i];
+      const float4 xj = p.x4[jj];
+      const float4 pi4 = ldg4(pi_plane + (size_t)i * CBG_H + 4 * lane);
+      {   // Pj rows of the node's 32 in-edges -> ring chunk (warp = row-coalesced 512-byte copies)
+        const int idx = 4 * kk + wq, c = idx % NCH;
+        if (idx >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)(((idx / NCH) - 1) & 1));
+        const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int jr = __shfl_sync(CBG_FULL, jj, r);
+          cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
+        }
+        cp_async_arrive(bar(B_PJFULL + c));
+      }
+      // geometry, edge type, Gaussian smearing (x2h_attention.py:46-52, unitransformer.py:88-99)
+      const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
+      const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+      const int fi = node_flags(xi), fj = node_flags(xj);
+      const int t_e = ((fj & 1) ? 0 : 2) + ((fi & 1) ? 0 : 1);
+      uint32_t ghi[10], glo[10];
+#pragma unroll
+      for (int mp = 0; mp < 10; ++mp) {
+        const float u0 = d - __ldg(rbf + 2 * mp), u1 = d - __ldg(rbf + 2 * mp + 1);
+        split_pair(expf(coeff * u0 * u0) * kScaleG, expf(coeff * u1 * u1) * kScaleG, ghi[mp], glo[mp]);
+      }
+      // centred Pi row: the planes are centred by construction (packer); nothing to do here
+      if (kk > 0) { mbar_wait(bar(B_GFREE), (uint32_t)((kk - 1) & 1)); tc_fence_after(); }
+      else mbar_wait(bar(B_WFULL), 0u);      // the Pi columns go into the Wg images: the bulk copy must have landed
+      {   // Pi row of this node -> K column (84 + slot + 4 * parity) of the Wg images (hi, lo), features 4*lane..+3
+        const int kcol = 84 + wq + 4 * (kk & 1);
+        const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
+        const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int nn = 4 * lane + q;
+          const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
+          const __half hh = __float2half_rn(pv[q]);
+          const __half hl = __float2half_rn(pv[q] - __half2float(hh));
+          *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
+          *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
+        }
+        fence_proxy_async();
+      }
+      // G row -> TMEM: hi 96 f16 (48 columns), lo 80 f16 (40 columns)
+#pragma unroll
+      for (int blk = 0; blk < 3; ++blk) {          // 16 columns = 32 f16 per store
+        uint32_t w16[16];
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          const int col = 16 * blk + cc;             // f16 pair (2*col, 2*col + 1)
+          uint32_t val = 0u;
+          if (col < 40) {
+            val = (t_e == col / 10) ? ghi[col % 10] : 0u;
+          } else if (col == 40) {
+            val = (t_e == 0) ? kHalfTypeOne : ((t_e == 1) ? (kHalfTypeOne << 16) : 0u);
+          } else if (col == 41) {
+            val = (t_e == 2) ? kHalfTypeOne : ((t_e == 3) ? (kHalfTypeOne << 16) : 0u);
+          } else if (col < 46) {
+            const int kc = 84 + wq + 4 * (kk & 1);
+            val = ((kc >> 1) == col) ? ((kc & 1) ? (kHalfNodeOne << 16) : kHalfNodeOne) : 0u;
+          }
+          w16[cc] = val;
+        }
+        tmem_st16(t_lane + TM_GHI + 16u * blk, w16);
+      }
+#pragma unroll
+      for (int blk = 0; blk < 5; ++blk) {          // 8 columns = 16 f16 per store
+        uint32_t w8[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const int col = 8 * blk + cc;
+          w8[cc] = (t_e == col / 10) ? glo[col % 10] : 0u;
+        }
+        tmem_st8(t_lane + TM_GLO + 8u * blk, w8);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_GREADY));
+    };
+    // ---- epilogue half
+    auto epilogue = [&](int kk, const TileIn& t) {
+      const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + wq;
+      const bool live = n < n_list;
+      const int i = t.i;
+      const size_t eoff = (size_t)i * CBG_KMAX + lane;
+      if constexpr (!IS_V) {
+        const bool valid = t.jn >= 0;
+        const float ew = p.ew[eoff];
+        const float* qi = p.q + (size_t)i * CBG_H;
+        float lg[CBG_HEADS];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar(B_ACC2 + h), (uint32_t)(kk & 1));
+          tc_fence_after();
+          uint32_t r[2][32];
+          tmem_ld32_nowait(t_lane + TM_OUT + 64u * h, r[0]);
+          tmem_ld32_nowait(t_lane + TM_OUT + 64u * h + 32u, r[1]);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_ACC2FREE + h));
+#pragma unroll
+          for (int hh = 0; hh < 8; ++hh) {
+            const float4 q0 = ldg4(qi + 64 * h + 8 * hh), q1 = ldg4(qi + 64 * h + 8 * hh + 4);
+            const uint32_t* rv = &r[hh >> 2][8 * (hh & 3)];
+            float2 tt = __fmul2_rn(make_float2(__uint_as_float(rv[0]), __uint_as_float(rv[1])), make_float2(q0.x, q0.y));
+            tt = __ffma2_rn(make_float2(__uint_as_float(rv[2]), __uint_as_float(rv[3])), make_float2(q0.z, q0.w), tt);
+            tt = __ffma2_rn(make_float2(__uint_as_float(rv[4]), __uint_as_float(rv[5])), make_float2(q1.x, q1.y), tt);
+            tt = __ffma2_rn(make_float2(__uint_as_float(rv[6]), __uint_as_float(rv[7])), make_float2(q1.z, q1.w), tt);
+            lg[8 * h + hh] = valid ? (tt.x + tt.y) * kInvOut : -INFINITY;
+          }
+        }
+        // softmax over the warp's 32 edges, per head; w = alpha * e_w
+        float wv[CBG_HEADS];
+#pragma unroll
+        for (int hd = 0; hd < CBG_HEADS; ++hd) {
+          float mx = lg[hd];
+#pragma unroll
+          for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, m));
+          const float ex = (mx == -INFINITY) ? 0.f : expf(lg[hd] - mx);
+          const float sum = warp_sum(ex);
+          wv[hd] = (ex / ((sum > 0.f) ? sum : 1.f)) * (valid ? ew : 0.f);
+        }
+        if (live) {
+          float* wo = p.w + eoff * CBG_HEADS;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) st4(wo + 4 * j, make_float4(wv[4 * j], wv[4 * j + 1], wv[4 * j + 2], wv[4 * j + 3]));
+        }
+      } else {
+        float wv[CBG_HEADS];
+        {
+          const float* wi = p.w + eoff * CBG_HEADS;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 tt = ld4(wi + 4 * j);
+            wv[4 * j] = tt.x; wv[4 * j + 1] = tt.y; wv[4 * j + 2] = tt.z; wv[4 * j + 3] = tt.w;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(bar(B_ACC2 + h), (uint32_t)(kk & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int qq = 0; qq < 2; ++qq) {           // 32 columns at a time: features 64h + 32qq + (0..31)
+            uint32_t r[32];
+            tmem_ld32_nowait(t_lane + TM_OUT + 64u * h + 32u * qq, r);
+            tmem_wait_ld();
+            if (qq == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar(B_ACC2FREE + h));
+            }
+            float val[32];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const float4 b1 = *reinterpret_cast<const float4*>(s_b1 + 64 * h + 32 * qq + 4 * c4);
+              const float wh = wv[8 * h + 4 * qq + (c4 >> 1)];
+              val[4 * c4 + 0] = fmaf(__uint_as_float(r[4 * c4 + 0]), kInvOut, b1.x) * wh;
+              val[4 * c4 + 1] = fmaf(__uint_as_float(r[4 * c4 + 1]), kInvOut, b1.y) * wh;
+              val[4 * c4 + 2] = fmaf(__uint_as_float(r[4 * c4 + 2]), kInvOut, b1.z) * wh;
+              val[4 * c4 + 3] = fmaf(__uint_as_float(r[4 * c4 + 3]), kInvOut, b1.w) * wh;
+            }
+            warp_transpose_reduce<32>(val, lane);      // lane l: sum over the 32 edges of feature 64h + 32qq + l
+            if (live) {
+              float* hp = p.h + (size_t)i * CBG_H + 64 * h + 32 * qq + lane;
+              *hp = *hp + val[0];
+            }
+          }
+        }
+      }
+    };
+    TileIn tA{0, -1}, tB, tC{0, -1}, tD{0, -1};      // tiles k-1, k, k+1, k+2 of this CTA
+    load_tile(0, tB);
+    if (n_my > 1) load_tile(1, tC);
+    produce(0, tB);
+#pragma unroll 1
+    for (int k = 0; k < n_my; ++k) {
+      if (k + 1 < n_my) produce(k + 1, tC);
+      if (k + 2 < n_my) load_tile(k + 2, tD);        // consumed one iteration later: the loads' latency is hidden
+      if (k >= 1) epilogue(k - 1, tA);
+      tA = tB; tB = tC; tC = tD;
+    }
+    epilogue(n_my - 1, tA);
+  } else if (warp == 12) {
+    // ===================================== MMA issuer ============================================================
+    if (lane == 0) {
+      mbar_expect_tx(bar(B_WFULL), 2 * W1_IMG + 2 * WG_IMG);
+      bulk_g2s(sbase + SM_W1, L + (IS_V ? kOffVW1 : kOffKW1), 2 * W1_IMG, bar(B_WFULL));
+      bulk_g2s(sbase + SM_WG, L + (IS_V ? kOffVWg : kOffKWg), 2 * WG_IMG, bar(B_WFULL));
+      mbar_wait(bar(B_WFULL), 0u);
+      const uint32_t w1_hi = sbase + SM_W1, w1_lo = w1_hi + W1_IMG;
+      const uint32_t wg_hi = sbase + SM_WG, wg_lo = wg_hi + WG_IMG;
+      auto issue_mma2 = [&](int kk) {
+        const int bb = kk & 1;
+        mbar_wait(bar(B_AREADY + bb), (uint32_t)((kk >> 1) & 1));
+        tc_fence_after();
+        const uint32_t a_hi = tmem + TM_BUF + 128u * (uint32_t)bb, a_lo = a_hi + 64u;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if (kk > 0) { mbar_wait(bar(B_ACC2FREE + h), (uint32_t)((kk - 1) & 1)); tc_fence_after(); }
+          const uint32_t d = tmem + TM_OUT + 64u * (uint32_t)h;
+          const uint32_t bh = w1_hi + (uint32_t)h * 8u * W1_SBO, bl = w1_lo + (uint32_t)h * 8u * W1_SBO;
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks)     // small terms first
+            umma_f16_ts(d, a_lo + 8u * ks, smem_desc(bh + 256u * ks, LBO, W1_SBO), IDESC64, ks > 0 ? 1u : 0u);
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, smem_desc(bl + 256u * ks, LBO, W1_SBO), IDESC64, 1u);
+#pragma unroll 1
+          for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, smem_desc(bh + 256u * ks, LBO, W1_SBO), IDESC64, 1u);
+          umma_commit(bar(B_ACC2 + h));
+        }
+      };
+      for (int k = 0; k < n_my; ++k) {
+        const int b = k & 1;
+        mbar_wait(bar(B_GREADY), (uint32_t)(k & 1));
+        tc_fence_after();
+        const uint32_t d = tmem + TM_BUF + 128u * (uint32_t)b;
+#pragma unroll 1
+        for (int ks = 0; ks < KG_LO / 16; ++ks)
+          umma_f16_ts(d, tmem + TM_GLO + 8u * ks, smem_desc(wg_hi + 256u * ks, LBO, WG_SBO), IDESC128, ks > 0 ? 1u : 0u);
+#pragma unroll 1
+        for (int ks = 0; ks < KG / 16; ++ks) umma_f16_ts(d, tmem + TM_GHI + 8u * ks, smem_desc(wg_lo + 256u * ks, LBO, WG_SBO), IDESC128, 1u);
+#pragma unroll 1
+        for (int ks = 0; ks < KG / 16; ++ks) umma_f16_ts(d, tmem + TM_GHI + 8u * ks, smem_desc(wg_hi + 256u * ks, LBO, WG_SBO), IDESC128, 1u);
+        umma_commit(bar(B_ACC1 + b));
+        umma_commit(bar(B_GFREE));
+        if (k > 0) issue_mma2(k - 1);
+      }
+      issue_mma2(n_my - 1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TM_COLS);
+}
+
+// =================================================================================================================
+// Hardware self-test of the operand conventions the kernel above relies on (A from TMEM with two K-consecutive f16
+// per column, B in the canonical K-major no-swizzle layout, fp32 accumulator read back with tcgen05.ld 32x32b).
+// D[128 x 128] = A[128 x 32] * B[128 x 32]^T, one CTA of 128 threads.  a, b: f16 row-major [128][32]; d: fp32 [128][128].
+__global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __half* a, const __half* b, float* d, int a_from_smem) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t SBO = (32 / 8) * 128;        // K = 32: 4 core matrices per 8-row group
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t sb_b = sbase, sb_a = sbase + 128 * 32 * 2, bar0 = sbase + 2 * 128 * 32 * 2;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 2 * 128 * 32 * 2 + 8);
+  if (warp == 0) tmem_alloc(smem_u32(slot), 256);
+  if (tid == 32) { mbar_init(bar0, 1); fence_mbar_init(); }
+  for (int e = tid; e < 128 * 32; e += 128) {
+    const int r = e >> 5, kk = e & 31;
+    const uint32_t off = (uint32_t)(r >> 3) * SBO + (uint32_t)(kk >> 3) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(kk & 7) * 2u;
+    *reinterpret_cast<__half*>(smem + off) = b[e];
+    *reinterpret_cast<__half*>(smem + 128 * 32 * 2 + off) = a[e];
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  const uint32_t t_lane = tmem + ((uint32_t)(32 * warp) << 16);
+  if (!a_from_smem) {     // row tid of A -> TMEM columns 128..143 (16 columns = 32 f16)
+    uint32_t w16[16];
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(a + (size_t)tid * 32);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) w16[c] = arow[c];
+    tmem_st16(t_lane + 128u, w16);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    for (int ks = 0; ks < 2; ++ks) {
+      if (a_from_smem) umma_f16_ss(tmem, smem_desc(sb_a + 256u * ks, 128, SBO), smem_desc(sb_b + 256u * ks, 128, SBO), idesc_f16(128), ks > 0);
+      else umma_f16_ts(tmem, tmem + 128u + 8u * ks, smem_desc(sb_b + 256u * ks, 128, SBO), idesc_f16(128), ks > 0);
+    }
+    umma_commit(bar0);
+  }
+  mbar_wait(bar0, 0u);
+  tc_fence_after();
+#pragma unroll 1
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[32];
+    tmem_ld32_nowait(t_lane + 32u * q, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) d[(size_t)tid * 128 + 32 * q + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+int g_tc_sms = 0;
+
+int tc_init() {
+  static bool done_dev[CBG_MAX_DEVICES] = {};
+  bool& done = cbg_dev_flag(done_dev);
+  if (done) return 0;
+  int dev = 0;
+  CBG_CUDA_OK(cudaGetDevice(&dev));
+  CBG_CUDA_OK(cudaDeviceGetAttribute(&g_tc_sms, cudaDevAttrMultiProcessorCount, dev));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+  done = true;
+  return 0;
+}
+
+}  // namespace
+
+int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st) {
+  if (a.n_nodes <= 0) return 0;
+  if (int rc = tc_init()) return rc;
+  const int tiles = (a.n_nodes + 3) / 4;
+  const int grid = tiles < g_tc_sms ? tiles : g_tc_sms;
+  CBG_PROF_BEGIN(CBG_K_X2H_K, st);
+  x2h_tc_kernel<false><<<grid, 512, SM_TOTAL, st>>>(a);
+  CBG_LAUNCHED(CBG_K_X2H_K, st);
+  CBG_PROF_BEGIN(CBG_K_X2H_V, st);
+  x2h_tc_kernel<true><<<grid, 512, SM_TOTAL, st>>>(a);
+  CBG_LAUNCHED(CBG_K_X2H_V, st);
+  return 0;
+}
+
+int cbg_launch_umma_selftest(const void* a, const void* b, float* d, int a_from_smem, cudaStream_t st) {
+  const int smem_bytes = 2 * 128 * 32 * 2 + 64;
+  umma_selftest_kernel<<<1, 128, smem_bytes, st>>>((const __half*)a, (const __half*)b, d, a_from_smem);
+  CBG_CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -125,6 +125,28 @@ def tc_weight_plane(w):
     return torch.from_numpy(out.reshape(-1)).to(torch.float64)
 
 
+def tc_f16_image(w):
+    """[128 n][K k] matrix (float64, already scaled by its power of two) -> the (hi | lo) f16 operand images of the
+    tcgen05 X2H kernels (csrc/x2h_tc.cu): w ~= hi + lo, each image in the UMMA canonical K-major / no-swizzle layout
+    for 16-bit types (8-row x 8-element core matrices, 128 B apart along K, K/8 * 128 B between 8-row groups).
+    Returns the raw bits as an int32 tensor (two f16 per word)."""
+    import numpy as np
+    w = np.asarray(w, dtype=np.float64)
+    n, k = w.shape
+    assert n == 128 and k % 16 == 0
+    hi = w.astype(np.float16)
+    lo = (w - hi.astype(np.float64)).astype(np.float16)
+    imgs = [m.reshape(16, 8, k // 8, 8).transpose(0, 2, 1, 3).reshape(-1) for m in (hi, lo)]
+    assert np.isfinite(np.concatenate(imgs).astype(np.float32)).all(), 'f16 overflow in a tensor-core weight image'
+    return torch.from_numpy(np.concatenate(imgs).view(np.int32).copy())
+
+
+# power-of-two scales of the f16 images (must match csrc/x2h_tc.cu)
+TC_SCALE_WG = 16.0
+TC_SCALE_W1 = 64.0
+TC_KG = 96
+
+
 def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
     """Pack a (reference-keyed) state dict into the flat fp32 blob of csrc/cbg_layout.h.
 
@@ -134,6 +156,12 @@ def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
     lay = _lib.blob_layout()
     total = lay['global_floats'] + num_layers * lay['layer_floats']
     blob = torch.zeros(total, dtype=torch.float64)
+    raw = []      # (offset, int32 bit patterns): fields that are not fp32 values (f16 images), written after the cast
+
+    def put_raw(base, field_map, name, bits):
+        off, size = field_map[name]
+        assert bits.dtype == torch.int32 and bits.numel() == size, (name, bits.numel(), size)
+        raw.append((base + off, bits))
 
     def put(base, field_map, name, value):
         off, size = field_map[name]
@@ -184,14 +212,22 @@ def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
                  ('H2X', f'blocks.{l}.h2x_layers.0.', 'xk_func', 'xv_func', 'xq_func')))
         for tag, sub, kname, vname, qname in subs:
             sp = p + sub
-            wrf_k, c_k, wi_k, wj_k = first_layer_split(sd[sp + kname + '.net.0.weight'])
-            wrf_v, c_v, wi_v, wj_v = first_layer_split(sd[sp + vname + '.net.0.weight'])
+            w0k, w0v = _t(sd[sp + kname + '.net.0.weight']), _t(sd[sp + vname + '.net.0.weight'])
+            b0k, b0v = _t(sd[sp + kname + '.net.0.bias']), _t(sd[sp + vname + '.net.0.bias'])
+            if tag == 'X2H':
+                # Centre the first Linear of the X2H edge MLPs over the OUTPUT-feature axis: LayerNorm follows it
+                # directly (common.py:151-171), so pre - mean_f(pre) is all that is ever used, and with
+                # W0 <- W0 - mean_f W0, b0 <- b0 - mean_f b0 every piece (Pi, Pj, Wrf g, c) has zero feature mean by
+                # itself.  Exact; the tcgen05 kernels then need only the sum of squares (the other kernels subtract
+                # a mean that is zero up to rounding).
+                w0k, w0v = w0k - w0k.mean(0, keepdim=True), w0v - w0v.mean(0, keepdim=True)
+                b0k, b0v = b0k - b0k.mean(), b0v - b0v.mean()
+            wrf_k, c_k, wi_k, wj_k = first_layer_split(w0k)
+            wrf_v, c_v, wi_v, wj_v = first_layer_split(w0v)
             wq0_t = _t(sd[sp + qname + '.net.0.weight']).t().contiguous()
             node_wt = torch.cat([wj_k, wj_v, wi_k, wi_v, wq0_t], dim=1)            # [128 k][640 n]
-            node_b = torch.cat([torch.zeros(256, dtype=torch.float64), _t(sd[sp + kname + '.net.0.bias']),
-                                _t(sd[sp + vname + '.net.0.bias']), _t(sd[sp + qname + '.net.0.bias'])])
+            node_b = torch.cat([torch.zeros(256, dtype=torch.float64), b0k, b0v, _t(sd[sp + qname + '.net.0.bias'])])
             put(base, lf, f'{tag}_NODE_WT', node_wt)
-            w0k, w0v = _t(sd[sp + kname + '.net.0.weight']), _t(sd[sp + vname + '.net.0.weight'])
             tc = [w0k[:, 212:340], w0v[:, 212:340], w0k[:, 84:212], w0v[:, 84:212],
                   _t(sd[sp + qname + '.net.0.weight']), _t(sd[sp + qname + '.net.3.weight']) * inv_sqrt_dh]
             put(base, lf, f'{tag}_NODE_TC', torch.cat([tc_weight_plane(m.to(torch.float32)) for m in tc]))
@@ -212,9 +248,20 @@ def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
             if tag == 'X2H':
                 put(base, lf, 'X2H_K_RBF', rbf)
                 put(base, lf, 'X2H_V_RBF', rbf)
+                for kv, w0, w1 in (('K', w0k, _t(sd[sp + kname + '.net.3.weight'])),
+                                   ('V', w0v, _t(sd[sp + vname + '.net.3.weight']))):
+                    wg = torch.zeros(HIDDEN, TC_KG, dtype=torch.float64)     # [f][k]: k = 20 t + m | 80 + t | Pi columns
+                    wg[:, 0:80] = w0[:, 4:84]
+                    wg[:, 80:84] = w0[:, 0:4]
+                    put_raw(base, lf, f'X2H_{kv}_TCWG', tc_f16_image((wg * TC_SCALE_WG).numpy()))
+                    put_raw(base, lf, f'X2H_{kv}_TCW1', tc_f16_image((w1 * TC_SCALE_W1).numpy()))
             else:
                 put(base, lf, 'H2X_RBF', rbf)
-    return blob.to(torch.float32)
+    blob32 = blob.to(torch.float32)
+    bits = blob32.view(torch.int32)
+    for off, b in raw:
+        bits[off: off + b.numel()] = b
+    return blob32
 
 
 class _Workspace:

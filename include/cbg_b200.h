@@ -60,6 +60,10 @@ int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family)
  * warps = CTA size in warps (8, 12, 16; 0 keeps the current value).  Process-wide; also env CBG_EDGE_IMPL,
  * CBG_EDGE_MMA_WARPS, CBG_EDGE_WARPS.  Needs a current CUDA device. */
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);
+/* Hardware self-test of the tcgen05 operand conventions the X2H kernels rely on (tests only):
+ * d[128][128] (fp32) = a[128][32] * b[128][32]^T with f16 row-major device inputs; a_from_smem = 0 feeds A from
+ * tensor memory (tcgen05.st, two K-consecutive f16 per column), 1 from shared memory (canonical K-major layout). */
+int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_from_smem, void* stream);
 /* Other process-wide switches (testing): "static_fast" = 1 (default; env CBG_STATIC_FAST) lets the X2H kernels skip the
  * coordinate gathers / RBF set-up of nodes whose 32 in-edges are all served from the R-cache (bit-identical results);
  * "dyn_sched" = 1 (default; env CBG_DYN_SCHED): warps of the X2H kernels draw their next node from a work counter instead

@@ -64,10 +64,15 @@ def test_packing_places_reference_weights():
     lay = _lib.blob_layout()
     assert blob.numel() == lay['global_floats'] + 9 * lay['layer_floats']
     base = lay['global_floats'] + 4 * lay['layer_floats']
-    w0 = den['blocks.4.x2h_layers.0.hk_func.net.0.weight']
+    # the first Linear of the X2H edge MLPs is packed CENTRED over its output-feature axis (exact: LayerNorm follows it)
+    w0_raw = den['blocks.4.x2h_layers.0.hk_func.net.0.weight']
+    w0 = (w0_raw.double() - w0_raw.double().mean(0, keepdim=True)).float()
+    b0_raw = den['blocks.4.x2h_layers.0.hk_func.net.0.bias']
+    b0 = (b0_raw.double() - b0_raw.double().mean()).float()
     o, n = lay['layer']['X2H_K_WRF']
     wrf = blob[base + o: base + o + n].view(4, 20, 128)
     assert torch.equal(wrf[2, 7], w0[:, 4 + 2 * 20 + 7])
+    assert float(wrf[2, 7].double().sum().abs()) < 1e-5
     o, n = lay['layer']['X2H_K_C']
     assert torch.equal(blob[base + o: base + o + n].view(4, 128)[3], w0[:, 3])
     o, n = lay['layer']['X2H_NODE_WT']
@@ -76,7 +81,25 @@ def test_packing_places_reference_weights():
     assert torch.equal(wt[5, 256:384], w0[:, 84 + 5])             # Pi_k plane = h_dst block
     o, n = lay['layer']['X2H_NODE_B']
     nb = blob[base + o: base + o + n]
-    assert torch.equal(nb[:256], torch.zeros(256)) and torch.equal(nb[256:384], den['blocks.4.x2h_layers.0.hk_func.net.0.bias'])
+    assert torch.equal(nb[:256], torch.zeros(256)) and torch.equal(nb[256:384], b0)
+    # f16 (hi | lo) images of the tcgen05 X2H kernels: hi + lo reproduces the scaled fp64 weight to ~2^-22
+    import numpy as np
+    o, n = lay['layer']['X2H_K_TCWG']
+    img = blob.view(torch.int32)[base + o: base + o + n].numpy().view(np.float16)
+    unpack = lambda a, k: a.reshape(16, k // 8, 8, 8).transpose(0, 2, 1, 3).reshape(128, k).astype(np.float64)
+    wg = unpack(img[:128 * 96], 96) + unpack(img[128 * 96:], 96)
+    w64 = w0_raw.double() - w0_raw.double().mean(0, keepdim=True)
+    assert np.abs(wg[:, 20 * 2 + 7] - 16.0 * w64[:, 4 + 2 * 20 + 7].numpy()).max() < 16.0 * 3e-7 * float(w64.abs().max())
+    assert np.abs(wg[:, 80 + 3] - 16.0 * w64[:, 3].numpy()).max() < 16.0 * 3e-7 * float(w64.abs().max())
+    assert (wg[:, 84:] == 0).all()                                   # the kernel writes the tile's Pi rows here
+    o, n = lay['layer']['X2H_V_TCW1']
+    img = blob.view(torch.int32)[base + o: base + o + n].numpy().view(np.float16)
+    w1 = unpack(img[:128 * 128], 128) + unpack(img[128 * 128:], 128)
+    w1_ref = 64.0 * den['blocks.4.x2h_layers.0.hv_func.net.3.weight'].double().numpy()
+    assert np.abs(w1 - w1_ref).max() < 3e-7 * np.abs(w1_ref).max()
+    # the H2X sub-layer is packed as is
+    assert torch.equal(blob[base + lay['layer']['H2X_K_C'][0]: base + lay['layer']['H2X_K_C'][0] + 512].view(4, 128)[1],
+                       den['blocks.4.h2x_layers.0.xk_func.net.0.weight'][:, 1])
     o, n = lay['layer']['H2X_V_W1']
     assert torch.equal(blob[base + o: base + o + n].view(16, 128), den['blocks.4.h2x_layers.0.xv_func.net.3.weight'])
     o, n = lay['global']['GATE_RBF']
