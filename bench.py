@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference', 'reference-gpu'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--e2e-steps', type=int, default=T_STEPS, help='denoise steps of the end-to-end sample() call')
     ap.add_argument('--no-e2e', action='store_true')
@@ -130,78 +130,95 @@ def workload_batch(name, rank, n_graphs=None):
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_steps(workload, n_graphs, steps, warmup, threads):
-    """Time `steps` denoise steps of the oracle port (torch CPU, fp32, as-written reference
-    formulation) on n_graphs graphs of the workload shape.  Returns seconds per step."""
-    import torch
-    from cbgbench_b200 import synthetic
-    from cbgbench_b200.targetdiff import TargetDiffB200
-    from oracle import diffusion as OD
-    torch.set_num_threads(threads)
-    torch.set_grad_enabled(False)
-    batch, enc = workload_batch(workload, 0, n_graphs)
-    model = TargetDiffB200(synthetic.targetdiff_config(num_steps=T_STEPS, **enc))
-    sd = synthetic.seeded_state_dict(model, seed=0)
-    import torch.nn.functional as F
-    x = batch['ligand_pos'].float()
-    c = F.one_hot(batch['ligand_atom_type'], 13).float()
-    gen = batch.get('ligand_gen_flag', batch['ligand_lig_flag'])
-    kw = dict(k=32, cutoff_mode=enc.get('cutoff_mode', 'knn'), r_max=enc.get('r_max', 10.0))
-    times = []
-    t_idx = T_STEPS - 1
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        x0, logits = OD.denoise_once(sd, batch, x, c, **kw)
-        x = OD.pos_reverse_step(sd, x0, x, t_idx, gen, torch.randn_like(x))
-        c, _ = OD.type_reverse_step(sd, logits, c, t_idx, gen, torch.rand_like(c), 13)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-        t_idx -= 1
-    return sum(times) / len(times)
+# Reference legs.  What is timed is the UNMODIFIED reference: TargetDiff.sample(batch) (repo/models/diffusion/
+# targetdiff.py:127-184) imported from baseline/_ref (staged copy of /root/reference, see baseline/ref_runner.py) with the
+# bench's seeded weights, on the FULL batch of the workload.  One sample() call with T = n steps is n denoise steps.
+def reference_enc(workload):
+    """Encoder overrides the reference can run: its radius branch is dead code (unitransformer.py:76-77), so the c3
+    workload falls back to the kNN graph there (said in the line)."""
+    enc = dict(WORKLOADS[workload][4])
+    note = None
+    if enc.get('cutoff_mode') == 'radius':
+        enc, note = {}, "reference cannot build a radius graph (dead code upstream): timed with its kNN graph"
+    return enc, note
 
 
-def pick_cpu_sample(workload, budget_s):
-    """Choose the torch thread count that runs the reference path fastest on this host (all cores is often
-    slower than a moderate count for these op sizes) and the largest graph count (<= the workload's) whose
-    step fits the time budget.  Returns (n_graphs, threads, tried)."""
-    B = WORKLOADS[workload][0]
+def cpu_thread_candidates():
     ncpu = os.cpu_count() or 1
-    # all-cores is pathologically slow for these op sizes on many-core hosts (measured 85 s/step for ONE pocket
-    # with 128 threads vs 0.07 s with 16), so the probe is capped at 64 threads to keep the run short
-    cands = sorted({c for c in (min(ncpu, 64), 32, 16, 8) if c <= ncpu}, reverse=True)
-    tried = {}
-    for c in cands:
-        tried[c] = cpu_reference_steps(workload, 1, 1, 1, c)
-    threads = min(tried, key=tried.get)
-    n = max(1, min(B, int(budget_s / max(tried[threads], 1e-3))))
-    return n, threads, {k: round(v, 3) for k, v in tried.items()}
+    cands = []
+    for c in (min(64, ncpu), 32, 16, ncpu):
+        if c <= ncpu and c not in cands:
+            cands.append(c)
+    return cands
+
+
+def reference_cpu_probe(workload, max_probe_s=240.0):
+    """Pick the torch thread count on the REAL batch: one 2-step sample() call per candidate (these calls are the
+    warm-up of the reference arm).  Returns (threads, {threads: s/step}, steps_run)."""
+    from baseline import ref_runner
+    batch, _ = workload_batch(workload, 0)
+    enc, _ = reference_enc(workload)
+    tried, t0, steps_run = {}, time.perf_counter(), 0
+    for c in cpu_thread_candidates():
+        if tried and time.perf_counter() - t0 > max_probe_s:
+            break
+        sec, _ = ref_runner.time_sample(batch, enc, 2, 'cpu', threads=c)
+        tried[c] = sec / 2
+        steps_run += 2
+    return min(tried, key=tried.get), {k: round(v, 3) for k, v in tried.items()}, steps_run
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: torch CPU
-    fp32, as-written formulation) on this box's host cores, same metric/config."""
+    """--impl reference / reference-gpu: the reference's own implementation of the path on this box (host cores, or
+    eager PyTorch on one GPU), same metric and config, rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    B, n_prot, n_lig, _, enc, desc = WORKLOADS[args.workload]
-    total_steps = args.steps + args.warmup
-    n_graphs, threads, tried = pick_cpu_sample(args.workload, budget_s=max(0.5, 120.0 / max(total_steps, 1)))
-    sec = cpu_reference_steps(args.workload, n_graphs, args.steps, args.warmup, threads)
-    value = n_graphs / (T_STEPS * sec)
-    sample = (f'{n_graphs} of {B} pockets ({n_prot}+{n_lig} atoms each), {args.steps} denoise steps after {args.warmup} '
-              f'warm-up, ligands/s = pockets / (1000 x s/step); {threads} torch threads of {os.cpu_count()} host cores '
-              f'(fastest of s/step for 1 pocket: {tried})')
+    import torch
+    from baseline import ref_runner
+    if ref_runner.ref_root() is None:
+        print(json.dumps({'impl': args.impl, 'unavailable': 'baseline/_ref missing and /root/reference absent'}), flush=True)
+        return
+    B, n_prot, n_lig, _, _, desc = WORKLOADS[args.workload]
+    enc, note = reference_enc(args.workload)
+    batch, _ = workload_batch(args.workload, 0)
+    gpu = args.impl == 'reference-gpu'
+    if gpu:
+        dev = 'cuda:%d' % int(os.environ.get('LOCAL_RANK', '0'))
+        torch.cuda.set_device(dev)
+        warm_steps = max(2, args.warmup)
+        ref_runner.time_sample(batch, enc, warm_steps, dev)                      # warm-up call (allocator, kernels)
+        sec, _ = ref_runner.time_sample(batch, enc, max(2, args.steps), dev)
+        threads, tried = torch.get_num_threads(), None
+        kind = 'reference eager PyTorch on one GPU (unmodified TargetDiff.sample, torch-op shims for pyg/scatter)'
+    else:
+        threads, tried, warm_steps = reference_cpu_probe(args.workload)
+        while warm_steps < args.warmup:                                         # top up to the requested warm-up
+            ref_runner.time_sample(batch, enc, 2, 'cpu', threads=threads)
+            warm_steps += 2
+        sec, _ = ref_runner.time_sample(batch, enc, max(2, args.steps), 'cpu', threads=threads)
+        kind = 'reference CPU path (unmodified TargetDiff.sample, torch CPU fp32)'
+    n_timed = max(2, args.steps)
+    sec_step = sec / n_timed
+    value = B / (T_STEPS * sec_step)
+    sample = (f'all {B} pockets ({n_prot}+{n_lig} atoms each): one TargetDiff.sample() call of {n_timed} denoise steps after '
+              f'{warm_steps} warm-up steps; ligands/s = pockets / (1000 x s/step)')
+    if not gpu:
+        sample += f'; {threads} torch threads of {os.cpu_count()} host cores (s/step on the full batch per thread count: {tried})'
     line = {
-        'impl': 'reference', 'metric': 'ligands/sec sampled (1000-step denoise, batch 64)', 'value': value,
+        'impl': args.impl, 'metric': 'ligands/sec sampled (1000-step denoise, batch 64)', 'value': value,
         'unit': 'ligands/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': {'workload': f'{args.workload}: {desc}', 'graphs_timed': n_graphs,
-                                        'kind': 'oracle port of the reference CPU path (torch CPU, all host threads)'},
-        'cpu_baseline': {'value': value, 'unit': 'ligands/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'ms_per_step': sec_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': f'{args.workload}: {desc}', 'graphs_per_gpu': B, 'graphs_timed': B, 'kind': kind,
+                   'denoise_steps_per_ligand': T_STEPS, 'step': 'one denoise step of the whole batch', 'note': note},
+        'cpu_baseline': {'value': value, 'unit': 'ligands/s', 'cores': threads, 'kind': 'reference', 'sample': sample},
         'e2e': {'value': value, 'unit': 'ligands/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
+    if gpu:
+        line['cpu_baseline'] = None
+        line['config']['device'] = torch.cuda.get_device_name()
     print(json.dumps(line), flush=True)
 
 
@@ -358,15 +375,29 @@ def run_b200(args):
                'd2h_bytes_per_step': d2h / steps_e2e, 'seconds': float(e2e_ms.item()) * 1e-3, 'denoise_steps': steps_e2e,
                'api': 'TargetDiffB200.sample(host batch) -> traj (CPU), H2D/D2H and final gather inside the timed region'}
 
-    # ---- CPU baseline beside it (rank 0, N = 1) ------------------------------------------------------
-    cpu = None
+    # ---- the reference beside it (rank 0, N = 1): its CPU path on the host cores (bounded sample: one 2-step
+    # sample() call on the full batch) and its eager-PyTorch path on this GPU (the same-box GPU comparator)
+    cpu, ref_gpu = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_graphs, threads, tried = pick_cpu_sample(args.workload, budget_s=6.0)
-        sec = cpu_reference_steps(args.workload, n_graphs, 2, 1, threads)
-        cpu = {'value': n_graphs / (T_STEPS * sec), 'unit': 'ligands/s', 'cores': threads, 'kind': 'port',
-               'sample': f'{n_graphs} of {B} pockets ({n_prot}+{n_lig} atoms), 2 denoise steps after 1 warm-up, '
-                         f'oracle port (torch CPU fp32), extrapolated: pockets / (1000 x s/step); {threads} torch threads '
-                         f'of {os.cpu_count()} host cores (fastest of {tried} s/step for 1 pocket)'}
+        from baseline import ref_runner
+        if ref_runner.ref_root() is not None:
+            enc_r, note_r = reference_enc(args.workload)
+            threads = min(64, os.cpu_count() or 1)
+            sec, _ = ref_runner.time_sample(batch, enc_r, 2, 'cpu', threads=threads)
+            cpu = {'value': B / (T_STEPS * sec / 2), 'unit': 'ligands/s', 'cores': threads, 'kind': 'reference',
+                   'sample': f'all {B} pockets, one unmodified TargetDiff.sample() call of 2 denoise steps (no warm-up), torch CPU '
+                             f'fp32, {threads} threads of {os.cpu_count()} host cores; extrapolated: pockets / (1000 x s/step); '
+                             f'the --impl reference arm times more steps and picks the thread count on the full batch'}
+            try:
+                ref_runner.time_sample(batch, enc_r, 2, str(dev))
+                n_ref = 5
+                sec_g, _ = ref_runner.time_sample(batch, enc_r, n_ref, str(dev))
+                ref_gpu = {'ms_per_step': sec_g / n_ref * 1e3, 'value': B / (T_STEPS * sec_g / n_ref), 'unit': 'ligands/s',
+                           'kind': 'reference eager PyTorch on this GPU (unmodified TargetDiff.sample, torch-op shims for '
+                                   'pyg/scatter), one call of %d steps after a 2-step warm-up call' % n_ref, 'note': note_r}
+            except Exception as e:     # the comparator must never take the bench line down
+                ref_gpu = {'unavailable': repr(e)[:200]}
+            torch.set_grad_enabled(False)
 
     if rank == 0:
         line = {
@@ -377,7 +408,7 @@ def run_b200(args):
                        'denoise_steps_per_ligand': T_STEPS, 'step': 'one denoise step of the whole batch',
                        'l2': 'flushed (256 MiB write) between timed steps', 'parallelism': f'dp{world} (pockets sharded, no data-path collective)'},
             'clocks': clocks.summary(), 'gpu_launches': int(gpu_launches), 'e2e': e2e, 'roofline': roofline,
-            'cpu_baseline': cpu, 'kernels': kernels,
+            'cpu_baseline': cpu, 'reference_gpu': ref_gpu, 'kernels': kernels,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -386,7 +417,7 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == 'reference':
+    if args.impl in ('reference', 'reference-gpu'):
         run_reference(args)
     else:
         run_b200(args)

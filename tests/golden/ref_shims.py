@@ -1,8 +1,8 @@
 """Import the UNMODIFIED reference (``/root/reference``) in the build container.
 
-Used only by ``tests/golden/make_golden.py`` (fixture generation) and by the optional
-``tests/test_reference_live.py`` (skipped when ``/root/reference`` is absent, e.g. on
-the GPU box).  Recipe from SURVEY.md Appendix C:
+Used only by the fixture generators ``tests/golden/make_golden*.py`` (build container; the GPU box has
+no ``/root/reference``).  bench.py's reference arms use the staged copy through ``baseline/ref_runner.py``
+instead.  Recipe from SURVEY.md Appendix C:
 
 * fake ``easydict`` (attr-dict), ``rdkit*`` (MagicMock: only touched at import time by
   repo/utils/molecule/constants.py:3-19);

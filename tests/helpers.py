@@ -58,3 +58,14 @@ def rel_err(a, b):
     if b.numel() == 0:
         return 0.0
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+def assert_close(a, b, rtol=1e-4, atol=1e-5, what=''):
+    """Element-wise check beside the global max-norm of ``rel_err``: |a - b| <= atol + rtol * |b| for EVERY element
+    (rel_err alone would admit 2e-3 A on any atom when |x| ~ 20 A)."""
+    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    bad = (a - b).abs() > atol + rtol * b.abs()
+    if bool(bad.any()):
+        i = int(torch.argmax(((a - b).abs() - rtol * b.abs()).flatten()))
+        raise AssertionError(f'{what}: {int(bad.sum())} of {bad.numel()} elements outside rtol={rtol} atol={atol}; worst '
+                             f'got {float(a.flatten()[i]):.7g} want {float(b.flatten()[i]):.7g}')
