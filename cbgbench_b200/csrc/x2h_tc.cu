@@ -20,12 +20,15 @@
 // R-cache is needed: the only per-edge gather is the 512-byte Pj row (cp.async, L2 resident).
 //
 // Warp roles (16 warps x 128 registers):
-//   warps 0-7   S1        thread = (edge row, column half): TMEM(pre) + Pj -> LayerNorm (mean-free: the packer centres
-//                         the first Linear over the feature axis) -> ReLU -> (hi, lo) f16 -> TMEM (in place)
-//   warps 8-11  PROD/EPI  thread = edge row.  PROD(tile t+1): neighbour / coordinates -> d, type, g(d) -> G (TMEM),
-//                         Pi columns of Wg (smem), cp.async of the node's 32 Pj rows into a 6-chunk ring;
-//                         EPI(tile t-1): TMEM(out) -> k: <q_i, k>, softmax over the warp's 32 edges, w = alpha * e_w
-//                                                     v: (v + b1v) * w, sum over the warp's 32 edges, h_i += .
+//   warps 0-7   S1 + PROD thread = (edge row, column half).  S1(tile t): TMEM(pre) + Pj -> LayerNorm (mean-free: the
+//                         packer centres the first Linear over the feature axis) -> ReLU -> (hi, lo) f16 -> TMEM (in
+//                         place).  PROD(tile t+1), right after MMA1(t) has completed (so G may be rewritten) and from
+//                         inputs prefetched one tile ahead: half-0 warps build the G rows (geometry, type, Gaussian
+//                         smearing -> TMEM), half-1 warps write the node's Pi row into its K column of the Wg images and
+//                         cp.async the node's 32 Pj rows into the slots of the ring that tile t frees
+//   warps 8-11  EPI       thread = edge row, inputs prefetched one tile ahead.  k: <q_i, k> per head, softmax over the
+//                         node's 32 edges through a shared-memory transpose, w = alpha * e_w;
+//                         v: (v + b1v) * w, sum over the node's 32 edges, h_i += .
 //   warp 12     MMA       one lane issues every tcgen05.mma / commit
 // Pipelining: TMEM holds two pre/activation buffers and two 64-column output halves, so MMA1 of tile t+1 and MMA2 of
 // tile t-1 run while S1 works on tile t and EPI on tile t-1.
@@ -59,7 +62,7 @@ constexpr float kInvOut = 1.f / 4096.f;  // W1 image is scaled by 64 -> out accu
 // ---- shapes -----------------------------------------------------------------------------------------------------
 constexpr int KG = 96;                   // K of MMA1 (84 used + 8 node one-hot columns (2 tile parities x 4) + 4 zero)
 constexpr int KG_LO = 80;                // the lo part of G is non-zero only in the RBF columns
-constexpr int NCH = 6;                   // Pj ring: chunks of 32 rows
+constexpr int NCH = 5;                   // Pj ring: chunks of 32 rows (a tile uses 4; the 5th decouples the warps)
 constexpr uint32_t PJ_ROW = 528;         // padded row stride: 16-byte row-per-lane reads are bank-conflict free
 constexpr uint32_t PJ_CHUNK = 32 * PJ_ROW;
 constexpr uint32_t W1_IMG = 128 * 128 * 2;            // one (hi | lo) image, bytes
@@ -71,11 +74,13 @@ constexpr uint32_t SM_PJ = SM_WG + 2 * WG_IMG;
 constexpr uint32_t SM_LN = SM_PJ + NCH * PJ_CHUNK;    // gamma * 64 [128] | beta * 64 [128]
 constexpr uint32_t SM_B1 = SM_LN + 1024;              // b1v [128]
 constexpr uint32_t SM_XCH = SM_B1 + 512;              // sum-of-squares exchange between the two half-row S1 warps
-constexpr uint32_t SM_BAR = SM_XCH + 2048;              // [tile parity][half][row]
+constexpr uint32_t SM_QBUF = SM_XCH + 2048;             // EPI: [warp][tile parity][128] q row of the warp's node
+constexpr uint32_t SM_SOFT = SM_QBUF + 4096;            // EPI: [warp][32 edges][17] logits <-> weights transpose
+constexpr uint32_t SM_BAR = SM_SOFT + 4 * 32 * 17 * 4;
 constexpr int NBAR = 11 + 2 * NCH;
 constexpr uint32_t SM_TOTAL = SM_BAR + 8 * NBAR + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
-enum { B_WFULL = 0, B_GREADY, B_GFREE, B_ACC1 /*2*/ = 3, B_AREADY /*2*/ = 5, B_ACC2 /*2*/ = 7, B_ACC2FREE /*2*/ = 9,
+enum { B_WFULL = 0, B_GREADY, B_UNUSED, B_ACC1 /*2*/ = 3, B_AREADY /*2*/ = 5, B_ACC2 /*2*/ = 7, B_ACC2FREE /*2*/ = 9,
        B_PJFULL = 11, B_PJFREE = 11 + NCH };
 // TMEM columns
 constexpr uint32_t TM_BUF = 0;           // 2 x 128: pre (fp32) -> a_hi (64 cols) | a_lo (64 cols)
@@ -96,12 +101,6 @@ __device__ __forceinline__ int node_of(const EdgeArgs& p, int n, int n_list) {
 }
 
 // =================================================================================================================
-// per-warp state of the producer half of the EPI/PROD warps: everything tile t+1 needs, loaded one stage ahead
-struct TileIn {
-  int i;          // destination node of this warp's slot
-  int jn;         // neighbour of this lane (-1: padded slot)
-};
-
 template <bool IS_V>
 __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -115,12 +114,13 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * NBAR);
   const float* L = p.layer;
   const int n_my = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;     // tiles of this CTA: blockIdx.x + k * gridDim.x
+  // node of slot `slot` of this CTA's kk-th tile (clamped to the list: surplus slots of the last tile redo the last node)
+  auto tile_node = [&](int kk, int slot) { return node_of(p, 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + slot, n_list); };
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
-    mbar_init(bar(B_GREADY), 4);
-    mbar_init(bar(B_GFREE), 1);
+    mbar_init(bar(B_GREADY), 8);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(B_ACC1 + b), 1);
       mbar_init(bar(B_AREADY + b), 8);
@@ -143,108 +143,25 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 8) {
-    // ===================================== S1: LayerNorm + ReLU + split =========================================
-    // thread = (edge row, column half).  The first Linear is centred over the feature axis by the packer (W0 and
-    // b0 minus their column means), so pre has zero mean and LayerNorm needs only the sum of squares.
+    // ===================================== S1 (tile k) + producer of tile k + 1 =================================
+    // thread = (edge row, column half hf).  S1: pre = TMEM + Pj -> LayerNorm -> ReLU -> (hi, lo) f16 -> TMEM.  The
+    // first Linear is centred over the feature axis by the packer, so pre has zero mean and LayerNorm needs only the
+    // sum of squares.  Producer duties (inputs prefetched one tile ahead, so no load latency is exposed):
+    //   hf = 0 warps: G row of the next tile (geometry -> type, Gaussian smearing -> TMEM);
+    //   hf = 1 warps: Pi row of the next tile's node -> its K column of the Wg images; the node's 32 Pj rows -> ring.
     const int wq = warp & 3, hf = warp >> 2;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
     const float* s_ln = reinterpret_cast<const float*>(smem + SM_LN) + 64 * hf;
     float* s_x = reinterpret_cast<float*>(smem + SM_XCH);
     const int row = 32 * wq + lane;
-    for (int k = 0; k < n_my; ++k) {
-      const int b = k & 1;
-      const int idx = 4 * k + wq, c = idx % NCH;
-      mbar_wait(bar(B_PJFULL + c), (uint32_t)((idx / NCH) & 1));
-      mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));
-      tc_fence_after();
-      const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
-      float v[64];
-      {
-        uint32_t r[2][32];
-        tmem_ld32_nowait(t_buf + 64u * hf, r[0]);
-        tmem_ld32_nowait(t_buf + 64u * hf + 32u, r[1]);
-        tmem_wait_ld();
-        const uint8_t* prow = smem + SM_PJ + (uint32_t)c * PJ_CHUNK + (uint32_t)lane * PJ_ROW + 256u * hf;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float4 pj = *reinterpret_cast<const float4*>(prow + 16 * j);
-          const uint32_t* rv = &r[j >> 3][4 * (j & 7)];
-          const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(rv[0]), __uint_as_float(rv[1])),
-                                       make_float2(kInvPre, kInvPre), make_float2(pj.x, pj.y));
-          const float2 a1 = __ffma2_rn(make_float2(__uint_as_float(rv[2]), __uint_as_float(rv[3])),
-                                       make_float2(kInvPre, kInvPre), make_float2(pj.z, pj.w));
-          v[4 * j] = a0.x; v[4 * j + 1] = a0.y; v[4 * j + 2] = a1.x; v[4 * j + 3] = a1.y;
-        }
-      }
-      float2 q2 = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) q2 = __ffma2_rn(make_float2(v[2 * j], v[2 * j + 1]), make_float2(v[2 * j], v[2 * j + 1]), q2);
-      const float qs = q2.x + q2.y;
-      s_x[256 * b + 128 * hf + row] = qs;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_PJFREE + c));          // this warp is done with the ring chunk
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");   // the two half-row warps of this row quarter
-      const float qo = s_x[256 * b + 128 * (hf ^ 1) + row];
-      const float rstd = 1.f / sqrtf((qs + qo) * (1.f / 128.f) + 1e-5f);
-      const float2 rr = make_float2(rstd, rstd);
-      // relu((pre * rstd) * gamma + beta) * 64 -> (hi, lo) f16 into the buffer's columns: hi 0-63, lo 64-127
-      // (the partner thread has read its accumulator columns before the barrier above)
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 ga = *reinterpret_cast<const float4*>(s_ln + 32 * ch + 4 * j);
-          const float4 be = *reinterpret_cast<const float4*>(s_ln + 128 + 32 * ch + 4 * j);
-          const int e = 32 * ch + 4 * j;
-          float2 y0 = __fmul2_rn(make_float2(v[e], v[e + 1]), rr);
-          float2 y1 = __fmul2_rn(make_float2(v[e + 2], v[e + 3]), rr);
-          y0 = __ffma2_rn(y0, make_float2(ga.x, ga.y), make_float2(be.x, be.y));
-          y1 = __ffma2_rn(y1, make_float2(ga.z, ga.w), make_float2(be.z, be.w));
-          split_pair_relu(y0.x, y0.y, hi[2 * j], lo[2 * j]);
-          split_pair_relu(y1.x, y1.y, hi[2 * j + 1], lo[2 * j + 1]);
-        }
-        tmem_st16(t_buf + 32u * hf + 16u * ch, hi);
-        tmem_st16(t_buf + 64u + 32u * hf + 16u * ch, lo);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_AREADY + b));
-    }
-  } else if (warp < 12) {
-    // ===================================== PROD (tile k + 1) then EPI (tile k - 1) ===============================
-    const int wq = warp - 8;
-    const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
-    const float* s_b1 = reinterpret_cast<const float*>(smem + SM_B1);
     const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
     const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
     const float* rbf = L + kOffRbf;
     const float coeff = __ldg(rbf + 20);
 
-    auto load_tile = [&](int kk, TileIn& t) {
-      const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + wq;
-      t.i = node_of(p, n, n_list);
-      t.jn = p.nbr[(size_t)t.i * CBG_KMAX + lane];
-    };
-    // ---- producer half: everything tile kk needs before its first MMA
-    auto produce = [&](int kk, const TileIn& t) {
-      const int i = t.i;
-      const int jj = t.jn >= 0 ? t.jn : i;
-      const float4 xi = p.x4[i];
-      const float4 xj = p.x4[jj];
-      const float4 pi4 = ldg4(pi_plane + (size_t)i * CBG_H + 4 * lane);
-      {   // Pj rows of the node's 32 in-edges -> ring chunk (warp = row-coalesced 512-byte copies)
-        const int idx = 4 * kk + wq, c = idx % NCH;
-        if (idx >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)(((idx / NCH) - 1) & 1));
-        const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)lane;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const int jr = __shfl_sync(CBG_FULL, jj, r);
-          cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
-        }
-        cp_async_arrive(bar(B_PJFULL + c));
-      }
+    // ---- producer pieces ------------------------------------------------------------------------------------
+    // hf = 0: G row of tile kk -> TMEM: hi 96 f16 (48 columns), lo 80 f16 (40 columns)
+    auto build_g = [&](int kk, const float4 xi, const float4 xj) {
       // geometry, edge type, Gaussian smearing (x2h_attention.py:46-52, unitransformer.py:88-99)
       const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
       const float d = sqrtf(rx * rx + ry * ry + rz * rz);
@@ -256,25 +173,6 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         const float u0 = d - __ldg(rbf + 2 * mp), u1 = d - __ldg(rbf + 2 * mp + 1);
         split_pair(expf(coeff * u0 * u0) * kScaleG, expf(coeff * u1 * u1) * kScaleG, ghi[mp], glo[mp]);
       }
-      // centred Pi row: the planes are centred by construction (packer); nothing to do here
-      if (kk > 0) { mbar_wait(bar(B_GFREE), (uint32_t)((kk - 1) & 1)); tc_fence_after(); }
-      else mbar_wait(bar(B_WFULL), 0u);      // the Pi columns go into the Wg images: the bulk copy must have landed
-      {   // Pi row of this node -> K column (84 + slot + 4 * parity) of the Wg images (hi, lo), features 4*lane..+3
-        const int kcol = 84 + wq + 4 * (kk & 1);
-        const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
-        const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int nn = 4 * lane + q;
-          const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
-          const __half hh = __float2half_rn(pv[q]);
-          const __half hl = __float2half_rn(pv[q] - __half2float(hh));
-          *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
-          *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
-        }
-        fence_proxy_async();
-      }
-      // G row -> TMEM: hi 96 f16 (48 columns), lo 80 f16 (40 columns)
 #pragma unroll
       for (int blk = 0; blk < 3; ++blk) {          // 16 columns = 32 f16 per store
         uint32_t w16[16];
@@ -311,20 +209,188 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_GREADY));
     };
-    // ---- epilogue half
-    auto epilogue = [&](int kk, const TileIn& t) {
-      const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + wq;
-      const bool live = n < n_list;
-      const int i = t.i;
+    // hf = 1: Pi row of the node -> K column (84 + slot + 4 * parity) of the Wg images (hi, lo), features 4*lane..+3
+    auto write_pi = [&](int kk, const float4 pi4) {
+      const int kcol = 84 + wq + 4 * (kk & 1);
+      const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
+      const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int nn = 4 * lane + q;
+        const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
+        const __half hh = __float2half_rn(pv[q]);
+        const __half hl = __float2half_rn(pv[q] - __half2float(hh));
+        *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
+        *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_GREADY));
+    };
+    // hf = 1: the node's 32 Pj rows -> ring chunk (warp = row-coalesced 512-byte copies)
+    auto copy_pj = [&](int kk, int jj) {
+      const int idx = 4 * kk + wq, c = idx % NCH;
+      if (idx >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)(((idx / NCH) - 1) & 1));
+      const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)lane;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int jr = __shfl_sync(CBG_FULL, jj, r);
+        cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
+      }
+      cp_async_arrive(bar(B_PJFULL + c));
+    };
+    // prefetch state: tile k+1 fully resolved (C), tile k+2 node + neighbour (B), tile k+3 node (A)
+    int iA = 0, iB = 0, jnB = -1, jjC = 0;
+    float4 xiC = make_float4(0.f, 0.f, 0.f, 0.f), xjC = xiC, piC = xiC;
+    auto fetch_geo = [&](int i, int jn, int& jj_out) {      // C <- inputs of the tile whose (node, neighbour) are (i, jn)
+      const int jj = jn >= 0 ? jn : i;
+      jj_out = jj;
+      if (hf == 0) { xiC = p.x4[i]; xjC = p.x4[jj]; }
+      else piC = ldg4(pi_plane + (size_t)i * CBG_H + 4 * lane);
+    };
+    {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
+      const int i0 = tile_node(0, wq);
+      const int jn0 = p.nbr[(size_t)i0 * CBG_KMAX + lane];
+      int jj0;
+      fetch_geo(i0, jn0, jj0);
+      if (hf == 0) build_g(0, xiC, xjC);
+      else {
+        copy_pj(0, jj0);
+        mbar_wait(bar(B_WFULL), 0u);      // the Pi columns go into the Wg images: the bulk copy must have landed
+        write_pi(0, piC);
+      }
+      if (n_my > 1) {
+        const int i1 = tile_node(1, wq);
+        fetch_geo(i1, p.nbr[(size_t)i1 * CBG_KMAX + lane], jjC);
+      }
+      if (n_my > 2) { iB = tile_node(2, wq); jnB = p.nbr[(size_t)iB * CBG_KMAX + lane]; }
+      if (n_my > 3) iA = tile_node(3, wq);
+    }
+    for (int k = 0; k < n_my; ++k) {
+      const int b = k & 1;
+      const int idx = 4 * k + wq, c = idx % NCH;
+      mbar_wait(bar(B_PJFULL + c), (uint32_t)((idx / NCH) & 1));
+      mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready AND G may be rewritten
+      tc_fence_after();
+      // ---- producer duties for tile k + 1, then rotate the prefetch registers (the loads land during S1 below)
+      const int jj_next = jjC;
+      if (k + 1 < n_my) {
+        if (hf == 0) build_g(k + 1, xiC, xjC);
+        else write_pi(k + 1, piC);
+      }
+      if (k + 2 < n_my) { int jj2; fetch_geo(iB, jnB, jj2); jjC = jj2; }
+      if (k + 3 < n_my) { iB = iA; jnB = p.nbr[(size_t)iA * CBG_KMAX + lane]; }
+      if (k + 4 < n_my) iA = tile_node(k + 4, wq);
+      // ---- S1
+      const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
+      float v[64];
+      {
+        uint32_t r[2][32];
+        tmem_ld32_nowait(t_buf + 64u * hf, r[0]);
+        tmem_ld32_nowait(t_buf + 64u * hf + 32u, r[1]);
+        tmem_wait_ld();
+        const uint8_t* prow = smem + SM_PJ + (uint32_t)c * PJ_CHUNK + (uint32_t)lane * PJ_ROW + 256u * hf;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 pj = *reinterpret_cast<const float4*>(prow + 16 * j);
+          const uint32_t* rv = &r[j >> 3][4 * (j & 7)];
+          const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(rv[0]), __uint_as_float(rv[1])),
+                                       make_float2(kInvPre, kInvPre), make_float2(pj.x, pj.y));
+          const float2 a1 = __ffma2_rn(make_float2(__uint_as_float(rv[2]), __uint_as_float(rv[3])),
+                                       make_float2(kInvPre, kInvPre), make_float2(pj.z, pj.w));
+          v[4 * j] = a0.x; v[4 * j + 1] = a0.y; v[4 * j + 2] = a1.x; v[4 * j + 3] = a1.y;
+        }
+      }
+      float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) q2 = __ffma2_rn(make_float2(v[2 * j], v[2 * j + 1]), make_float2(v[2 * j], v[2 * j + 1]), q2);
+      const float qs = q2.x + q2.y;
+      s_x[256 * b + 128 * hf + row] = qs;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_PJFREE + c));          // this warp is done with the ring chunk
+      if (hf == 1 && k + 1 < n_my) copy_pj(k + 1, jj_next);   // the next tile's rows go into the slots this tile frees
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");   // the two half-row warps of this row quarter
+      const float qo = s_x[256 * b + 128 * (hf ^ 1) + row];
+      const float rstd = 1.f / sqrtf((qs + qo) * (1.f / 128.f) + 1e-5f);
+      const float2 rr = make_float2(rstd, rstd);
+      // relu((pre * rstd) * gamma + beta) * 64 -> (hi, lo) f16 into the buffer's columns: hi 0-63, lo 64-127
+      // (the partner thread has read its accumulator columns before the barrier above)
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 ga = *reinterpret_cast<const float4*>(s_ln + 32 * ch + 4 * j);
+          const float4 be = *reinterpret_cast<const float4*>(s_ln + 128 + 32 * ch + 4 * j);
+          const int e = 32 * ch + 4 * j;
+          float2 y0 = __fmul2_rn(make_float2(v[e], v[e + 1]), rr);
+          float2 y1 = __fmul2_rn(make_float2(v[e + 2], v[e + 3]), rr);
+          y0 = __ffma2_rn(y0, make_float2(ga.x, ga.y), make_float2(be.x, be.y));
+          y1 = __ffma2_rn(y1, make_float2(ga.z, ga.w), make_float2(be.z, be.w));
+          split_pair_relu(y0.x, y0.y, hi[2 * j], lo[2 * j]);
+          split_pair_relu(y1.x, y1.y, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        tmem_st16(t_buf + 32u * hf + 16u * ch, hi);
+        tmem_st16(t_buf + 64u + 32u * hf + 16u * ch, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_AREADY + b));
+    }
+  } else if (warp < 12) {
+    // ===================================== EPI (tile k), inputs prefetched one tile ahead ========================
+    const int wq = warp - 8;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
+    const float* s_b1 = reinterpret_cast<const float*>(smem + SM_B1);
+    float* s_q = reinterpret_cast<float*>(smem + SM_QBUF) + wq * 256;          // [tile parity][128]: q row of the node
+    float* s_sm = reinterpret_cast<float*>(smem + SM_SOFT) + wq * (32 * 17);   // [edge][17]: logits / weights transpose
+    // prefetched inputs of the next tile
+    int i_n = tile_node(0, wq), i_nn = n_my > 1 ? tile_node(1, wq) : 0;
+    bool valid_n = false;
+    float ew_n = 0.f, h_n[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 w_n[4];
+    auto prefetch = [&](int kk, int i) {
       const size_t eoff = (size_t)i * CBG_KMAX + lane;
       if constexpr (!IS_V) {
-        const bool valid = t.jn >= 0;
-        const float ew = p.ew[eoff];
-        const float* qi = p.q + (size_t)i * CBG_H;
-        float lg[CBG_HEADS];
+        valid_n = p.nbr[eoff] >= 0;
+        ew_n = p.ew[eoff];
+        cp_async16(smem_u32(s_q + 128 * (kk & 1)) + 16u * (uint32_t)lane, p.q + (size_t)i * CBG_H + 4 * lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      } else {
+        const float* wi = p.w + eoff * CBG_HEADS;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w_n[j] = ld4(wi + 4 * j);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h_n[j] = p.h[(size_t)i * CBG_H + 32 * j + lane];
+      }
+    };
+    prefetch(0, i_n);
+    for (int k = 0; k < n_my; ++k) {
+      const int n = 4 * ((int)blockIdx.x + k * (int)gridDim.x) + wq;
+      const bool live = n < n_list;
+      const int i = i_n;
+      const size_t eoff = (size_t)i * CBG_KMAX + lane;
+      // take over this tile's inputs, start the next tile's
+      const bool valid = valid_n;
+      const float ew = ew_n;
+      float wv[CBG_HEADS], hv[4];
+      if constexpr (IS_V) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { wv[4 * j] = w_n[j].x; wv[4 * j + 1] = w_n[j].y; wv[4 * j + 2] = w_n[j].z; wv[4 * j + 3] = w_n[j].w; hv[j] = h_n[j]; }
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // q row of this tile has landed (own copies only)
+        __syncwarp();
+      }
+      i_n = i_nn;
+      if (k + 1 < n_my) prefetch(k + 1, i_n);
+      if (k + 2 < n_my) i_nn = tile_node(k + 2, wq);
+      if constexpr (!IS_V) {
+        const float* qs = s_q + 128 * (k & 1);
+        float* my = s_sm + lane * 17;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar(B_ACC2 + h), (uint32_t)(kk & 1));
+          mbar_wait(bar(B_ACC2 + h), (uint32_t)(k & 1));
           tc_fence_after();
           uint32_t r[2][32];
           tmem_ld32_nowait(t_lane + TM_OUT + 64u * h, r[0]);
@@ -335,44 +401,47 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
           if (lane == 0) mbar_arrive(bar(B_ACC2FREE + h));
 #pragma unroll
           for (int hh = 0; hh < 8; ++hh) {
-            const float4 q0 = ldg4(qi + 64 * h + 8 * hh), q1 = ldg4(qi + 64 * h + 8 * hh + 4);
+            const float4 q0 = *reinterpret_cast<const float4*>(qs + 64 * h + 8 * hh);
+            const float4 q1 = *reinterpret_cast<const float4*>(qs + 64 * h + 8 * hh + 4);
             const uint32_t* rv = &r[hh >> 2][8 * (hh & 3)];
             float2 tt = __fmul2_rn(make_float2(__uint_as_float(rv[0]), __uint_as_float(rv[1])), make_float2(q0.x, q0.y));
             tt = __ffma2_rn(make_float2(__uint_as_float(rv[2]), __uint_as_float(rv[3])), make_float2(q0.z, q0.w), tt);
             tt = __ffma2_rn(make_float2(__uint_as_float(rv[4]), __uint_as_float(rv[5])), make_float2(q1.x, q1.y), tt);
             tt = __ffma2_rn(make_float2(__uint_as_float(rv[6]), __uint_as_float(rv[7])), make_float2(q1.z, q1.w), tt);
-            lg[8 * h + hh] = valid ? (tt.x + tt.y) * kInvOut : -INFINITY;
+            my[8 * h + hh] = valid ? (tt.x + tt.y) * kInvOut : -INFINITY;      // row = edge, stride 17: conflict free
           }
         }
-        // softmax over the warp's 32 edges, per head; w = alpha * e_w
-        float wv[CBG_HEADS];
+        __syncwarp();
+        // softmax over the 32 edges per head through the shared-memory transpose: lane = (head, half of the edges)
+        {
+          const int hd = lane & 15, e0 = 16 * (lane >> 4);
+          float l[16];
+          float mx = -INFINITY;
 #pragma unroll
-        for (int hd = 0; hd < CBG_HEADS; ++hd) {
-          float mx = lg[hd];
+          for (int j = 0; j < 16; ++j) { l[j] = s_sm[(e0 + j) * 17 + hd]; mx = fmaxf(mx, l[j]); }
+          mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, 16));
+          float sum = 0.f;
 #pragma unroll
-          for (int m = 16; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(CBG_FULL, mx, m));
-          const float ex = (mx == -INFINITY) ? 0.f : expf(lg[hd] - mx);
-          const float sum = warp_sum(ex);
-          wv[hd] = (ex / ((sum > 0.f) ? sum : 1.f)) * (valid ? ew : 0.f);
+          for (int j = 0; j < 16; ++j) { l[j] = (mx == -INFINITY) ? 0.f : __expf(l[j] - mx); sum += l[j]; }
+          sum += __shfl_xor_sync(CBG_FULL, sum, 16);
+          const float inv = 1.f / ((sum > 0.f) ? sum : 1.f);
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s_sm[(e0 + j) * 17 + hd] = l[j] * inv;
         }
-        if (live) {
+        __syncwarp();
+        if (live) {      // w = alpha * e_w, this lane's edge row
+          const float sc = valid ? ew : 0.f;
           float* wo = p.w + eoff * CBG_HEADS;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) st4(wo + 4 * j, make_float4(wv[4 * j], wv[4 * j + 1], wv[4 * j + 2], wv[4 * j + 3]));
+          for (int j = 0; j < 4; ++j)
+            st4(wo + 4 * j, make_float4(my[4 * j] * sc, my[4 * j + 1] * sc, my[4 * j + 2] * sc, my[4 * j + 3] * sc));
         }
+        __syncwarp();
       } else {
-        float wv[CBG_HEADS];
-        {
-          const float* wi = p.w + eoff * CBG_HEADS;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 tt = ld4(wi + 4 * j);
-            wv[4 * j] = tt.x; wv[4 * j + 1] = tt.y; wv[4 * j + 2] = tt.z; wv[4 * j + 3] = tt.w;
-          }
-        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar(B_ACC2 + h), (uint32_t)(kk & 1));
+          mbar_wait(bar(B_ACC2 + h), (uint32_t)(k & 1));
           tc_fence_after();
 #pragma unroll
           for (int qq = 0; qq < 2; ++qq) {           // 32 columns at a time: features 64h + 32qq + (0..31)
@@ -395,26 +464,11 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
               val[4 * c4 + 3] = fmaf(__uint_as_float(r[4 * c4 + 3]), kInvOut, b1.w) * wh;
             }
             warp_transpose_reduce<32>(val, lane);      // lane l: sum over the 32 edges of feature 64h + 32qq + l
-            if (live) {
-              float* hp = p.h + (size_t)i * CBG_H + 64 * h + 32 * qq + lane;
-              *hp = *hp + val[0];
-            }
+            if (live) p.h[(size_t)i * CBG_H + 64 * h + 32 * qq + lane] = hv[2 * h + qq] + val[0];
           }
         }
       }
-    };
-    TileIn tA{0, -1}, tB, tC{0, -1}, tD{0, -1};      // tiles k-1, k, k+1, k+2 of this CTA
-    load_tile(0, tB);
-    if (n_my > 1) load_tile(1, tC);
-    produce(0, tB);
-#pragma unroll 1
-    for (int k = 0; k < n_my; ++k) {
-      if (k + 1 < n_my) produce(k + 1, tC);
-      if (k + 2 < n_my) load_tile(k + 2, tD);        // consumed one iteration later: the loads' latency is hidden
-      if (k >= 1) epilogue(k - 1, tA);
-      tA = tB; tB = tC; tC = tD;
     }
-    epilogue(n_my - 1, tA);
   } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================
     if (lane == 0) {
@@ -457,7 +511,6 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
 #pragma unroll 1
         for (int ks = 0; ks < KG / 16; ++ks) umma_f16_ts(d, tmem + TM_GHI + 8u * ks, smem_desc(wg_hi + 256u * ks, LBO, WG_SBO), IDESC128, 1u);
         umma_commit(bar(B_ACC1 + b));
-        umma_commit(bar(B_GFREE));
         if (k > 0) issue_mma2(k - 1);
       }
       issue_mma2(n_my - 1);
