@@ -476,25 +476,30 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       bulk_g2s(sbase + SM_W1, L + (IS_V ? kOffVW1 : kOffKW1), 2 * W1_IMG, bar(B_WFULL));
       bulk_g2s(sbase + SM_WG, L + (IS_V ? kOffVWg : kOffKWg), 2 * WG_IMG, bar(B_WFULL));
       mbar_wait(bar(B_WFULL), 0u);
-      const uint32_t w1_hi = sbase + SM_W1, w1_lo = w1_hi + W1_IMG;
-      const uint32_t wg_hi = sbase + SM_WG, wg_lo = wg_hi + WG_IMG;
+      // Descriptors are tile-invariant: build the four bases once; a K step of 16 f16 (two core matrices, 256 bytes)
+      // adds 16 to the 14-bit start-address field, so every MMA below costs one integer add and the issue itself
+      // (the loops are fully unrolled - a rolled loop spends ~100 cycles per MMA on the uniform datapath, which made the
+      // single issuing thread, not the tensor pipe, the limiter of the whole kernel).
+      const uint64_t dg_hi = smem_desc(sbase + SM_WG, LBO, WG_SBO), dg_lo = smem_desc(sbase + SM_WG + WG_IMG, LBO, WG_SBO);
+      const uint64_t d1_hi = smem_desc(sbase + SM_W1, LBO, W1_SBO), d1_lo = smem_desc(sbase + SM_W1 + W1_IMG, LBO, W1_SBO);
+      constexpr uint64_t kHalfRows = (uint64_t)((8u * W1_SBO) >> 4);      // output features 64..127 of W1: 8 row groups further
       auto issue_mma2 = [&](int kk) {
         const int bb = kk & 1;
         mbar_wait(bar(B_AREADY + bb), (uint32_t)((kk >> 1) & 1));
         tc_fence_after();
         const uint32_t a_hi = tmem + TM_BUF + 128u * (uint32_t)bb, a_lo = a_hi + 64u;
-#pragma unroll 1
+#pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (kk > 0) { mbar_wait(bar(B_ACC2FREE + h), (uint32_t)((kk - 1) & 1)); tc_fence_after(); }
           const uint32_t d = tmem + TM_OUT + 64u * (uint32_t)h;
-          const uint32_t bh = w1_hi + (uint32_t)h * 8u * W1_SBO, bl = w1_lo + (uint32_t)h * 8u * W1_SBO;
-#pragma unroll 1
+          const uint64_t bh = d1_hi + (uint64_t)h * kHalfRows, bl = d1_lo + (uint64_t)h * kHalfRows;
+#pragma unroll
           for (int ks = 0; ks < 8; ++ks)     // small terms first
-            umma_f16_ts(d, a_lo + 8u * ks, smem_desc(bh + 256u * ks, LBO, W1_SBO), IDESC64, ks > 0 ? 1u : 0u);
-#pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, smem_desc(bl + 256u * ks, LBO, W1_SBO), IDESC64, 1u);
-#pragma unroll 1
-          for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, smem_desc(bh + 256u * ks, LBO, W1_SBO), IDESC64, 1u);
+            umma_f16_ts(d, a_lo + 8u * ks, bh + 16u * ks, IDESC64, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, bl + 16u * ks, IDESC64, 1u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, bh + 16u * ks, IDESC64, 1u);
           umma_commit(bar(B_ACC2 + h));
         }
       };
@@ -503,13 +508,13 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         mbar_wait(bar(B_GREADY), (uint32_t)(k & 1));
         tc_fence_after();
         const uint32_t d = tmem + TM_BUF + 128u * (uint32_t)b;
-#pragma unroll 1
+#pragma unroll
         for (int ks = 0; ks < KG_LO / 16; ++ks)
-          umma_f16_ts(d, tmem + TM_GLO + 8u * ks, smem_desc(wg_hi + 256u * ks, LBO, WG_SBO), IDESC128, ks > 0 ? 1u : 0u);
-#pragma unroll 1
-        for (int ks = 0; ks < KG / 16; ++ks) umma_f16_ts(d, tmem + TM_GHI + 8u * ks, smem_desc(wg_lo + 256u * ks, LBO, WG_SBO), IDESC128, 1u);
-#pragma unroll 1
-        for (int ks = 0; ks < KG / 16; ++ks) umma_f16_ts(d, tmem + TM_GHI + 8u * ks, smem_desc(wg_hi + 256u * ks, LBO, WG_SBO), IDESC128, 1u);
+          umma_f16_ts(d, tmem + TM_GLO + 8u * ks, dg_hi + 16u * ks, IDESC128, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KG / 16; ++ks) umma_f16_ts(d, tmem + TM_GHI + 8u * ks, dg_lo + 16u * ks, IDESC128, 1u);
+#pragma unroll
+        for (int ks = 0; ks < KG / 16; ++ks) umma_f16_ts(d, tmem + TM_GHI + 8u * ks, dg_hi + 16u * ks, IDESC128, 1u);
         umma_commit(bar(B_ACC1 + b));
         if (k > 0) issue_mma2(k - 1);
       }

@@ -76,7 +76,6 @@ def device_built_batches(args, dev):
             b = builder.build([pocket], min(args.batch_size, args.num_samples - s0), device=dev)
             if args.model == 'diffsbdd':          # our DiffSBDD host class takes integer types like the other two
                 b['ligand_atom_type'] = torch.zeros(b['ligand_pos'].shape[0], dtype=torch.int64, device=dev)
-            b['protein_translation'] = b['graph_translation']      # per graph, the driver's convention (sample.py:199 uses row 0)
             batches.append(b)
     return batches
 
@@ -119,8 +118,9 @@ def run(args):
         else:
             x, v = final_state(model, batch)
             gid = batch['ligand_element_batch'].to(x.device)
-        # translate back like sample.py:198-201 (synthetic pockets are already centred: translation = 0)
-        tr = batch.get('protein_translation')
+        # translate back like sample.py:198-201, per graph (the reference adds protein_translation[:1] to the whole batch,
+        # identical for its batches of copies of one pocket; synthetic pockets are already centred: no translation)
+        tr = sharding.graph_translation(batch)
         if tr is not None:
             x = x + tr.to(x.device)[gid]
         results.extend(split_batch_into_samples(x, v, gid, n_graphs))

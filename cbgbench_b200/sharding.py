@@ -15,7 +15,9 @@ import torch.distributed as dist
 BATCH_LIG_KEYS = ('ligand_pos', 'ligand_atom_type', 'ligand_lig_flag', 'ligand_gen_flag', 'ligand_ctx_flag',
                   'ligand_element_batch')
 BATCH_REC_KEYS = ('protein_pos', 'protein_atom_feature', 'protein_aa_type', 'protein_lig_flag',
-                  'protein_gen_flag', 'protein_element_batch')
+                  'protein_gen_flag', 'protein_translation', 'protein_element_batch')
+# 'protein_translation' has the reference's layout: one row per PROTEIN ATOM ([n_rec, 3], center_pos transform,
+# translation.py:11-24); the per-graph form used by the driver is 'graph_translation' [B, 3]
 
 
 def graph_sizes(batch):
@@ -54,8 +56,33 @@ def take_graphs(batch, graph_ids):
             if k in batch:
                 out[k] = batch[k][keep.to(batch[k].device)]
         out[bkey] = remap[b[keep]].to(batch[bkey].device)
-    if 'protein_translation' in batch:
-        out['protein_translation'] = batch['protein_translation'][gids.to(batch['protein_translation'].device)]
+    if 'graph_translation' in batch:
+        out['graph_translation'] = batch['graph_translation'][gids.to(batch['graph_translation'].device)]
+    return out
+
+
+def graph_translation(batch):
+    """Per-graph translation [B, 3] that undoes the centring transform, or None.
+
+    Accepts 'graph_translation' [B, 3] (DeviceBatchBuilder) or the reference's per-protein-atom
+    'protein_translation' [n_rec, 3] (every atom of a graph carries its graph's vector: the first protein row of each
+    graph is taken).  The reference itself adds ``protein_translation[:1]`` to the whole batch (sample.py:198-199),
+    which is the same thing for its batches of copies of ONE pocket and wrong for mixed pockets."""
+    if 'graph_translation' in batch and batch['graph_translation'] is not None:
+        return batch['graph_translation']
+    tr = batch.get('protein_translation') if hasattr(batch, 'get') else None
+    if tr is None:
+        return None
+    br = batch['protein_element_batch']
+    B = int(max(int(batch['ligand_element_batch'].max()), int(br.max()))) + 1
+    if tr.shape[0] != br.shape[0]:
+        raise ValueError(f"protein_translation has {tr.shape[0]} rows, expected one per protein atom ({br.shape[0]}); "
+                         "use 'graph_translation' for a per-graph tensor")
+    first = torch.full((B,), br.shape[0], dtype=torch.long, device=br.device)
+    first = first.scatter_reduce(0, br, torch.arange(br.shape[0], device=br.device), reduce='amin')
+    out = torch.zeros((B, 3), dtype=tr.dtype, device=tr.device)
+    has = first < br.shape[0]                       # graphs without protein atoms keep a zero translation
+    out[has.to(tr.device)] = tr[first[has].to(tr.device)]
     return out
 
 
@@ -79,6 +106,8 @@ def gather_final(x_lig, v_lig, graph_id_global, group=None, counts=None):
     m = max(counts) if counts else 0
     packed = torch.zeros((m, 5), dtype=torch.float32, device=x_lig.device)
     packed[: x_lig.shape[0], 0:3] = x_lig
+    if x_lig.shape[0]:
+        assert int(graph_id_global.max()) < (1 << 24) and int(v_lig.max()) < (1 << 24), 'ids must be exact in fp32'
     packed[: x_lig.shape[0], 3] = v_lig.to(torch.float32)        # class ids < 2^24: exact in fp32
     packed[: x_lig.shape[0], 4] = graph_id_global.to(torch.float32)
     bufs = [torch.empty_like(packed) for _ in range(world)]

@@ -136,7 +136,7 @@ def make_batch(n_prot, n_lig, seed=2024, num_classes=13, gen_mode='denovo', prot
         'ligand_lig_flag': torch.ones(n_l, dtype=torch.bool),
         'protein_lig_flag': torch.zeros(n_p, dtype=torch.bool),
         'ligand_element_batch': cat(lb, np.int64), 'protein_element_batch': cat(pb, np.int64),
-        'protein_translation': torch.zeros(len(n_prot), 3),
+        'protein_translation': torch.zeros(n_p, 3),     # one row per protein atom, like center_pos (translation.py:11-24)
     }
     if gen_mode == 'partial':
         batch['ligand_gen_flag'] = cat(gen, np.bool_)

@@ -179,5 +179,5 @@ def test_take_graphs_renumbers_and_selects():
     assert sub['protein_element_batch'].tolist() == [0] * 4 + [1] * 5
     assert torch.equal(sub['ligand_pos'][2:], batch['ligand_pos'][3:])
     assert torch.equal(sub['protein_pos'][:4], batch['protein_pos'][:4])
-    assert sub['ligand_gen_flag'].shape[0] == 5 and sub['protein_translation'].shape[0] == 2
+    assert sub['ligand_gen_flag'].shape[0] == 5 and sub['protein_translation'].shape[0] == 9
     assert sharding.graph_sizes(batch).tolist() == [6, 4, 8]
