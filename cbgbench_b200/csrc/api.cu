@@ -106,17 +106,19 @@ int check_ws(const void* workspace, size_t have, long long n_nodes, long long n_
   return 0;
 }
 
-// node GEMM implementation: tcgen05 (3xTF32) unless CBG_NODE_GEMM=simt
+// node GEMM implementation: tcgen05 kind::f16 with the (hi, lo) split (default), CBG_NODE_GEMM=tf32 the 3xTF32
+// kernel, CBG_NODE_GEMM=simt the fp32 SIMT kernel
 int node_gemm_impl() {
   static int impl = -1;
   if (impl < 0) {
     const char* e = getenv("CBG_NODE_GEMM");
-    impl = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+    impl = (e && strcmp(e, "simt") == 0) ? 0 : ((e && strcmp(e, "tf32") == 0) ? 1 : 2);
   }
   return impl;
 }
 int launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st) {
-  return node_gemm_impl() ? cbg_launch_node_gemm_tc(a, st) : cbg_launch_node_gemm(a, st);
+  const int impl = node_gemm_impl();
+  return impl == 2 ? cbg_launch_node_gemm_f16(a, st) : (impl == 1 ? cbg_launch_node_gemm_tc(a, st) : cbg_launch_node_gemm(a, st));
 }
 
 // Second stream for the H2X chain of layer l, which overlaps the X2H node GEMM of layer l+1
@@ -229,6 +231,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     g.q_b1 = L + cbg_layout::layer_offset(CBG_LF_X2H_Q_B1);
     g.out_q = ws.plane[4];
     g.tc_planes = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_TC); g.tc_first_plane = 0;
+    g.tch_planes = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_TCH);
     if (!prune) {
       if (int rc = launch_node_gemm(g, st)) return rc;          // reads h only: may overlap the previous H2X chain
     } else {
@@ -278,6 +281,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     gj.ldw = 640; gj.n_planes = 2; gj.has_q = 0;
     gj.out[0] = ws.hplane[0]; gj.out[1] = ws.hplane[1];
     gj.tc_planes = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_TC); gj.tc_first_plane = 0;
+    gj.tch_planes = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_TCH);
     if (prune) { gj.row_idx = ws.order; gj.n_rows_dev = ws.cnt + num_layers; }   // depth == top: generated atoms + neighbours
     if (int rc = launch_node_gemm(gj, sx)) return rc;
     NodeGemmArgs gi{};
@@ -289,7 +293,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     gi.q_w1t = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_W1T);
     gi.q_b1 = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_B1);
     gi.out_q = ws.hplane[4];
-    gi.tc_planes = gj.tc_planes; gi.tc_first_plane = 2;
+    gi.tc_planes = gj.tc_planes; gi.tc_first_plane = 2; gi.tch_planes = gj.tch_planes;
     if (int rc = launch_node_gemm(gi, overlap ? g_aux.s4 : sx)) return rc;     // beside gj
     if (overlap) {
       CBG_CUDA_OK(cudaEventRecord(g_aux.ev_gi, g_aux.s4));
@@ -307,21 +311,31 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
   return 0;
 }
 
-// cached device scratch for the *_host entry points
+// cached device scratch for the *_host entry points: one per DEVICE (the buffers belong to the device that was current
+// when they were allocated); the weight blob is re-uploaded whenever the caller's (version, size, host pointer) changes -
+// the version is a process-unique id handed out by the Python side, so two models never alias
 struct HostCache {
   void* dev = nullptr;
   size_t bytes = 0;
   float* blob = nullptr;
   long long blob_floats = 0;
   long long blob_version = -1;
-} g_cache;
+  const void* blob_host = nullptr;
+};
+HostCache g_cache_dev[kMaxDevices];
 
-int cache_reserve(size_t bytes) {
-  if (g_cache.bytes >= bytes) return 0;
-  if (g_cache.dev) CBG_CUDA_OK(cudaFree(g_cache.dev));
-  g_cache.dev = nullptr; g_cache.bytes = 0;
-  CBG_CUDA_OK(cudaMalloc(&g_cache.dev, bytes));
-  g_cache.bytes = bytes;
+HostCache* host_cache() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  return &g_cache_dev[dev];
+}
+
+int cache_reserve(HostCache& c, size_t bytes) {
+  if (c.bytes >= bytes) return 0;
+  if (c.dev) CBG_CUDA_OK(cudaFree(c.dev));
+  c.dev = nullptr; c.bytes = 0;
+  CBG_CUDA_OK(cudaMalloc(&c.dev, bytes));
+  c.bytes = bytes;
   return 0;
 }
 
@@ -470,13 +484,18 @@ int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_float
   for (long long i = 0; i < n_nodes; ++i) if (gen_flag_host[i]) gen_idx.push_back((int)i);
   const int n_gen = (int)gen_idx.size();
 
-  if (g_cache.blob_version != blob_version || g_cache.blob_floats != blob_floats) {
+  HostCache* cp = host_cache();
+  if (!cp) { cbg_set_error("no current CUDA device"); return 2; }
+  HostCache& g_cache = *cp;
+  if (g_cache.blob_version != blob_version || g_cache.blob_floats != blob_floats || g_cache.blob_host != (const void*)blob_host) {
     if (g_cache.blob) CBG_CUDA_OK(cudaFree(g_cache.blob));
     g_cache.blob = nullptr;
+    g_cache.blob_version = -1;
     CBG_CUDA_OK(cudaMalloc((void**)&g_cache.blob, (size_t)blob_floats * 4));
     CBG_CUDA_OK(cudaMemcpy(g_cache.blob, blob_host, (size_t)blob_floats * 4, cudaMemcpyHostToDevice));
     g_cache.blob_floats = blob_floats;
     g_cache.blob_version = blob_version;
+    g_cache.blob_host = (const void*)blob_host;
   }
   const size_t ws_bytes = carve(nullptr, n_nodes, n_gen).bytes;
   size_t off = ws_bytes;
@@ -486,7 +505,7 @@ int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_float
   const size_t o_gi = region((size_t)(n_gen > 0 ? n_gen : 1) * 4);
   const size_t o_xo = region((size_t)n_nodes * 12), o_ho = region((size_t)n_nodes * CBG_H * 4);
   const size_t o_lo = region((size_t)n_nodes * num_classes * 4);
-  if (int rc = cache_reserve(off)) return rc;
+  if (int rc = cache_reserve(g_cache, off)) return rc;
   char* d = (char*)g_cache.dev;
   cudaStream_t st = 0;
   CBG_CUDA_OK(cudaMemcpyAsync(d + o_x, x_host, (size_t)n_nodes * 12, cudaMemcpyHostToDevice, st));
@@ -510,7 +529,7 @@ int32_t cbg_denoiser_forward_host_f32(const float* blob_host, int64_t blob_float
 
 int32_t cbg_node_proj_f32(const float* blob_layer, int32_t sublayer, int32_t impl, const float* h,
                           const int32_t* row_idx, int32_t n_rows, int64_t n_nodes, float* planes, void* stream) {
-  if (sublayer < 0 || sublayer > 1 || (impl != 0 && impl != 1 && impl != 11 && impl != 12 && impl != 14)) { cbg_set_error("bad sublayer/impl"); return 1; }
+  if (sublayer < 0 || sublayer > 1 || (impl != 0 && impl != 1 && impl != 2 && impl != 11 && impl != 12 && impl != 14)) { cbg_set_error("bad sublayer/impl"); return 1; }
   const float* L = blob_layer;
   NodeGemmArgs g{};
   g.a = h; g.row_idx = row_idx; g.n_rows = n_rows;
@@ -524,8 +543,10 @@ int32_t cbg_node_proj_f32(const float* blob_layer, int32_t sublayer, int32_t imp
   g.q_b1 = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_Q_B1 : CBG_LF_X2H_Q_B1);
   g.out_q = planes + (size_t)4 * n_nodes * CBG_H;
   g.tc_planes = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_NODE_TC : CBG_LF_X2H_NODE_TC);
+  g.tch_planes = L + cbg_layout::layer_offset(sublayer ? CBG_LF_H2X_NODE_TCH : CBG_LF_X2H_NODE_TCH);
   g.tc_first_plane = 0;
   if (impl == 0) return cbg_launch_node_gemm(g, (cudaStream_t)stream);
+  if (impl == 2) return cbg_launch_node_gemm_f16(g, (cudaStream_t)stream);
   return cbg_launch_node_gemm_tc(g, (cudaStream_t)stream, impl == 12 ? 2 : (impl == 14 ? 4 : (impl == 11 ? 1 : 0)));
 }
 
@@ -657,6 +678,7 @@ int32_t cbg_bp_step_f32(const cbg_sample_plan* plan, const float* com_blob, int3
       gj.ldw = 640; gj.n_planes = 2; gj.has_q = 0;
       gj.out[0] = ws.hplane[0]; gj.out[1] = ws.hplane[1];
       gj.tc_planes = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_TC); gj.tc_first_plane = 0;
+    gj.tch_planes = L + cbg_layout::layer_offset(CBG_LF_H2X_NODE_TCH);
       if (pruned) { gj.row_idx = ws.order; gj.n_rows_dev = ws.cnt + plan->num_layers; }   // generated atoms + neighbours
       if (int rc = launch_node_gemm(gj, st)) return rc;
       NodeGemmArgs gi{};
@@ -668,7 +690,7 @@ int32_t cbg_bp_step_f32(const cbg_sample_plan* plan, const float* com_blob, int3
       gi.q_w1t = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_W1T);
       gi.q_b1 = L + cbg_layout::layer_offset(CBG_LF_H2X_Q_B1);
       gi.out_q = ws.hplane[4];
-      gi.tc_planes = gj.tc_planes; gi.tc_first_plane = 2;
+      gi.tc_planes = gj.tc_planes; gi.tc_first_plane = 2; gi.tch_planes = gj.tch_planes;
       if (int rc = launch_node_gemm(gi, st)) return rc;
       EdgeArgs x{};
       x.x4 = ws.x4; x.nbr = ws.nbr; x.ew = ws.ew;

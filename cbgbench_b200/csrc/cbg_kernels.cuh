@@ -45,10 +45,13 @@ struct NodeGemmArgs {
   const int* n_rows_dev;   // optional: rows to process is min(n_rows, *n_rows_dev) (device-side list length)
   const float* tc_planes;  // plane 0 of the sub-layer
   int tc_first_plane;      // index of this launch's first plane (q second Linear is always plane 5)
+  const float* tch_planes; // f16 (hi | lo) images of the same six planes (node_gemm_f16.cu)
 };
 int cbg_launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st);      // fp32 SIMT
 // tcgen05 3xTF32; cluster = 1/2/4 CTAs sharing weight chunks by multicast, 0 = default (env CBG_GEMM_CLUSTER)
 int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st, int cluster = 0);
+// tcgen05 kind::f16 with the (hi, lo) split: default
+int cbg_launch_node_gemm_f16(const NodeGemmArgs& a, cudaStream_t st);
 
 // edge.cu
 struct EdgeArgs {

@@ -20,16 +20,16 @@
 // R-cache is needed: the only per-edge gather is the 512-byte Pj row (cp.async, L2 resident).
 //
 // Warp roles (16 warps x 128 registers):
-//   warps 0-7   S1 + PROD thread = (edge row, column half).  S1(tile t): TMEM(pre) + Pj -> LayerNorm (mean-free: the
+//   warps 0-7   S1        thread = (edge row, column half).  S1(tile t): TMEM(pre) + Pj -> LayerNorm (mean-free: the
 //                         packer centres the first Linear over the feature axis) -> ReLU -> (hi, lo) f16 -> TMEM (in
-//                         place).  PROD(tile t+1), right after MMA1(t) has completed (so G may be rewritten) and from
-//                         inputs prefetched one tile ahead: half-0 warps build the G rows (geometry, type, Gaussian
-//                         smearing -> TMEM), half-1 warps write the node's Pi row into its K column of the Wg images and
-//                         cp.async the node's 32 Pj rows into the slots of the ring that tile t frees
+//                         place).  The half-0 warps also build the G rows of tile t+1 (geometry, type, Gaussian
+//                         smearing -> TMEM) right after MMA1(t) has completed, from coordinates prefetched a tile ahead
 //   warps 8-11  EPI       thread = edge row, inputs prefetched one tile ahead.  k: <q_i, k> per head, softmax over the
 //                         node's 32 edges through a shared-memory transpose, w = alpha * e_w;
 //                         v: (v + b1v) * w, sum over the node's 32 edges, h_i += .
-//   warp 12     MMA       one lane issues every tcgen05.mma / commit
+//   warp 12     MMA       one lane issues every tcgen05.mma / commit (fully unrolled, tile-invariant descriptors)
+//   warps 13-15 PROD      one tile ahead: cp.async of every node's 32 Pj rows into a 5-chunk ring; the node's Pi row
+//                         into its K column of the Wg images
 // Pipelining: TMEM holds two pre/activation buffers and two 64-column output halves, so MMA1 of tile t+1 and MMA2 of
 // tile t-1 run while S1 works on tile t and EPI on tile t-1.
 #include <math.h>
@@ -77,11 +77,11 @@ constexpr uint32_t SM_XCH = SM_B1 + 512;              // sum-of-squares exchange
 constexpr uint32_t SM_QBUF = SM_XCH + 2048;             // EPI: [warp][tile parity][128] q row of the warp's node
 constexpr uint32_t SM_SOFT = SM_QBUF + 4096;            // EPI: [warp][32 edges][17] logits <-> weights transpose
 constexpr uint32_t SM_BAR = SM_SOFT + 4 * 32 * 17 * 4;
-constexpr int NBAR = 11 + 2 * NCH;
+constexpr int NBAR = 13 + 2 * NCH;
 constexpr uint32_t SM_TOTAL = SM_BAR + 8 * NBAR + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 enum { B_WFULL = 0, B_GREADY, B_UNUSED, B_ACC1 /*2*/ = 3, B_AREADY /*2*/ = 5, B_ACC2 /*2*/ = 7, B_ACC2FREE /*2*/ = 9,
-       B_PJFULL = 11, B_PJFREE = 11 + NCH };
+       B_PJFULL = 11, B_PJFREE = 11 + NCH, B_PIREADY /*2*/ = 11 + 2 * NCH };
 // TMEM columns
 constexpr uint32_t TM_BUF = 0;           // 2 x 128: pre (fp32) -> a_hi (64 cols) | a_lo (64 cols)
 constexpr uint32_t TM_OUT = 256;         // 2 x 64 : output halves (features 0-63, 64-127)
@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
-    mbar_init(bar(B_GREADY), 8);
+    mbar_init(bar(B_GREADY), 4);
+    mbar_init(bar(B_PIREADY), 4);
+    mbar_init(bar(B_PIREADY + 1), 4);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(B_ACC1 + b), 1);
       mbar_init(bar(B_AREADY + b), 8);
@@ -143,26 +145,23 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 8) {
-    // ===================================== S1 (tile k) + producer of tile k + 1 =================================
+    // ===================================== S1 (tile k); half-0 warps also build G of tile k + 1 ==================
     // thread = (edge row, column half hf).  S1: pre = TMEM + Pj -> LayerNorm -> ReLU -> (hi, lo) f16 -> TMEM.  The
     // first Linear is centred over the feature axis by the packer, so pre has zero mean and LayerNorm needs only the
-    // sum of squares.  Producer duties (inputs prefetched one tile ahead, so no load latency is exposed):
-    //   hf = 0 warps: G row of the next tile (geometry -> type, Gaussian smearing -> TMEM);
-    //   hf = 1 warps: Pi row of the next tile's node -> its K column of the Wg images; the node's 32 Pj rows -> ring.
+    // sum of squares.  Right after MMA1(k) has completed (the wait below) the G region of TMEM may be rewritten: the
+    // hf = 0 warps build the next tile's G rows there from coordinates prefetched one tile ahead.
     const int wq = warp & 3, hf = warp >> 2;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
     const float* s_ln = reinterpret_cast<const float*>(smem + SM_LN) + 64 * hf;
     float* s_x = reinterpret_cast<float*>(smem + SM_XCH);
     const int row = 32 * wq + lane;
-    const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
-    const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
     const float* rbf = L + kOffRbf;
-    const float coeff = __ldg(rbf + 20);
+    const float c2 = __ldg(rbf + 20) * 1.4426950408889634f;      // exp(c u^2) = 2^(c log2(e) u^2)
 
-    // ---- producer pieces ------------------------------------------------------------------------------------
-    // hf = 0: G row of tile kk -> TMEM: hi 96 f16 (48 columns), lo 80 f16 (40 columns)
+    // G row of tile kk -> TMEM: hi 96 f16 (48 columns), lo 80 f16 (40 columns)
     auto build_g = [&](int kk, const float4 xi, const float4 xj) {
-      // geometry, edge type, Gaussian smearing (x2h_attention.py:46-52, unitransformer.py:88-99)
+      // geometry, edge type, Gaussian smearing (x2h_attention.py:46-52, unitransformer.py:88-99); the factor 1024 of
+      // the G scale rides in the exponent
       const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
       const float d = sqrtf(rx * rx + ry * ry + rz * rz);
       const int fi = node_flags(xi), fj = node_flags(xj);
@@ -171,7 +170,10 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
 #pragma unroll
       for (int mp = 0; mp < 10; ++mp) {
         const float u0 = d - __ldg(rbf + 2 * mp), u1 = d - __ldg(rbf + 2 * mp + 1);
-        split_pair(expf(coeff * u0 * u0) * kScaleG, expf(coeff * u1 * u1) * kScaleG, ghi[mp], glo[mp]);
+        float g0, g1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g0) : "f"(fmaf(c2 * u0, u0, 10.f)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g1) : "f"(fmaf(c2 * u1, u1, 10.f)));
+        split_pair(g0, g1, ghi[mp], glo[mp]);
       }
 #pragma unroll
       for (int blk = 0; blk < 3; ++blk) {          // 16 columns = 32 f16 per store
@@ -209,59 +211,17 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_GREADY));
     };
-    // hf = 1: Pi row of the node -> K column (84 + slot + 4 * parity) of the Wg images (hi, lo), features 4*lane..+3
-    auto write_pi = [&](int kk, const float4 pi4) {
-      const int kcol = 84 + wq + 4 * (kk & 1);
-      const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
-      const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int nn = 4 * lane + q;
-        const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
-        const __half hh = __float2half_rn(pv[q]);
-        const __half hl = __float2half_rn(pv[q] - __half2float(hh));
-        *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
-        *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_GREADY));
-    };
-    // hf = 1: the node's 32 Pj rows -> ring chunk (warp = row-coalesced 512-byte copies)
-    auto copy_pj = [&](int kk, int jj) {
-      const int idx = 4 * kk + wq, c = idx % NCH;
-      if (idx >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)(((idx / NCH) - 1) & 1));
-      const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)lane;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        const int jr = __shfl_sync(CBG_FULL, jj, r);
-        cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
-      }
-      cp_async_arrive(bar(B_PJFULL + c));
-    };
-    // prefetch state: tile k+1 fully resolved (C), tile k+2 node + neighbour (B), tile k+3 node (A)
-    int iA = 0, iB = 0, jnB = -1, jjC = 0;
-    float4 xiC = make_float4(0.f, 0.f, 0.f, 0.f), xjC = xiC, piC = xiC;
-    auto fetch_geo = [&](int i, int jn, int& jj_out) {      // C <- inputs of the tile whose (node, neighbour) are (i, jn)
-      const int jj = jn >= 0 ? jn : i;
-      jj_out = jj;
-      if (hf == 0) { xiC = p.x4[i]; xjC = p.x4[jj]; }
-      else piC = ldg4(pi_plane + (size_t)i * CBG_H + 4 * lane);
-    };
-    {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
+    // prefetch state of the G builders: coordinates of tile k+1 (C), node + neighbour of tile k+2 (B), node of tile k+3 (A)
+    int iA = 0, iB = 0, jnB = -1;
+    float4 xiC = make_float4(0.f, 0.f, 0.f, 0.f), xjC = xiC;
+    auto fetch_geo = [&](int i, int jn) { xiC = p.x4[i]; xjC = p.x4[jn >= 0 ? jn : i]; };
+    if (hf == 0) {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
       const int i0 = tile_node(0, wq);
-      const int jn0 = p.nbr[(size_t)i0 * CBG_KMAX + lane];
-      int jj0;
-      fetch_geo(i0, jn0, jj0);
-      if (hf == 0) build_g(0, xiC, xjC);
-      else {
-        copy_pj(0, jj0);
-        mbar_wait(bar(B_WFULL), 0u);      // the Pi columns go into the Wg images: the bulk copy must have landed
-        write_pi(0, piC);
-      }
+      fetch_geo(i0, p.nbr[(size_t)i0 * CBG_KMAX + lane]);
+      build_g(0, xiC, xjC);
       if (n_my > 1) {
         const int i1 = tile_node(1, wq);
-        fetch_geo(i1, p.nbr[(size_t)i1 * CBG_KMAX + lane], jjC);
+        fetch_geo(i1, p.nbr[(size_t)i1 * CBG_KMAX + lane]);
       }
       if (n_my > 2) { iB = tile_node(2, wq); jnB = p.nbr[(size_t)iB * CBG_KMAX + lane]; }
       if (n_my > 3) iA = tile_node(3, wq);
@@ -272,15 +232,12 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       mbar_wait(bar(B_PJFULL + c), (uint32_t)((idx / NCH) & 1));
       mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready AND G may be rewritten
       tc_fence_after();
-      // ---- producer duties for tile k + 1, then rotate the prefetch registers (the loads land during S1 below)
-      const int jj_next = jjC;
-      if (k + 1 < n_my) {
-        if (hf == 0) build_g(k + 1, xiC, xjC);
-        else write_pi(k + 1, piC);
+      if (hf == 0) {      // G of tile k + 1, then rotate the prefetch registers (the loads land during S1 below)
+        if (k + 1 < n_my) build_g(k + 1, xiC, xjC);
+        if (k + 2 < n_my) fetch_geo(iB, jnB);
+        if (k + 3 < n_my) { iB = iA; jnB = p.nbr[(size_t)iA * CBG_KMAX + lane]; }
+        if (k + 4 < n_my) iA = tile_node(k + 4, wq);
       }
-      if (k + 2 < n_my) { int jj2; fetch_geo(iB, jnB, jj2); jjC = jj2; }
-      if (k + 3 < n_my) { iB = iA; jnB = p.nbr[(size_t)iA * CBG_KMAX + lane]; }
-      if (k + 4 < n_my) iA = tile_node(k + 4, wq);
       // ---- S1
       const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
       float v[64];
@@ -308,7 +265,6 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       s_x[256 * b + 128 * hf + row] = qs;
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_PJFREE + c));          // this warp is done with the ring chunk
-      if (hf == 1 && k + 1 < n_my) copy_pj(k + 1, jj_next);   // the next tile's rows go into the slots this tile frees
       asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");   // the two half-row warps of this row quarter
       const float qo = s_x[256 * b + 128 * (hf ^ 1) + row];
       const float rstd = 1.f / sqrtf((qs + qo) * (1.f / 128.f) + 1e-5f);
@@ -469,6 +425,73 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         }
       }
     }
+  } else if (warp >= 13) {
+    // ===================================== PROD: Pj rows and Pi columns, one tile ahead ===========================
+    // warp 13 serves node slots 0 and 1, warp 14 slot 2, warp 15 slot 3 (no TMEM access here, so no lane-quarter rule).
+    // Per slot and tile: cp.async the node's 32 Pj rows into the ring chunk (row-coalesced 512-byte copies), and write
+    // the node's Pi row into its K column (84 + slot + 4 * tile parity) of the Wg images (hi, lo).
+    const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
+    const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
+    const int slot0 = (warp == 13) ? 0 : warp - 12;
+    const int nslot = (warp == 13) ? 2 : 1;
+    int i_c[2] = {0, 0}, jn_c[2] = {-1, -1}, i_n[2] = {0, 0};
+    float4 pi_c[2];
+    pi_c[0] = pi_c[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (q < nslot) {
+        i_c[q] = tile_node(0, slot0 + q);
+        jn_c[q] = p.nbr[(size_t)i_c[q] * CBG_KMAX + lane];
+        pi_c[q] = ldg4(pi_plane + (size_t)i_c[q] * CBG_H + 4 * lane);
+        if (n_my > 1) i_n[q] = tile_node(1, slot0 + q);
+      }
+    for (int kk = 0; kk < n_my; ++kk) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q >= nslot) continue;
+        const int slot = slot0 + q;
+        const int i = i_c[q], jj = jn_c[q] >= 0 ? jn_c[q] : i;
+        const float4 pi4 = pi_c[q];
+        // start the next tile's loads (node id was fetched one tile earlier: nothing here waits on a dependent load)
+        if (kk + 1 < n_my) {
+          i_c[q] = i_n[q];
+          jn_c[q] = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
+          pi_c[q] = ldg4(pi_plane + (size_t)i_n[q] * CBG_H + 4 * lane);
+          if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
+        }
+        {   // Pj rows
+          const int idx = 4 * kk + slot, c = idx % NCH;
+          if (idx >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)(((idx / NCH) - 1) & 1));
+          const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)lane;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            const int jr = __shfl_sync(CBG_FULL, jj, r);
+            cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
+          }
+          cp_async_arrive(bar(B_PJFULL + c));
+        }
+        // Pi column of this tile parity: last read by MMA1(kk - 2)
+        if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
+        else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
+        {
+          const int kcol = 84 + slot + 4 * (kk & 1);
+          const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
+          const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int nn = 4 * lane + e;
+            const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
+            const __half hh = __float2half_rn(pv[e]);
+            const __half hl = __float2half_rn(pv[e] - __half2float(hh));
+            *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
+            *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
+        }
+      }
+    }
   } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================
     if (lane == 0) {
@@ -506,6 +529,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       for (int k = 0; k < n_my; ++k) {
         const int b = k & 1;
         mbar_wait(bar(B_GREADY), (uint32_t)(k & 1));
+        mbar_wait(bar(B_PIREADY + b), (uint32_t)((k >> 1) & 1));
         tc_fence_after();
         const uint32_t d = tmem + TM_BUF + 128u * (uint32_t)b;
 #pragma unroll

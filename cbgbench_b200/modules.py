@@ -95,6 +95,10 @@ class E3DualAttentionLayer(_NoTorchPath):
         self.h2x_layers = nn.ModuleList([H2XAttention(hidden, n_heads, edge_feat_dim, num_r_gaussian)])
 
 
+import itertools
+_BLOB_VERSIONS = itertools.count(1)
+
+
 def _t(w):
     return w.detach().to('cpu', torch.float64)
 
@@ -145,6 +149,7 @@ def tc_f16_image(w):
 TC_SCALE_WG = 16.0
 TC_SCALE_W1 = 64.0
 TC_KG = 96
+TC_SCALE_NODE = 256.0       # node GEMM weight planes (csrc/node_gemm_f16.cu)
 
 
 def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
@@ -231,6 +236,8 @@ def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
             tc = [w0k[:, 212:340], w0v[:, 212:340], w0k[:, 84:212], w0v[:, 84:212],
                   _t(sd[sp + qname + '.net.0.weight']), _t(sd[sp + qname + '.net.3.weight']) * inv_sqrt_dh]
             put(base, lf, f'{tag}_NODE_TC', torch.cat([tc_weight_plane(m.to(torch.float32)) for m in tc]))
+            put_raw(base, lf, f'{tag}_NODE_TCH', torch.cat([tc_f16_image((m[:, 64 * c: 64 * c + 64] * TC_SCALE_NODE).numpy())
+                                                             for m in tc for c in range(2)]))
             put(base, lf, f'{tag}_NODE_B', node_b)
             put(base, lf, f'{tag}_Q_LN', torch.cat([_t(sd[sp + qname + '.net.1.weight']), _t(sd[sp + qname + '.net.1.bias'])]))
             put(base, lf, f'{tag}_Q_W1T', (_t(sd[sp + qname + '.net.3.weight']) * inv_sqrt_dh).t().contiguous())
@@ -358,7 +365,7 @@ class UniTransformerB200(nn.Module):
             sd = {k: v for k, v in self.state_dict().items()}
             self._blob = pack_denoiser_blob(sd, '', self.num_layers, self.out_classes).to(device)
             self._blob_key = key
-            self._blob_version = getattr(self, '_blob_version', 0) + 1
+            self._blob_version = next(_BLOB_VERSIONS)       # process-unique: the C side keys its device copy on it
         return self._blob
 
     @property

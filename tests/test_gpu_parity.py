@@ -321,8 +321,8 @@ def test_ragged_config5_shape_vs_oracle_subset():
 
 # ---------------------------------------------------------------------------------------------
 # node projections: fp32 SIMT kernel and tcgen05 (3xTF32) kernel against a float64 reference
-@pytest.mark.parametrize('impl', [0, 1, 11, 12, 14],
-                         ids=['simt', 'tcgen05-ws', 'tcgen05-single', 'tcgen05-cluster2', 'tcgen05-cluster4'])
+@pytest.mark.parametrize('impl', [0, 1, 2, 11, 12, 14],
+                         ids=['simt', 'tcgen05-tf32-ws', 'tcgen05-f16', 'tcgen05-single', 'tcgen05-cluster2', 'tcgen05-cluster4'])
 @pytest.mark.parametrize('sublayer', [0, 1], ids=['x2h', 'h2x'])
 def test_node_projections_match_float64(impl, sublayer):
     model, sd = make_model(10, device=dev())
