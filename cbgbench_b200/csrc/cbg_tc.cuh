@@ -20,18 +20,28 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 // Blocking wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint expires),
 // so waiting warps do not burn issue slots in a polling loop (measured: polling was a third of all issued instructions
-// of the X2H kernels).  Never hang the GPU: a wait that is still incomplete after many expirations traps.
+// of the X2H kernels).  Never hang the GPU: a wait that is still incomplete after 2 s of wall time traps.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
+  uint32_t done = 0;
+  uint64_t t0 = 0;
   while (!done) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "r"(bar), "r"(parity), "r"(100000u)
         : "memory");
-    if (!done && ++spins > (1u << 20)) __trap();
+    if (!done) {
+      const uint64_t t = global_timer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 2000000000ull) __trap();
+    }
   }
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }

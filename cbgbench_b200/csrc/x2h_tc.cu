@@ -76,7 +76,8 @@ constexpr uint32_t SM_B1 = SM_LN + 1024;              // b1v [128]
 constexpr uint32_t SM_XCH = SM_B1 + 512;              // sum-of-squares exchange between the two half-row S1 warps
 constexpr uint32_t SM_QBUF = SM_XCH + 2048;             // EPI: [warp][tile parity][128] q row of the warp's node
 constexpr uint32_t SM_SOFT = SM_QBUF + 4096;            // EPI: [warp][32 edges][17] logits <-> weights transpose
-constexpr uint32_t SM_BAR = SM_SOFT + 4 * 32 * 17 * 4;
+constexpr uint32_t SM_VRED = SM_QBUF;                   // EPI of the v kernel (aliases QBUF / SOFT): [warp][32 edges][36] transpose
+constexpr uint32_t SM_BAR = SM_QBUF + 4 * 32 * 36 * 4;
 constexpr int NBAR = 13 + 2 * NCH;
 constexpr uint32_t SM_TOTAL = SM_BAR + 8 * NBAR + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     const float* s_b1 = reinterpret_cast<const float*>(smem + SM_B1);
     float* s_q = reinterpret_cast<float*>(smem + SM_QBUF) + wq * 256;          // [tile parity][128]: q row of the node
     float* s_sm = reinterpret_cast<float*>(smem + SM_SOFT) + wq * (32 * 17);   // [edge][17]: logits / weights transpose
+    float* s_vr = reinterpret_cast<float*>(smem + SM_VRED) + wq * (32 * 36);   // v kernel: [edge][36] transpose (aliases the two above)
     // prefetched inputs of the next tile
     int i_n = tile_node(0, wq), i_nn = n_my > 1 ? tile_node(1, wq) : 0;
     bool valid_n = false;
@@ -409,17 +411,34 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
               __syncwarp();
               if (lane == 0) mbar_arrive(bar(B_ACC2FREE + h));
             }
-            float val[32];
+            // (v + b1v) * w -> this lane's row of the transpose buffer (stride 36 words: 16-byte stores conflict free),
+            // then lane l sums column l over the node's 32 edges (fixed order: deterministic)
+            float* vrow = s_vr + lane * 36;
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
               const float4 b1 = *reinterpret_cast<const float4*>(s_b1 + 64 * h + 32 * qq + 4 * c4);
               const float wh = wv[8 * h + 4 * qq + (c4 >> 1)];
-              val[4 * c4 + 0] = fmaf(__uint_as_float(r[4 * c4 + 0]), kInvOut, b1.x) * wh;
-              val[4 * c4 + 1] = fmaf(__uint_as_float(r[4 * c4 + 1]), kInvOut, b1.y) * wh;
-              val[4 * c4 + 2] = fmaf(__uint_as_float(r[4 * c4 + 2]), kInvOut, b1.z) * wh;
-              val[4 * c4 + 3] = fmaf(__uint_as_float(r[4 * c4 + 3]), kInvOut, b1.w) * wh;
+              float4 o;
+              o.x = fmaf(__uint_as_float(r[4 * c4 + 0]), kInvOut, b1.x) * wh;
+              o.y = fmaf(__uint_as_float(r[4 * c4 + 1]), kInvOut, b1.y) * wh;
+              o.z = fmaf(__uint_as_float(r[4 * c4 + 2]), kInvOut, b1.z) * wh;
+              o.w = fmaf(__uint_as_float(r[4 * c4 + 3]), kInvOut, b1.w) * wh;
+              *reinterpret_cast<float4*>(vrow + 4 * c4) = o;
             }
-            warp_transpose_reduce<32>(val, lane);      // lane l: sum over the 32 edges of feature 64h + 32qq + l
+            __syncwarp();
+            float val[1];
+            {
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int e = 0; e < 32; e += 4) {
+                s0 += s_vr[(e + 0) * 36 + lane];
+                s1 += s_vr[(e + 1) * 36 + lane];
+                s2 += s_vr[(e + 2) * 36 + lane];
+                s3 += s_vr[(e + 3) * 36 + lane];
+              }
+              val[0] = (s0 + s1) + (s2 + s3);
+            }
+            __syncwarp();
             if (live) p.h[(size_t)i * CBG_H + 64 * h + 32 * qq + lane] = hv[2 * h + qq] + val[0];
           }
         }

@@ -26,24 +26,32 @@ def main():
     rep = sys.argv[1]
     nodes = float(sys.argv[2]) if len(sys.argv) > 2 else None
     rows = list(csv.reader(io.StringIO(ncu(['-i', rep, '--page', 'raw', '--csv']))))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
     print(f'# {rep}')
-    for i, h in enumerate(hdr):
-        if h in ('Kernel Name',):
-            print(h, '=', vals[i])
-    for w in WANT:
-        for i, h in enumerate(hdr):
-            if h == w:
-                print(f'{w:70s} {vals[i]:>16s} {units[i]}')
+    for vals in rows[2:]:
+        print('==== ' + vals[hdr.index('Kernel Name')])
+        for w in WANT:
+            for i, h in enumerate(hdr):
+                if h == w:
+                    print(f'{w:70s} {vals[i]:>16s} {units[i]}')
     src = list(csv.reader(io.StringIO(ncu(['-i', rep, '--page', 'source', '--csv']))))
-    if len(src) > 2:
-        h = src[1]
-        iS, iE, iN = h.index('Source'), h.index('Instructions Executed'), h.index('# Samples')
+    blocks, cur = [], None
+    for r in src:
+        if len(r) >= 2 and r[0] == 'Kernel Name':
+            cur = {'name': r[1], 'hdr': None, 'rows': []}
+            blocks.append(cur)
+        elif cur is not None and len(r) > 2 and r[0] == 'Address':
+            cur['hdr'] = r
+        elif cur is not None and cur['hdr'] is not None and len(r) == len(cur['hdr']):
+            cur['rows'].append(r)
+    for b in blocks:
+        h = b['hdr']
+        if not h:
+            continue
+        iS, iE = h.index('Source'), h.index('Instructions Executed')
         stall_cols = [(i, n) for i, n in enumerate(h) if n.startswith('stall_') and 'Not Issued' not in n]
         ops, stalls, tot = collections.Counter(), collections.Counter(), 0
-        for r in src[2:]:
-            if len(r) <= iE:
-                continue
+        for r in b['rows']:
             toks = r[iS].strip().split()
             if not toks:
                 continue
@@ -54,8 +62,9 @@ def main():
             tot += n
             for i, name in stall_cols:
                 stalls[name] += int(r[i] or 0)
+        print('==== ' + b['name'])
         print(f'total warp instructions {tot}' + (f'  ({tot / nodes:.0f} per node)' if nodes else ''))
-        print('opcode mix:', ', '.join(f'{o} {100 * n / tot:.1f}%' for o, n in ops.most_common(14)))
+        print('opcode mix:', ', '.join(f'{o} {100 * n / max(tot, 1):.1f}%' for o, n in ops.most_common(16)))
         st = sum(stalls.values()) or 1
         print('stall samples:', ', '.join(f'{k[6:]} {100 * v / st:.1f}%' for k, v in stalls.most_common(9)))
 
