@@ -348,6 +348,10 @@ const char* cbg_last_error(void) { return g_err; }
 int64_t cbg_launch_count(void) { return g_cbg_launches; }
 
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps) { return cbg_edge_set_impl(impl, warps); }
+int32_t cbg_debug_x2h_trace(int64_t* buf_dev, int32_t max_tiles) {
+  cbg_x2h_tc_set_trace((long long*)buf_dev, max_tiles);
+  return 0;
+}
 int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_from_smem, void* stream) {
   if (!a || !b || !d) { cbg_set_error("cbg_selftest_umma_f16: null argument"); return 1; }
   return cbg_launch_umma_selftest(a, b, d, a_from_smem, (cudaStream_t)stream);
@@ -356,6 +360,7 @@ int32_t cbg_set_option(const char* key, int32_t value) {
   if (key && strcmp(key, "static_fast") == 0) { g_static_fast = value ? 1 : 0; return 0; }
   if (key && strcmp(key, "dyn_sched") == 0) { g_dyn_sched = value ? 1 : 0; return 0; }
   if (key && strcmp(key, "h2x_impl") == 0) return cbg_edge_set_h2x_impl(value);
+  if (key && strcmp(key, "x2h_trace_off") == 0) { cbg_x2h_tc_set_trace(nullptr, 0); return 0; }
   cbg_set_error("cbg_set_option: unknown key '%s'", key ? key : "(null)");
   return 1;
 }

@@ -74,6 +74,8 @@ struct EdgeArgs {
   const float* rc_v;
   int* ticket;           // x2h: optional work counter (zeroed by the caller) for dynamic node scheduling; k uses ticket[0], v ticket[1]
   const unsigned char* fstat;  // x2h with an R-cache: 1 = all 32 in-edges of the node are static (nbr row == its static list)
+  long long* trace;      // x2h_tc debugging: per-tile SM-clock stamps of CTA 0 ([tile][16 events]) or nullptr
+  int trace_tiles;
 };
 int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, const int* snbr, int n_nodes,
                       float* rcache, cudaStream_t st);
@@ -81,6 +83,8 @@ int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st);
 // x2h_tc.cu: both X2H kernels on tcgen05 (A operands in TMEM, f16 hi/lo split); edge order of w = neighbour-table order
 int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st);
 // hardware self-test of the tcgen05 operand conventions (tests): d[128][128] = a[128][32] * b[128][32]^T, f16 inputs
+// debugging: x2h_tc kernels of later launches stamp CTA 0's pipeline events into buf ([max_tiles][16] int64; nullptr = off)
+void cbg_x2h_tc_set_trace(long long* buf, int max_tiles);
 int cbg_launch_umma_selftest(const void* a, const void* b, float* d, int a_from_smem, cudaStream_t st);
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st);
 int cbg_edge_init(void);  // sets max-dynamic-smem attributes once

@@ -101,6 +101,12 @@ __device__ __forceinline__ int node_of(const EdgeArgs& p, int n, int n_list) {
   return p.node_idx ? p.node_idx[nc] : nc;
 }
 
+// pipeline event stamps of CTA 0 (debugging; p.trace == nullptr in production: one predicated-off branch per event)
+#define TC_STAMP(k, ev)                                                                                  \
+  do {                                                                                                   \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (k) < p.trace_tiles) p.trace[(k) * 16 + (ev)] = clock64(); \
+  } while (0)
+
 // =================================================================================================================
 template <bool IS_V>
 __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
@@ -233,12 +239,15 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       mbar_wait(bar(B_PJFULL + c), (uint32_t)((idx / NCH) & 1));
       mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready AND G may be rewritten
       tc_fence_after();
+      if (warp == 0) TC_STAMP(k, 0);
+      if (warp == 4) TC_STAMP(k, 5);
       if (hf == 0) {      // G of tile k + 1, then rotate the prefetch registers (the loads land during S1 below)
         if (k + 1 < n_my) build_g(k + 1, xiC, xjC);
         if (k + 2 < n_my) fetch_geo(iB, jnB);
         if (k + 3 < n_my) { iB = iA; jnB = p.nbr[(size_t)iA * CBG_KMAX + lane]; }
         if (k + 4 < n_my) iA = tile_node(k + 4, wq);
       }
+      if (warp == 0) TC_STAMP(k, 1);
       // ---- S1
       const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
       float v[64];
@@ -259,6 +268,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
           v[4 * j] = a0.x; v[4 * j + 1] = a0.y; v[4 * j + 2] = a1.x; v[4 * j + 3] = a1.y;
         }
       }
+      if (warp == 0) TC_STAMP(k, 2);
       float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 32; ++j) q2 = __ffma2_rn(make_float2(v[2 * j], v[2 * j + 1]), make_float2(v[2 * j], v[2 * j + 1]), q2);
@@ -267,6 +277,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_PJFREE + c));          // this warp is done with the ring chunk
       asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");   // the two half-row warps of this row quarter
+      if (warp == 0) TC_STAMP(k, 3);
       const float qo = s_x[256 * b + 128 * (hf ^ 1) + row];
       const float rstd = 1.f / sqrtf((qs + qo) * (1.f / 128.f) + 1e-5f);
       const float2 rr = make_float2(rstd, rstd);
@@ -294,6 +305,8 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_AREADY + b));
+      if (warp == 0) TC_STAMP(k, 4);
+      if (warp == 4) TC_STAMP(k, 6);
     }
   } else if (warp < 12) {
     // ===================================== EPI (tile k), inputs prefetched one tile ahead ========================
@@ -350,6 +363,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         for (int h = 0; h < 2; ++h) {
           mbar_wait(bar(B_ACC2 + h), (uint32_t)(k & 1));
           tc_fence_after();
+          if (warp == 8) TC_STAMP(k, 7 + h);
           uint32_t r[2][32];
           tmem_ld32_nowait(t_lane + TM_OUT + 64u * h, r[0]);
           tmem_ld32_nowait(t_lane + TM_OUT + 64u * h + 32u, r[1]);
@@ -401,6 +415,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         for (int h = 0; h < 2; ++h) {
           mbar_wait(bar(B_ACC2 + h), (uint32_t)(k & 1));
           tc_fence_after();
+          if (warp == 8) TC_STAMP(k, 7 + h);
 #pragma unroll
           for (int qq = 0; qq < 2; ++qq) {           // 32 columns at a time: features 64h + 32qq + (0..31)
             uint32_t r[32];
@@ -443,6 +458,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
           }
         }
       }
+      if (warp == 8) TC_STAMP(k, 9);
     }
   } else if (warp >= 13) {
     // ===================================== PROD: Pj rows and Pi columns, one tile ahead ===========================
@@ -465,6 +481,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         if (n_my > 1) i_n[q] = tile_node(1, slot0 + q);
       }
     for (int kk = 0; kk < n_my; ++kk) {
+      if (warp == 13) TC_STAMP(kk, 14);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (q >= nslot) continue;
@@ -510,6 +527,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
           if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
         }
       }
+      if (warp == 13) TC_STAMP(kk, 15);
     }
   } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================
@@ -529,6 +547,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         const int bb = kk & 1;
         mbar_wait(bar(B_AREADY + bb), (uint32_t)((kk >> 1) & 1));
         tc_fence_after();
+        TC_STAMP(kk, 12);
         const uint32_t a_hi = tmem + TM_BUF + 128u * (uint32_t)bb, a_lo = a_hi + 64u;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -544,12 +563,14 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
           for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, bh + 16u * ks, IDESC64, 1u);
           umma_commit(bar(B_ACC2 + h));
         }
+        TC_STAMP(kk, 13);
       };
       for (int k = 0; k < n_my; ++k) {
         const int b = k & 1;
         mbar_wait(bar(B_GREADY), (uint32_t)(k & 1));
         mbar_wait(bar(B_PIREADY + b), (uint32_t)((k >> 1) & 1));
         tc_fence_after();
+        TC_STAMP(k, 10);
         const uint32_t d = tmem + TM_BUF + 128u * (uint32_t)b;
 #pragma unroll
         for (int ks = 0; ks < KG_LO / 16; ++ks)
@@ -559,6 +580,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
 #pragma unroll
         for (int ks = 0; ks < KG / 16; ++ks) umma_f16_ts(d, tmem + TM_GHI + 8u * ks, dg_hi + 16u * ks, IDESC128, 1u);
         umma_commit(bar(B_ACC1 + b));
+        TC_STAMP(k, 11);
         if (k > 0) issue_mma2(k - 1);
       }
       issue_mma2(n_my - 1);
@@ -628,6 +650,8 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __half* a, 
 }
 
 int g_tc_sms = 0;
+long long* g_tc_trace = nullptr;
+int g_tc_trace_tiles = 0;
 
 int tc_init() {
   static bool done_dev[CBG_MAX_DEVICES] = {};
@@ -649,14 +673,18 @@ int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st) {
   if (int rc = tc_init()) return rc;
   const int tiles = (a.n_nodes + 3) / 4;
   const int grid = tiles < g_tc_sms ? tiles : g_tc_sms;
+  EdgeArgs ak = a;
+  ak.trace = g_tc_trace; ak.trace_tiles = g_tc_trace_tiles;          // debugging hook: stamps of the k kernel only
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
-  x2h_tc_kernel<false><<<grid, 512, SM_TOTAL, st>>>(a);
+  x2h_tc_kernel<false><<<grid, 512, SM_TOTAL, st>>>(ak);
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
   x2h_tc_kernel<true><<<grid, 512, SM_TOTAL, st>>>(a);
   CBG_LAUNCHED(CBG_K_X2H_V, st);
   return 0;
 }
+
+void cbg_x2h_tc_set_trace(long long* buf, int max_tiles) { g_tc_trace = buf; g_tc_trace_tiles = buf ? max_tiles : 0; }
 
 int cbg_launch_umma_selftest(const void* a, const void* b, float* d, int a_from_smem, cudaStream_t st) {
   const int smem_bytes = 2 * 128 * 32 * 2 + 64;

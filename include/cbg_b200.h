@@ -64,6 +64,9 @@ int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);
  * d[128][128] (fp32) = a[128][32] * b[128][32]^T with f16 row-major device inputs; a_from_smem = 0 feeds A from
  * tensor memory (tcgen05.st, two K-consecutive f16 per column), 1 from shared memory (canonical K-major layout). */
 int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_from_smem, void* stream);
+/* Debugging: later launches of the tcgen05 attention-weight kernel stamp the pipeline events of CTA 0 (SM clock) into
+ * buf_dev[max_tiles][16] (int64, device memory); NULL turns it off.  Process-wide. */
+int32_t cbg_debug_x2h_trace(int64_t* buf_dev, int32_t max_tiles);
 /* Other process-wide switches (testing): "static_fast" = 1 (default; env CBG_STATIC_FAST) lets the X2H kernels skip the
  * coordinate gathers / RBF set-up of nodes whose 32 in-edges are all served from the R-cache (bit-identical results);
  * "dyn_sched" = 1 (default; env CBG_DYN_SCHED): warps of the X2H kernels draw their next node from a work counter instead
