@@ -10,7 +10,7 @@ import os
 from .build import LIB_PATH
 
 _lib = None
-DEFAULT_EDGE_IMPL = 4      # library default of cbg_set_edge_impl (csrc/edge.cu: g_edge_impl)
+DEFAULT_EDGE_IMPL = 6      # library default of cbg_set_edge_impl (csrc/edge.cu: g_edge_impl)
 
 
 class SamplePlan(C.Structure):
@@ -22,7 +22,7 @@ class SamplePlan(C.Structure):
         ('gen_lig', C.c_void_p), ('gen_node', C.c_void_p), ('n_gen', C.c_int32),
         ('mode', C.c_int32), ('k', C.c_int32), ('r_max', C.c_float),
         ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t),
-        ('rcache', C.c_void_p), ('rcache_bytes', C.c_size_t), ('prune', C.c_int32),
+        ('rcache', C.c_void_p), ('rcache_bytes', C.c_size_t), ('prune', C.c_int32), ('static_lists', C.c_int32),
     ]
 
 

@@ -190,9 +190,11 @@ bool static_fast_path() {
 // graph build + gate + layers on an initialised workspace (x4, h valid)
 int run_core(const float* blob, int num_layers, const Workspace& ws, const int* graph_ptr, int n_graphs,
              int max_graph_nodes, long long n_nodes, const int* gen_idx, int n_gen, int mode, int k,
-             float r_max, const float* rcache, const int* cls_idx, int n_cls, bool prune, cudaStream_t st) {
+             float r_max, const float* rcache, const int* cls_idx, int n_cls, bool prune, cudaStream_t st,
+             bool static_lists = false) {
+  static_lists = static_lists || rcache != nullptr;      // the R-cache is indexed by the static lists
   if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
-  if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, rcache ? ws.snbr : nullptr, ws.nbr, st)) return rc;
+  if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, static_lists ? ws.snbr : nullptr, ws.nbr, st)) return rc;
   const float* layers = blob + cbg_layout::kGlobalFloats;
   // Receptive-field pruning (only when the caller consumes nothing but the generated / classified rows):
   // layer l updates h only for the nodes that can still reach such a row through the remaining layers.
@@ -211,7 +213,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
                                   num_layers, ws.depth, ws.order, ws.cnt, fork_depth ? g_aux.s3 : st)) return rc;
   }
   if (fork_depth) CBG_CUDA_OK(cudaEventRecord(g_aux.ev_p, g_aux.s3));
-  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, rcache ? ws.sew : nullptr,
+  if (int rc = cbg_launch_edge_gate(blob, ws.x4, ws.nbr, n_nodes, static_lists ? ws.sew : nullptr,
                                     gate_compact() ? (int*)ws.w : nullptr, ws.ew, st, ws.fstat)) return rc;
   if (fork_depth) CBG_CUDA_OK(cudaStreamWaitEvent(st, g_aux.ev_p, 0));
   cudaStream_t sx = overlap ? g_aux.s2 : st;       // stream of the H2X chain
@@ -562,13 +564,16 @@ int32_t cbg_sample_begin_f32(const cbg_sample_plan* plan, const float* x_nodes, 
   if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = cbg_launch_pack_x4(x_nodes, lig_flag, gen_flag, plan->n_nodes, ws.x4, st)) return rc;
-  if (plan->rcache) {
-    // step-invariant edge terms of the static (non-generated) part of every graph, SURVEY.md Appendix B
-    const int64_t need = cbg_rcache_bytes(plan->n_nodes, plan->num_layers);
-    if ((int64_t)plan->rcache_bytes < need) { cbg_set_error("rcache too small: have %zu bytes, need %lld", plan->rcache_bytes, (long long)need); return 1; }
+  if (plan->rcache || plan->static_lists) {
+    // static-only neighbour lists and their gates: atoms without gen_flag never move
     if (int rc = cbg_launch_knn(ws.x4, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes, CBG_MODE_KNN, CBG_KMAX,
                                 0.f, 1, nullptr, ws.snbr, st)) return rc;
     if (int rc = cbg_launch_edge_gate(plan->blob, ws.x4, ws.snbr, plan->n_nodes, nullptr, nullptr, ws.sew, st)) return rc;
+  }
+  if (plan->rcache) {
+    // step-invariant first-Linear terms of the static edges, for the legacy (non-tcgen05) X2H kernels
+    const int64_t need = cbg_rcache_bytes(plan->n_nodes, plan->num_layers);
+    if ((int64_t)plan->rcache_bytes < need) { cbg_set_error("rcache too small: have %zu bytes, need %lld", plan->rcache_bytes, (long long)need); return 1; }
     if (int rc = cbg_launch_rcache(plan->blob + cbg_layout::kGlobalFloats, plan->num_layers, ws.x4, ws.snbr,
                                    (int)plan->n_nodes, plan->rcache, st)) return rc;
   }
@@ -598,7 +603,7 @@ int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* co
                                     plan->h_static, plan->n_nodes, ws.x4, ws.h, st)) return rc;
   if (int rc = run_core(plan->blob, plan->num_layers, ws, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes,
                         plan->n_nodes, plan->gen_node, plan->n_gen, plan->mode, plan->k, plan->r_max, plan->rcache,
-                        plan->lig_node, plan->n_lig, plan->prune != 0 && prune_enabled(), st)) return rc;
+                        plan->lig_node, plan->n_lig, plan->prune != 0 && prune_enabled(), st, plan->static_lists != 0)) return rc;
   // classifier on ligand rows only; logits scratch lives in the w buffer (free after the layers)
   float* lg = logits ? logits : ws.w;
   if (int rc = cbg_launch_classifier(plan->blob, ws.h, plan->lig_node, plan->n_lig, K, lg, st)) return rc;
@@ -620,7 +625,7 @@ int32_t cbg_sbdd_step_f32(const cbg_sample_plan* plan, const cbg_sbdd_coef* coef
                           const float* x_noise, const float* c_noise, float* x_next, float* c_next,
                           float* x_pred, float* logits, void* stream) {
   if (!plan || !coef) { cbg_set_error("null plan/coef"); return 1; }
-  if (plan->rcache) { cbg_set_error("DiffSBDD moves the pocket every step: the plan must not carry an R-cache"); return 1; }
+  if (plan->rcache || plan->static_lists) { cbg_set_error("DiffSBDD moves the pocket every step: the plan must not carry static lists / an R-cache"); return 1; }
   if (coef->mode != 0 && coef->mode != 1) { cbg_set_error("cbg_sbdd_coef.mode must be 0 or 1"); return 1; }
   Workspace ws;
   if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
@@ -662,7 +667,7 @@ int32_t cbg_bp_step_f32(const cbg_sample_plan* plan, const float* com_blob, int3
   const bool prune = plan->prune != 0 && prune_enabled();
   if (int rc = run_core(plan->blob, plan->num_layers, ws, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes,
                         n_nodes, plan->gen_node, n_gen, plan->mode, plan->k, plan->r_max, plan->rcache,
-                        plan->lig_node, n_lig, prune, st)) return rc;
+                        plan->lig_node, n_lig, prune, st, plan->static_lists != 0)) return rc;
   // scratch in the attention-weight buffer (free after the layers): logits | denoiser output coordinates
   float* lg = logits ? logits : ws.w;
   float* xp = ws.w + align256((size_t)n_lig * K * 4) / 4;

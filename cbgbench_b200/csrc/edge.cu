@@ -1746,7 +1746,7 @@ __global__ void __launch_bounds__(kPairs * 64, 1) h2x_pair_kernel(EdgeArgs p) {
 
 int g_num_sms = 0;
 int g_edge_warps = 12;
-int g_edge_impl = 4;       // 4 (default, fastest measured): x2h_k_mma2 (contraction + RBF on the tensor cores) + SIMT x2h_v; see launch_x2h_mma
+int g_edge_impl = 6;       // 6 (default): tcgen05 kernels (x2h_tc.cu); 0-5: the SIMT / mma.sync generations below (kept as tested alternatives)
 int g_edge_mma_warps = 8;
 int g_h2x_warps = 12;
 int g_h2x_pairs = 4;       // node pairs per CTA of the pair kernel (4: 255 registers, 5: 204)

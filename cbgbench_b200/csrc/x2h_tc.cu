@@ -165,15 +165,17 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     const float* rbf = L + kOffRbf;
     const float c2 = __ldg(rbf + 20) * 1.4426950408889634f;      // exp(c u^2) = 2^(c log2(e) u^2)
 
-    // G row of tile kk -> TMEM: hi 96 f16 (48 columns), lo 80 f16 (40 columns)
-    auto build_g = [&](int kk, const float4 xi, const float4 xj) {
-      // geometry, edge type, Gaussian smearing (x2h_attention.py:46-52, unitransformer.py:88-99); the factor 1024 of
-      // the G scale rides in the exponent
+    // G row of a tile: values in registers (compute_g: geometry, edge type, Gaussian smearing - x2h_attention.py:46-52,
+    // unitransformer.py:88-99; the factor 1024 of the G scale rides in the exponent), then TMEM (store_g): hi 96 f16
+    // (48 columns), lo 80 f16 (40 columns).  The values are computed BEFORE the wait for MMA1 of the current tile, the
+    // stores right after it, so MMA1 of the next tile can be issued as early as possible.
+    uint32_t ghi[10], glo[10];
+    int t_e = 0;
+    auto compute_g = [&](const float4 xi, const float4 xj) {
       const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
       const float d = sqrtf(rx * rx + ry * ry + rz * rz);
       const int fi = node_flags(xi), fj = node_flags(xj);
-      const int t_e = ((fj & 1) ? 0 : 2) + ((fi & 1) ? 0 : 1);
-      uint32_t ghi[10], glo[10];
+      t_e = ((fj & 1) ? 0 : 2) + ((fi & 1) ? 0 : 1);
 #pragma unroll
       for (int mp = 0; mp < 10; ++mp) {
         const float u0 = d - __ldg(rbf + 2 * mp), u1 = d - __ldg(rbf + 2 * mp + 1);
@@ -182,6 +184,8 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g1) : "f"(fmaf(c2 * u1, u1, 10.f)));
         split_pair(g0, g1, ghi[mp], glo[mp]);
       }
+    };
+    auto store_g = [&](int kk) {
 #pragma unroll
       for (int blk = 0; blk < 3; ++blk) {          // 16 columns = 32 f16 per store
         uint32_t w16[16];
@@ -225,7 +229,8 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     if (hf == 0) {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
       const int i0 = tile_node(0, wq);
       fetch_geo(i0, p.nbr[(size_t)i0 * CBG_KMAX + lane]);
-      build_g(0, xiC, xjC);
+      compute_g(xiC, xjC);
+      store_g(0);
       if (n_my > 1) {
         const int i1 = tile_node(1, wq);
         fetch_geo(i1, p.nbr[(size_t)i1 * CBG_KMAX + lane]);
@@ -236,18 +241,19 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     for (int k = 0; k < n_my; ++k) {
       const int b = k & 1;
       const int idx = 4 * k + wq, c = idx % NCH;
-      mbar_wait(bar(B_PJFULL + c), (uint32_t)((idx / NCH) & 1));
-      mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready AND G may be rewritten
-      tc_fence_after();
-      if (warp == 0) TC_STAMP(k, 0);
-      if (warp == 4) TC_STAMP(k, 5);
-      if (hf == 0) {      // G of tile k + 1, then rotate the prefetch registers (the loads land during S1 below)
-        if (k + 1 < n_my) build_g(k + 1, xiC, xjC);
+      if (hf == 0) {      // G values of tile k + 1 into registers, then rotate the prefetch registers (the loads land during S1)
+        if (k + 1 < n_my) compute_g(xiC, xjC);
         if (k + 2 < n_my) fetch_geo(iB, jnB);
         if (k + 3 < n_my) { iB = iA; jnB = p.nbr[(size_t)iA * CBG_KMAX + lane]; }
         if (k + 4 < n_my) iA = tile_node(k + 4, wq);
       }
+      mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready AND G may be rewritten
+      tc_fence_after();
+      if (warp == 0) TC_STAMP(k, 0);
+      if (warp == 4) TC_STAMP(k, 5);
+      if (hf == 0 && k + 1 < n_my) store_g(k + 1);
       if (warp == 0) TC_STAMP(k, 1);
+      mbar_wait(bar(B_PJFULL + c), (uint32_t)((idx / NCH) & 1));
       // ---- S1
       const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
       float v[64];
@@ -461,73 +467,66 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       if (warp == 8) TC_STAMP(k, 9);
     }
   } else if (warp >= 13) {
-    // ===================================== PROD: Pj rows and Pi columns, one tile ahead ===========================
-    // warp 13 serves node slots 0 and 1, warp 14 slot 2, warp 15 slot 3 (no TMEM access here, so no lane-quarter rule).
-    // Per slot and tile: cp.async the node's 32 Pj rows into the ring chunk (row-coalesced 512-byte copies), and write
-    // the node's Pi row into its K column (84 + slot + 4 * tile parity) of the Wg images (hi, lo).
+    // ===================================== PROD: Pi columns and Pj rows, ahead of the tiles =========================
+    // Work item g = 4 * tile + node slot; warp w takes g = w - 13, w - 10, ... (no TMEM access here, so no lane-quarter
+    // rule).  Per item: the node's Pi row -> its K column (84 + slot + 4 * tile parity) of the Wg images (hi, lo) - needs
+    // only MMA1 of tile - 2 to be complete - then cp.async of the node's 32 Pj rows into the ring chunk as soon as the
+    // chunk is free (row-coalesced 512-byte copies).  Inputs are prefetched one item ahead.
     const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
     const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
-    const int slot0 = (warp == 13) ? 0 : warp - 12;
-    const int nslot = (warp == 13) ? 2 : 1;
-    int i_c[2] = {0, 0}, jn_c[2] = {-1, -1}, i_n[2] = {0, 0};
-    float4 pi_c[2];
-    pi_c[0] = pi_c[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < 2; ++q)
-      if (q < nslot) {
-        i_c[q] = tile_node(0, slot0 + q);
-        jn_c[q] = p.nbr[(size_t)i_c[q] * CBG_KMAX + lane];
-        pi_c[q] = ldg4(pi_plane + (size_t)i_c[q] * CBG_H + 4 * lane);
-        if (n_my > 1) i_n[q] = tile_node(1, slot0 + q);
+    const int n_items = 4 * n_my;
+    int g = warp - 13;
+    int i_c = 0, jn_c = -1, i_n = 0;
+    float4 pi_c = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g < n_items) {
+      i_c = tile_node(g >> 2, g & 3);
+      jn_c = p.nbr[(size_t)i_c * CBG_KMAX + lane];
+      pi_c = ldg4(pi_plane + (size_t)i_c * CBG_H + 4 * lane);
+      if (g + 3 < n_items) i_n = tile_node((g + 3) >> 2, (g + 3) & 3);
+    }
+    for (; g < n_items; g += 3) {
+      const int kk = g >> 2, slot = g & 3;
+      if (warp == 13 && slot == 0) TC_STAMP(kk, 14);
+      const int i = i_c, jj = jn_c >= 0 ? jn_c : i;
+      const float4 pi4 = pi_c;
+      if (g + 3 < n_items) {      // next item's loads (its node id was fetched one item earlier)
+        i_c = i_n;
+        jn_c = p.nbr[(size_t)i_n * CBG_KMAX + lane];
+        pi_c = ldg4(pi_plane + (size_t)i_n * CBG_H + 4 * lane);
+        if (g + 6 < n_items) i_n = tile_node((g + 6) >> 2, (g + 6) & 3);
       }
-    for (int kk = 0; kk < n_my; ++kk) {
-      if (warp == 13) TC_STAMP(kk, 14);
+      // Pi column of this tile parity: last read by MMA1(kk - 2)
+      if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
+      else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
+      {
+        const int kcol = 84 + slot + 4 * (kk & 1);
+        const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
+        const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (q >= nslot) continue;
-        const int slot = slot0 + q;
-        const int i = i_c[q], jj = jn_c[q] >= 0 ? jn_c[q] : i;
-        const float4 pi4 = pi_c[q];
-        // start the next tile's loads (node id was fetched one tile earlier: nothing here waits on a dependent load)
-        if (kk + 1 < n_my) {
-          i_c[q] = i_n[q];
-          jn_c[q] = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
-          pi_c[q] = ldg4(pi_plane + (size_t)i_n[q] * CBG_H + 4 * lane);
-          if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
+        for (int e = 0; e < 4; ++e) {
+          const int nn = 4 * lane + e;
+          const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
+          const __half hh = __float2half_rn(pv[e]);
+          const __half hl = __float2half_rn(pv[e] - __half2float(hh));
+          *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
+          *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
         }
-        {   // Pj rows
-          const int idx = 4 * kk + slot, c = idx % NCH;
-          if (idx >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)(((idx / NCH) - 1) & 1));
-          const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)lane;
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
+      }
+      {   // Pj rows
+        const int c = g % NCH;
+        if (g >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)(((g / NCH) - 1) & 1));
+        const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)lane;
 #pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const int jr = __shfl_sync(CBG_FULL, jj, r);
-            cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
-          }
-          cp_async_arrive(bar(B_PJFULL + c));
+        for (int r = 0; r < 32; ++r) {
+          const int jr = __shfl_sync(CBG_FULL, jj, r);
+          cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
         }
-        // Pi column of this tile parity: last read by MMA1(kk - 2)
-        if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
-        else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
-        {
-          const int kcol = 84 + slot + 4 * (kk & 1);
-          const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
-          const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int nn = 4 * lane + e;
-            const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
-            const __half hh = __float2half_rn(pv[e]);
-            const __half hl = __float2half_rn(pv[e] - __half2float(hh));
-            *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
-            *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
-        }
+        cp_async_arrive(bar(B_PJFULL + c));
       }
-      if (warp == 13) TC_STAMP(kk, 15);
+      if (warp == 13 && slot == 0) TC_STAMP(kk, 15);
     }
   } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================

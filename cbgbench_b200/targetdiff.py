@@ -99,9 +99,13 @@ class BaseDiffB200(nn.Module):
         self._ws = _Workspace()
         self._rc = _Workspace()
         self.last_launches = 0
-        # R-cache: step-invariant first-Linear terms of edges between non-generated atoms are computed
-        # once per batch and streamed from HBM (2*L*N*16 KB).  CBG_RCACHE=0 / use_rcache=False turns it off.
-        self.use_rcache = self.allow_rcache and os.environ.get('CBG_RCACHE', '1') != '0'
+        # Static lists: atoms without gen_flag never move, so their static-only neighbour lists / edge gates are built
+        # once per batch (incremental kNN, cached gates; exact).  On by default wherever the pocket is static.
+        self.use_static_lists = self.allow_rcache and os.environ.get('CBG_STATIC_LISTS', '1') != '0'
+        # R-cache (legacy, for the non-tcgen05 X2H kernels only): step-invariant first-Linear terms of static edges,
+        # computed once per batch and streamed from HBM (2*L*N*16 KB).  The default tcgen05 kernels recompute these
+        # terms on the tensor cores and never read it, so it is off unless CBG_RCACHE=1 / use_rcache=True.
+        self.use_rcache = self.allow_rcache and os.environ.get('CBG_RCACHE', '0') == '1'
         # receptive-field pruning of the per-step denoiser (exact for the sampled ligand rows)
         self.use_prune = os.environ.get('CBG_PRUNE', '1') != '0'
 
@@ -179,6 +183,9 @@ class BaseDiffB200(nn.Module):
             have = self._rc.buf.numel() if self._rc.buf is not None and self._rc.buf.device == dev else 0
             free_b, _ = torch.cuda.mem_get_info(dev)
             if rc_bytes + 256 > have and rc_bytes > 0.6 * (free_b + have):
+                import warnings
+                warnings.warn(f'R-cache of {rc_bytes / 2**30:.1f} GiB does not fit ({free_b / 2**30:.1f} GiB free): the legacy X2H '
+                              'kernels recompute the static first-Linear terms instead (slower)')
                 rc_bytes = 0          # batch too large for the cache on this GPU: fall back to recomputing the terms
             else:
                 rc_ptr, rc_bytes = self._rc.get(rc_bytes, dev)
@@ -189,7 +196,8 @@ class BaseDiffB200(nn.Module):
             lig_node=lig_node.data_ptr(), n_lig=n_lig, gen_lig=gen_lig8.data_ptr(),
             gen_node=gen_node.data_ptr() if n_gen else None, n_gen=n_gen,
             mode=den.mode_id, k=den.cut_off, r_max=den.r_max, workspace=ws_ptr, workspace_bytes=ws_have,
-            rcache=rc_ptr, rcache_bytes=rc_bytes, prune=1 if self.use_prune else 0)
+            rcache=rc_ptr, rcache_bytes=rc_bytes, prune=1 if self.use_prune else 0,
+            static_lists=1 if (self.use_static_lists and self.allow_rcache) else 0)
         with torch.cuda.device(dev):
             _lib.check(L.cbg_sample_begin_f32(C.byref(plan), x_nodes.data_ptr(), lig_nodes.data_ptr(),
                                               gen_nodes_flag.data_ptr(), _lib.stream_ptr(dev)))

@@ -181,6 +181,10 @@ typedef struct cbg_sample_plan {
   int32_t prune;                /* 1: receptive-field pruning - layer l only updates the nodes that can still
                                    influence a generated / ligand atom through the remaining layers (exact for
                                    everything cbg_sample_step_f32 returns; intermediate h of other nodes is skipped) */
+  int32_t static_lists;         /* 1: atoms without gen_flag never move, so cbg_sample_begin_f32 builds their static-only
+                                   neighbour lists and edge gates once per batch; every step's neighbour search is then
+                                   incremental and static edges reuse their gate (exact).  Implied by rcache != NULL.
+                                   Must be 0 for samplers that move the pocket (DiffSBDD). */
 } cbg_sample_plan;
 
 typedef struct cbg_step_coef {  /* scheduler table entries of the current step (host scalars) */

@@ -499,7 +499,7 @@ def edge_impl_reset():
     yield
     _lib.check(_lib.lib().cbg_set_edge_impl(1, 8))
     _lib.check(_lib.lib().cbg_set_edge_impl(0, 12))
-    _lib.check(_lib.lib().cbg_set_edge_impl(4, 0))     # library default
+    _lib.check(_lib.lib().cbg_set_edge_impl(_lib.DEFAULT_EDGE_IMPL, 0))     # library default
 
 
 @pytest.mark.parametrize('case', FORWARD_CASES, ids=[c[0] for c in FORWARD_CASES])
