@@ -302,10 +302,6 @@ def run_b200(args):
                    for k, v in prof.items() if v[1]}
         dom = max(('x2h_k', 'x2h_v'), key=lambda k: prof[k][0])
         dom_ms = prof[dom][0] / prof[dom][1]
-        # ALGORITHMIC bytes per launch of the fused X2H kernels, per node:
-        #   x2h_k: Pj_k + Pi_k + q rows (3 x 512 B) + nbr (128) + e_w (128) + x (16) read, w (2048) written
-        #   x2h_v: Pj_v + Pi_v (2 x 512) + nbr + e_w + x (272) + w (2048) + h (512) read, h (512) written
-        #   + the node's R-cache block (32 slots x 512 B) streamed for static (non-generated) nodes
         # rows one launch processes: with receptive-field pruning layer l only updates the nodes that can still reach a
         # sampled atom, so the per-launch average over the layers is what the measured launch time corresponds to
         n_layers = state['plan'].num_layers
@@ -315,31 +311,40 @@ def run_b200(args):
             cnt = (ctypes.c_int32 * (n_layers + 1))()
             _lib.check(L.cbg_sample_prune_counts_host(ctypes.byref(state['plan']), cnt, _lib.stream_ptr(dev)))
             rows = sum(cnt[l + 1] for l in range(n_layers)) / n_layers
-        rows_static = max(rows - state['plan'].n_gen, 0.0)       # generated atoms are in every layer's list
-        rc_bytes = 32 * 512 * rows_static if model.use_rcache else 0
-        per_node = {'x2h_k': 3 * 512 + 272 + 2048, 'x2h_v': 2 * 512 + 272 + 2048 + 1024}[dom]
-        alg_bytes = per_node * rows + rc_bytes
-        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        # useful fp32 work of the same launch (query-folded / aggregated second Linears; the RBF mat-vec only
-        # for the edges that are not served from the R-cache is NOT counted: lower bound of useful FLOPs)
-        flops_node = {'x2h_k': 2 * (128 * 128 + 32 * 128 * 16), 'x2h_v': 2 * (32 * 128 * 16 + 128 * 128)}[dom]
-        sm_max = (clocks.summary()['sm_max_mhz'] or peaks.get('sm_max_mhz') or 1965.0)
-        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
+            rows_src = sum(cnt[l] for l in range(n_layers)) / n_layers          # rows whose Pj plane a launch may gather
+        else:
+            rows_src = rows
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')      # dram bytes/launch from the last ncu --set full capture
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = (json.load(f).get(dom) or {}).get('dram_bytes_per_launch')
-        roofline = {'kernel': dom, 'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                    'frac': achieved / peaks['hbm_gbs'], 'peak_source': f'{peak_kind} copy bandwidth (MEASURED_PEAKS.json)',
-                    'traffic': traffic, 'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms': dom_ms,
-                    'note': 'per-edge k/v tensors are never materialised; the kernel streams node planes + the R-cache; bytes are '
-                            'counted for the rows a launch really processes (receptive-field pruning); the loaded unit is the '
-                            'L1/shared data pipe, not DRAM (DESIGN.md section 5)',
-                    'rows_per_launch': rows,
-                    'fp32': {'achieved_tflops': flops_node * rows / (dom_ms * 1e-3) / 1e12, 'peak_tflops': fp32_peak,
-                             'frac': flops_node * rows / (dom_ms * 1e-3) / 1e12 / fp32_peak,
-                             'peak_source': 'nominal 148 SM x 128 FMA x 2 x max SM clock'}}
+                traffic = (json.load(f).get(dom + '_tc') or {}).get('dram_bytes_per_launch')
+        # The fused X2H kernels (csrc/x2h_tc.cu) are TENSOR-bound, not HBM-bound: per 128-edge tile
+        # they issue 17 + 48 tcgen05 MMAs, nothing of size [E, 128] crosses HBM.
+        #   executed tensor FLOPs per tile = 17 x (128 x 128 x 16 x 2) + 48 x (128 x 64 x 16 x 2); the (hi, lo) f16 split
+        #   runs three f16 products per fp32 product and pads K = 84 to 96
+        #   algorithmic (fp32-equivalent) FLOPs per edge and kernel = (84 + 128) x 128 x 2   (first-Linear RBF part + second Linear)
+        #   algorithmic HBM bytes per launch: node planes read once + per-row neighbour / gate / coordinate rows + w / h
+        tiles = rows / 4.0
+        exec_flops = tiles * (17 * 128 * 128 * 16 * 2 + 48 * 128 * 64 * 16 * 2)
+        alg_flops = rows * 32 * (84 + 128) * 128 * 2
+        per_row = {'x2h_k': 512 + 512 + 128 + 128 + 16 + 2048, 'x2h_v': 512 + 128 + 16 + 2048 + 1024}[dom]
+        alg_bytes = per_row * rows + 512 * rows_src
+        tf_peak = peaks.get('bf16_tflops_sustained') or peaks.get('bf16_tflops')
+        ach_exec = exec_flops / (dom_ms * 1e-3) / 1e12
+        ach_alg = alg_flops / (dom_ms * 1e-3) / 1e12
+        hbm = alg_bytes / (dom_ms * 1e-3) / 1e9
+        roofline = {'kernel': dom + ' (x2h_tc_kernel)', 'bound': 'tensor', 'achieved': ach_alg, 'peak': tf_peak / 3.0, 'unit': 'TFLOP/s',
+                    'frac': ach_alg / (tf_peak / 3.0), 'traffic': traffic,
+                    'peak_source': f'{peak_kind} bf16 cuBLAS TFLOP/s sustained (MEASURED_PEAKS.json: {tf_peak}) / 3: the fp32-accurate '
+                                   '(hi, lo) f16 split needs three tensor-core products per algorithmic product',
+                    'algorithmic_flops_per_launch': alg_flops, 'launch_ms': dom_ms, 'rows_per_launch': rows,
+                    'executed': {'tflops': ach_exec, 'peak_tflops': tf_peak, 'frac': ach_exec / tf_peak,
+                                 'note': 'tcgen05 FLOPs actually issued (3 products, K padded 84 -> 96)'},
+                    'hbm': {'algorithmic_bytes_per_launch': alg_bytes, 'achieved_gbs': hbm, 'peak_gbs': peaks['hbm_gbs'],
+                            'frac': hbm / peaks['hbm_gbs'],
+                            'note': "the north-star's 60 % HBM target assumed per-edge k/v tensors crossing HBM (9.9 GB/step); they are "
+                                    'never materialised, the kernel moves ~4 KB per node and is bounded by the tensor pipe'}}
 
     # ---- end to end through the public API: host batch -> model.sample() -> host trajectory -------
     e2e = None

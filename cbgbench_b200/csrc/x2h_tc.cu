@@ -28,8 +28,8 @@
 //                         node's 32 edges through a shared-memory transpose, w = alpha * e_w;
 //                         v: (v + b1v) * w, sum over the node's 32 edges, h_i += .
 //   warp 12     MMA       one lane issues every tcgen05.mma / commit (fully unrolled, tile-invariant descriptors)
-//   warps 13-15 PROD      one tile ahead: cp.async of every node's 32 Pj rows into a 5-chunk ring; the node's Pi row
-//                         into its K column of the Wg images
+//   warps 13-14 PROD      one tile ahead, two node slots each: cp.async of the node's 32 Pj rows into the slot's chunk;
+//                         the node's Pi row into its K column of the Wg images
 // Pipelining: TMEM holds two pre/activation buffers and two 64-column output halves, so MMA1 of tile t+1 and MMA2 of
 // tile t-1 run while S1 works on tile t and EPI on tile t-1.
 #include <math.h>
@@ -62,7 +62,8 @@ constexpr float kInvOut = 1.f / 4096.f;  // W1 image is scaled by 64 -> out accu
 // ---- shapes -----------------------------------------------------------------------------------------------------
 constexpr int KG = 96;                   // K of MMA1 (84 used + 8 node one-hot columns (2 tile parities x 4) + 4 zero)
 constexpr int KG_LO = 80;                // the lo part of G is non-zero only in the RBF columns
-constexpr int NCH = 5;                   // Pj ring: chunks of 32 rows (a tile uses 4; the 5th decouples the warps)
+constexpr int NCH = 4;                   // Pj buffers: one 32-row chunk per node slot of a tile (refilled for tile t+1 as soon
+                                         // as the slot's S1 warps have consumed tile t)
 constexpr uint32_t PJ_ROW = 528;         // padded row stride: 16-byte row-per-lane reads are bank-conflict free
 constexpr uint32_t PJ_CHUNK = 32 * PJ_ROW;
 constexpr uint32_t W1_IMG = 128 * 128 * 2;            // one (hi | lo) image, bytes
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     }
     for (int k = 0; k < n_my; ++k) {
       const int b = k & 1;
-      const int idx = 4 * k + wq, c = idx % NCH;
+      const int c = wq;                                   // this quarter's Pj chunk, refilled once per tile
       if (hf == 0) {      // G values of tile k + 1 into registers, then rotate the prefetch registers (the loads land during S1)
         if (k + 1 < n_my) compute_g(xiC, xjC);
         if (k + 2 < n_my) fetch_geo(iB, jnB);
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       if (warp == 4) TC_STAMP(k, 5);
       if (hf == 0 && k + 1 < n_my) store_g(k + 1);
       if (warp == 0) TC_STAMP(k, 1);
-      mbar_wait(bar(B_PJFULL + c), (uint32_t)((idx / NCH) & 1));
+      mbar_wait(bar(B_PJFULL + c), (uint32_t)(k & 1));
       // ---- S1
       const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
       float v[64];
@@ -466,67 +467,71 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       }
       if (warp == 8) TC_STAMP(k, 9);
     }
-  } else if (warp >= 13) {
-    // ===================================== PROD: Pi columns and Pj rows, ahead of the tiles =========================
-    // Work item g = 4 * tile + node slot; warp w takes g = w - 13, w - 10, ... (no TMEM access here, so no lane-quarter
-    // rule).  Per item: the node's Pi row -> its K column (84 + slot + 4 * tile parity) of the Wg images (hi, lo) - needs
-    // only MMA1 of tile - 2 to be complete - then cp.async of the node's 32 Pj rows into the ring chunk as soon as the
-    // chunk is free (row-coalesced 512-byte copies).  Inputs are prefetched one item ahead.
+  } else if (warp == 13 || warp == 14) {
+    // ===================================== PROD: Pj rows and Pi columns, ahead of the tiles =========================
+    // Warp 13 serves node slots 0 and 2, warp 14 slots 1 and 3 (no TMEM access here, so no lane-quarter rule).  Every
+    // chunk / barrier has ONE producer warp that walks the tiles in order: a parity wait is only sound while the waiter
+    // can never be two phases ahead of the barrier, which a shared ring with several producers does not guarantee.
+    // Per (tile, slot): cp.async of the node's 32 Pj rows into the slot's chunk as soon as the slot's S1 warps have
+    // consumed the previous tile (row-coalesced 512-byte copies), then the node's Pi row -> its K column
+    // (84 + slot + 4 * tile parity) of the Wg images (hi, lo), which MMA1 of tile - 2 was the last to read.
     const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
     const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
-    const int n_items = 4 * n_my;
-    int g = warp - 13;
-    int i_c = 0, jn_c = -1, i_n = 0;
-    float4 pi_c = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (g < n_items) {
-      i_c = tile_node(g >> 2, g & 3);
-      jn_c = p.nbr[(size_t)i_c * CBG_KMAX + lane];
-      pi_c = ldg4(pi_plane + (size_t)i_c * CBG_H + 4 * lane);
-      if (g + 3 < n_items) i_n = tile_node((g + 3) >> 2, (g + 3) & 3);
-    }
-    for (; g < n_items; g += 3) {
-      const int kk = g >> 2, slot = g & 3;
-      if (warp == 13 && slot == 0) TC_STAMP(kk, 14);
-      const int i = i_c, jj = jn_c >= 0 ? jn_c : i;
-      const float4 pi4 = pi_c;
-      if (g + 3 < n_items) {      // next item's loads (its node id was fetched one item earlier)
-        i_c = i_n;
-        jn_c = p.nbr[(size_t)i_n * CBG_KMAX + lane];
-        pi_c = ldg4(pi_plane + (size_t)i_n * CBG_H + 4 * lane);
-        if (g + 6 < n_items) i_n = tile_node((g + 6) >> 2, (g + 6) & 3);
-      }
-      // Pi column of this tile parity: last read by MMA1(kk - 2)
-      if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
-      else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
-      {
-        const int kcol = 84 + slot + 4 * (kk & 1);
-        const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
-        const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
+    const int s0 = warp - 13;                       // slots s0 and s0 + 2
+    int i_c[2], jn_c[2], i_n[2];
+    float4 pi_c[2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int nn = 4 * lane + e;
-          const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
-          const __half hh = __float2half_rn(pv[e]);
-          const __half hl = __float2half_rn(pv[e] - __half2float(hh));
-          *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
-          *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
+    for (int q = 0; q < 2; ++q) {
+      i_c[q] = tile_node(0, s0 + 2 * q);
+      jn_c[q] = p.nbr[(size_t)i_c[q] * CBG_KMAX + lane];
+      pi_c[q] = ldg4(pi_plane + (size_t)i_c[q] * CBG_H + 4 * lane);
+      i_n[q] = n_my > 1 ? tile_node(1, s0 + 2 * q) : 0;
+    }
+    for (int kk = 0; kk < n_my; ++kk) {
+      if (warp == 13) TC_STAMP(kk, 14);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int slot = s0 + 2 * q;
+        const int i = i_c[q], jj = jn_c[q] >= 0 ? jn_c[q] : i;
+        const float4 pi4 = pi_c[q];
+        if (kk + 1 < n_my) {      // next tile's loads (its node id was fetched one tile earlier: no dependent load is waited on)
+          i_c[q] = i_n[q];
+          jn_c[q] = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
+          pi_c[q] = ldg4(pi_plane + (size_t)i_n[q] * CBG_H + 4 * lane);
+          if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
-      }
-      {   // Pj rows
-        const int c = g % NCH;
-        if (g >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)(((g / NCH) - 1) & 1));
-        const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)lane;
+        {   // Pj rows
+          if (kk >= 1) mbar_wait(bar(B_PJFREE + slot), (uint32_t)((kk - 1) & 1));
+          const uint32_t dst = sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + 16u * (uint32_t)lane;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const int jr = __shfl_sync(CBG_FULL, jj, r);
-          cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
+          for (int r = 0; r < 32; ++r) {
+            const int jr = __shfl_sync(CBG_FULL, jj, r);
+            cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
+          }
+          cp_async_arrive(bar(B_PJFULL + slot));
         }
-        cp_async_arrive(bar(B_PJFULL + c));
+        // Pi column of this tile parity: last read by MMA1(kk - 2), complete because this slot's S1(kk - 1) has run
+        if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
+        else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
+        {
+          const int kcol = 84 + slot + 4 * (kk & 1);
+          const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
+          const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int nn = 4 * lane + e;
+            const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
+            const __half hh = __float2half_rn(pv[e]);
+            const __half hl = __float2half_rn(pv[e] - __half2float(hh));
+            *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
+            *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
+        }
       }
-      if (warp == 13 && slot == 0) TC_STAMP(kk, 15);
+      if (warp == 13) TC_STAMP(kk, 15);
     }
   } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================
@@ -673,7 +678,8 @@ int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st) {
   const int tiles = (a.n_nodes + 3) / 4;
   const int grid = tiles < g_tc_sms ? tiles : g_tc_sms;
   EdgeArgs ak = a;
-  ak.trace = g_tc_trace; ak.trace_tiles = g_tc_trace_tiles;          // debugging hook: stamps of the k kernel only
+  ak.trace = g_tc_trace; ak.trace_tiles = g_tc_trace_tiles;          // debugging hook: one-shot, the next k kernel launch only
+  g_tc_trace = nullptr;
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
   x2h_tc_kernel<false><<<grid, 512, SM_TOTAL, st>>>(ak);
   CBG_LAUNCHED(CBG_K_X2H_K, st);

@@ -34,7 +34,7 @@ torch.cuda.synchronize()
 NT = 40
 buf = torch.zeros((NT, 16), dtype=torch.int64, device=dev)
 _lib.check(L.cbg_debug_x2h_trace(buf.data_ptr(), NT))
-model.run_steps(state, [996], X, Cc)          # 9 launches overwrite each other: the last layer's stamps remain
+model.run_steps(state, [996], X, Cc)          # one-shot hook: the first (layer 0) attention-weight launch of this step
 torch.cuda.synchronize()
 _lib.check(L.cbg_debug_x2h_trace(None, 0))
 t = buf.cpu().numpy()
