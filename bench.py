@@ -48,6 +48,10 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-steps', type=int, default=3)
+    ap.add_argument('--scaling', default=None, choices=['weak', 'strong'],
+                    help="weak: every rank gets the workload's pockets (default for c2/c3/c1); strong: ONE global batch is "
+                         'partitioned over the ranks by atom count (default for c5: 256 ragged pockets over the box)')
+    ap.add_argument('--global-graphs', type=int, default=None, help='pockets of the global batch for --scaling strong')
     return ap.parse_args()
 
 
@@ -243,7 +247,24 @@ def run_b200(args):
     L = _lib.lib()
 
     B, n_prot, n_lig, gen_mode, enc, desc = WORKLOADS[args.workload]
-    batch, _ = workload_batch(args.workload, rank)
+    scaling = args.scaling or ('strong' if args.workload == 'c5' else 'weak')
+    shard = None
+    if scaling == 'strong':
+        # ONE global batch, identical on every rank (same seed), partitioned by atom count (LPT, cbgbench_b200/sharding.py);
+        # every rank samples its share with no communication, the final states meet in one all-gather
+        from cbgbench_b200 import sharding
+        total = args.global_graphs or (256 if args.workload == 'c5' else B)
+        full, _ = workload_batch(args.workload, 0, total)
+        sizes = sharding.graph_sizes(full).tolist()
+        parts = sharding.assign_graphs(sizes, world)
+        batch = sharding.take_graphs(full, parts[rank])
+        lig_per_graph = torch.bincount(full['ligand_element_batch'], minlength=total)
+        shard = {'parts': parts, 'counts': [int(lig_per_graph[torch.as_tensor(p_, dtype=torch.long)].sum()) for p_ in parts],
+                 'atoms': [int(sum(sizes[g] for g in p_)) for p_ in parts], 'total_graphs': total}
+        B_total, B = total, len(parts[rank])
+    else:
+        batch, _ = workload_batch(args.workload, rank)
+        B_total = B * world
     model = TargetDiffB200(synthetic.targetdiff_config(num_steps=T_STEPS, **enc))
     model.load_state_dict(synthetic.seeded_state_dict(model, seed=0), strict=True)
     model = model.to(dev).eval()
@@ -285,7 +306,8 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item())
-    value = (B * world) / (T_STEPS * ms_per_step * 1e-3)
+    ms_rank = sum(step_ms) / len(step_ms)
+    value = B_total / (T_STEPS * ms_per_step * 1e-3)
 
     # ---- per-kernel CUDA-event profile of a few more steps (roofline of the dominant kernel) ------
     prof = None
@@ -356,26 +378,26 @@ def run_b200(args):
         model.sample(host_batch, num_steps=2, traj_mode='final')
         if world > 1:
             from cbgbench_b200 import sharding
-            gid0 = (batch['ligand_element_batch'] + rank * B).to(dev)
+            gid_map = (torch.as_tensor(shard['parts'][rank], dtype=torch.long) if shard else torch.arange(B) + rank * B).to(dev)
+            counts = shard['counts'] if shard else [n_lig_tot] * world
+            gid0 = gid_map[batch['ligand_element_batch'].to(dev)]
             sharding.gather_final(torch.zeros(n_lig_tot, 3, device=dev), torch.zeros(n_lig_tot, dtype=torch.int64, device=dev),
-                                  gid0, counts=[n_lig_tot] * world)
+                                  gid0, counts=counts)
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         traj = model.sample(host_batch, num_steps=steps_e2e)          # H2D + steps + D2H of the trajectory
         t_last = T_STEPS - steps_e2e
-        x_fin, v_fin = traj[t_last][0], traj[t_last][1].argmax(-1)    # what sample.py consumes (traj[0] at full T)
-        if world > 1:                                                  # the single gather of final coordinates
-            from cbgbench_b200 import sharding
-            gid = (batch['ligand_element_batch'] + rank * B).to(dev)
-            sharding.gather_final(x_fin.to(dev), v_fin.to(dev), gid, counts=[n_lig_tot] * world)
+        if world > 1:                                                  # the single gather of final coordinates, device to device:
+            xd, cd, _ = traj[t_last - 1]                               # the state after the last step is still on the GPU (traj[-1] at full T)
+            sharding.gather_final(xd, cd.argmax(-1), gid0, counts=counts)
         ev1.record()
         barrier()
         e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         d2h = sum(traj[t][0].numel() * 4 + traj[t][1].numel() * 4 for t in traj if t >= 0)
-        e2e_value = (B * world) / (float(e2e_ms.item()) * 1e-3) * (steps_e2e / T_STEPS)
+        e2e_value = B_total / (float(e2e_ms.item()) * 1e-3) * (steps_e2e / T_STEPS)
         e2e = {'value': e2e_value, 'unit': 'ligands/s', 'h2d_bytes_per_step': h2d / steps_e2e,
                'd2h_bytes_per_step': d2h / steps_e2e, 'seconds': float(e2e_ms.item()) * 1e-3, 'denoise_steps': steps_e2e,
                'api': 'TargetDiffB200.sample(host batch) -> traj (CPU), H2D/D2H and final gather inside the timed region'}
@@ -404,17 +426,28 @@ def run_b200(args):
                 ref_gpu = {'unavailable': repr(e)[:200]}
             torch.set_grad_enabled(False)
 
+    ranks = None
+    if world > 1:
+        mine = {'rank': rank, 'graphs': B, 'nodes': int(N), 'ms_per_step': ms_rank}
+        allr = [None] * world
+        dist.all_gather_object(allr, mine)
+        ranks = allr
+        slow = max(allr, key=lambda r_: r_['ms_per_step'])
+        ranks_summary = {'per_rank': allr, 'limiting_rank': slow['rank'],
+                         'imbalance': slow['ms_per_step'] / (sum(r_['ms_per_step'] for r_ in allr) / world)}
     if rank == 0:
         line = {
             'metric': 'ligands/sec sampled (1000-step denoise, batch 64)', 'value': value, 'unit': 'ligands/s',
             'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{args.workload}: {desc}', 'graphs_per_gpu': B, 'nodes_per_gpu': N,
+            'higher_is_better': True, 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{args.workload}: {desc}', 'graphs_per_gpu': B, 'graphs_total': B_total, 'nodes_per_gpu': N,
                        'denoise_steps_per_ligand': T_STEPS, 'step': 'one denoise step of the whole batch',
                        'l2': 'flushed (256 MiB write) between timed steps', 'parallelism': f'dp{world} (pockets sharded, no data-path collective)'},
             'clocks': clocks.summary(), 'gpu_launches': int(gpu_launches), 'e2e': e2e, 'roofline': roofline,
             'cpu_baseline': cpu, 'reference_gpu': ref_gpu, 'kernels': kernels,
         }
+        if ranks is not None:
+            line['ranks'] = ranks_summary
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

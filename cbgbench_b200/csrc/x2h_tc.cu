@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
     mbar_init(bar(B_GREADY), 4);
-    mbar_init(bar(B_PIREADY), 4);
-    mbar_init(bar(B_PIREADY + 1), 4);
+    mbar_init(bar(B_PIREADY), 2);
+    mbar_init(bar(B_PIREADY + 1), 2);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(B_ACC1 + b), 1);
       mbar_init(bar(B_AREADY + b), 8);
@@ -489,10 +489,17 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     }
     for (int kk = 0; kk < n_my; ++kk) {
       if (warp == 13) TC_STAMP(kk, 14);
+      int jj_s[2];
+      // ---- Pi columns of both slots first: nothing is in flight, so the proxy fence is cheap, and MMA1 of this tile
+      // never waits on the producers.  The column of this tile parity was last read by MMA1(kk - 2), which is complete
+      // because this warp's slots have already consumed tile kk - 2 (the Pj wait of the previous iteration).
+      if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
+      else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int slot = s0 + 2 * q;
-        const int i = i_c[q], jj = jn_c[q] >= 0 ? jn_c[q] : i;
+        const int i = i_c[q];
+        jj_s[q] = jn_c[q] >= 0 ? jn_c[q] : i;
         const float4 pi4 = pi_c[q];
         if (kk + 1 < n_my) {      // next tile's loads (its node id was fetched one tile earlier: no dependent load is waited on)
           i_c[q] = i_n[q];
@@ -500,36 +507,34 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
           pi_c[q] = ldg4(pi_plane + (size_t)i_n[q] * CBG_H + 4 * lane);
           if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
         }
-        {   // Pj rows
-          if (kk >= 1) mbar_wait(bar(B_PJFREE + slot), (uint32_t)((kk - 1) & 1));
-          const uint32_t dst = sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + 16u * (uint32_t)lane;
-#pragma unroll 8
-          for (int r = 0; r < 32; ++r) {
-            const int jr = __shfl_sync(CBG_FULL, jj, r);
-            cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
-          }
-          cp_async_arrive(bar(B_PJFULL + slot));
-        }
-        // Pi column of this tile parity: last read by MMA1(kk - 2), complete because this slot's S1(kk - 1) has run
-        if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
-        else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
-        {
-          const int kcol = 84 + slot + 4 * (kk & 1);
-          const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
-          const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
+        const int kcol = 84 + slot + 4 * (kk & 1);
+        const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
+        const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int nn = 4 * lane + e;
-            const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
-            const __half hh = __float2half_rn(pv[e]);
-            const __half hl = __float2half_rn(pv[e] - __half2float(hh));
-            *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
-            *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
+        for (int e = 0; e < 4; ++e) {
+          const int nn = 4 * lane + e;
+          const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
+          const __half hh = __float2half_rn(pv[e]);
+          const __half hl = __float2half_rn(pv[e] - __half2float(hh));
+          *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
+          *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
         }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
+      // ---- Pj rows of both slots, each as soon as the slot's S1 warps have consumed the previous tile
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int slot = s0 + 2 * q;
+        if (kk >= 1) mbar_wait(bar(B_PJFREE + slot), (uint32_t)((kk - 1) & 1));
+        const uint32_t dst = sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + 16u * (uint32_t)lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int jr = __shfl_sync(CBG_FULL, jj_s[q], r);
+          cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
+        }
+        cp_async_arrive(bar(B_PJFULL + slot));
       }
       if (warp == 13) TC_STAMP(kk, 15);
     }
