@@ -75,7 +75,8 @@ constexpr uint32_t SM_WG = SM_W1 + 2 * W1_IMG;
 constexpr uint32_t SM_PJ = SM_WG + 2 * WG_IMG;
 constexpr uint32_t SM_LN = SM_PJ + NCH * PJ_CHUNK;    // gamma * 64 [128] | beta * 64 [128]
 constexpr uint32_t SM_B1 = SM_LN + 1024;              // b1v [128]
-constexpr uint32_t SM_XCH = SM_B1 + 512;              // sum-of-squares exchange between the two half-row S1 warps
+constexpr uint32_t SM_RBF = SM_B1 + 512;              // Gaussian offsets [20] + coeff
+constexpr uint32_t SM_XCH = SM_RBF + 128;              // sum-of-squares exchange between the two half-row S1 warps
 constexpr uint32_t SM_QBUF = SM_XCH + 2048;             // EPI: [warp][tile parity][128] q row of the warp's node
 constexpr uint32_t SM_SOFT = SM_QBUF + 4096;            // EPI: [warp][32 edges][17] logits <-> weights transpose
 constexpr uint32_t SM_VRED = SM_QBUF;                   // EPI of the v kernel (aliases QBUF / SOFT): [warp][32 edges][36] transpose
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
-    mbar_init(bar(B_GREADY), 4);
+    mbar_init(bar(B_GREADY), 8);
     mbar_init(bar(B_PIREADY), 2);
     mbar_init(bar(B_PIREADY + 1), 2);
     for (int b = 0; b < 2; ++b) {
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     const float* ln = L + (IS_V ? kOffVLn : kOffKLn);
     if (tid < 256) s_ln[tid] = ln[tid] * kScaleA;
     else if (tid < 384) s_b1[tid - 256] = IS_V ? L[kOffVB1 + tid - 256] : 0.f;
+    else if (tid < 384 + 24) reinterpret_cast<float*>(smem + SM_RBF)[tid - 384] = L[kOffRbf + tid - 384];
   }
   tc_fence_before();
   __syncthreads();
@@ -164,14 +166,16 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     const float* s_ln = reinterpret_cast<const float*>(smem + SM_LN) + 64 * hf;
     float* s_x = reinterpret_cast<float*>(smem + SM_XCH);
     const int row = 32 * wq + lane;
-    const float* rbf = L + kOffRbf;
-    const float c2 = __ldg(rbf + 20) * 1.4426950408889634f;      // exp(c u^2) = 2^(c log2(e) u^2)
+    const float* rbf = reinterpret_cast<const float*>(smem + SM_RBF);
+    const float c2 = rbf[20] * 1.4426950408889634f;      // exp(c u^2) = 2^(c log2(e) u^2)
 
-    // G row of a tile: values in registers (compute_g: geometry, edge type, Gaussian smearing - x2h_attention.py:46-52,
-    // unitransformer.py:88-99; the factor 1024 of the G scale rides in the exponent), then TMEM (store_g): hi 96 f16
-    // (48 columns), lo 80 f16 (40 columns).  The values are computed BEFORE the wait for MMA1 of the current tile, the
-    // stores right after it, so MMA1 of the next tile can be issued as early as possible.
-    uint32_t ghi[10], glo[10];
+    // G row of a tile, split between the two half-row warps of the quarter: this thread owns the Gaussians
+    // m = 10 hf .. 10 hf + 9 of its edge row.  compute_g: values in registers (geometry, edge type, Gaussian smearing -
+    // x2h_attention.py:46-52, unitransformer.py:88-99; the factor 1024 of the G scale rides in the exponent), BEFORE the
+    // wait for MMA1 of the current tile; store_g: TMEM stores right after it, so MMA1 of the next tile can be issued as
+    // early as possible.  G_hi: 48 columns (96 f16), G_lo: 40 columns; type block tb occupies columns 10 tb .. 10 tb + 9,
+    // the type / node one-hots columns 40 .. 45 of G_hi (written by the half-0 warp).
+    uint32_t ghi[5], glo[5];
     int t_e = 0;
     auto compute_g = [&](const float4 xi, const float4 xj) {
       const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
@@ -179,8 +183,8 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       const int fi = node_flags(xi), fj = node_flags(xj);
       t_e = ((fj & 1) ? 0 : 2) + ((fi & 1) ? 0 : 1);
 #pragma unroll
-      for (int mp = 0; mp < 10; ++mp) {
-        const float u0 = d - __ldg(rbf + 2 * mp), u1 = d - __ldg(rbf + 2 * mp + 1);
+      for (int mp = 0; mp < 5; ++mp) {
+        const float u0 = d - rbf[10 * hf + 2 * mp], u1 = d - rbf[10 * hf + 2 * mp + 1];
         float g0, g1;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g0) : "f"(fmaf(c2 * u0, u0, 10.f)));
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g1) : "f"(fmaf(c2 * u1, u1, 10.f)));
@@ -189,15 +193,21 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     };
     auto store_g = [&](int kk) {
 #pragma unroll
-      for (int blk = 0; blk < 3; ++blk) {          // 16 columns = 32 f16 per store
-        uint32_t w16[16];
+      for (int tb = 0; tb < 4; ++tb) {
+        const bool on = t_e == tb;
+        const uint32_t col = 10u * tb + 5u * (uint32_t)hf;
+        tmem_st4(t_lane + TM_GHI + col, on ? ghi[0] : 0u, on ? ghi[1] : 0u, on ? ghi[2] : 0u, on ? ghi[3] : 0u);
+        tmem_st1(t_lane + TM_GHI + col + 4u, on ? ghi[4] : 0u);
+        tmem_st4(t_lane + TM_GLO + col, on ? glo[0] : 0u, on ? glo[1] : 0u, on ? glo[2] : 0u, on ? glo[3] : 0u);
+        tmem_st1(t_lane + TM_GLO + col + 4u, on ? glo[4] : 0u);
+      }
+      if (hf == 0) {
+        uint32_t w8[8];
 #pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-          const int col = 16 * blk + cc;             // f16 pair (2*col, 2*col + 1)
+        for (int cc = 0; cc < 8; ++cc) {
+          const int col = 40 + cc;                   // f16 pair (2*col, 2*col + 1): k = 80 .. 95
           uint32_t val = 0u;
-          if (col < 40) {
-            val = (t_e == col / 10) ? ghi[col % 10] : 0u;
-          } else if (col == 40) {
+          if (col == 40) {
             val = (t_e == 0) ? kHalfTypeOne : ((t_e == 1) ? (kHalfTypeOne << 16) : 0u);
           } else if (col == 41) {
             val = (t_e == 2) ? kHalfTypeOne : ((t_e == 3) ? (kHalfTypeOne << 16) : 0u);
@@ -205,19 +215,9 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
             const int kc = 84 + wq + 4 * (kk & 1);
             val = ((kc >> 1) == col) ? ((kc & 1) ? (kHalfNodeOne << 16) : kHalfNodeOne) : 0u;
           }
-          w16[cc] = val;
+          w8[cc] = val;
         }
-        tmem_st16(t_lane + TM_GHI + 16u * blk, w16);
-      }
-#pragma unroll
-      for (int blk = 0; blk < 5; ++blk) {          // 8 columns = 16 f16 per store
-        uint32_t w8[8];
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-          const int col = 8 * blk + cc;
-          w8[cc] = (t_e == col / 10) ? glo[col % 10] : 0u;
-        }
-        tmem_st8(t_lane + TM_GLO + 8u * blk, w8);
+        tmem_st8(t_lane + TM_GHI + 40u, w8);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     int iA = 0, iB = 0, jnB = -1;
     float4 xiC = make_float4(0.f, 0.f, 0.f, 0.f), xjC = xiC;
     auto fetch_geo = [&](int i, int jn) { xiC = p.x4[i]; xjC = p.x4[jn >= 0 ? jn : i]; };
-    if (hf == 0) {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
+    {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
       const int i0 = tile_node(0, wq);
       fetch_geo(i0, p.nbr[(size_t)i0 * CBG_KMAX + lane]);
       compute_g(xiC, xjC);
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     for (int k = 0; k < n_my; ++k) {
       const int b = k & 1;
       const int c = wq;                                   // this quarter's Pj chunk, refilled once per tile
-      if (hf == 0) {      // G values of tile k + 1 into registers, then rotate the prefetch registers (the loads land during S1)
+      {      // G values of tile k + 1 into registers, then rotate the prefetch registers (the loads land during S1)
         if (k + 1 < n_my) compute_g(xiC, xjC);
         if (k + 2 < n_my) fetch_geo(iB, jnB);
         if (k + 3 < n_my) { iB = iA; jnB = p.nbr[(size_t)iA * CBG_KMAX + lane]; }
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       tc_fence_after();
       if (warp == 8) TC_STAMP(k, 0);
       if (warp == 12) TC_STAMP(k, 5);
-      if (hf == 0 && k + 1 < n_my) store_g(k + 1);
+      if (k + 1 < n_my) store_g(k + 1);
       if (warp == 8) TC_STAMP(k, 1);
       mbar_wait(bar(B_PJFULL + c), (uint32_t)(k & 1));
       // ---- S1
