@@ -88,7 +88,7 @@ enum { B_WFULL = 0, B_GREADY, B_UNUSED, B_ACC1 /*2*/ = 3, B_AREADY /*2*/ = 5, B_
        B_PJFULL = 11, B_PJFREE = 11 + NCH, B_PIREADY /*2*/ = 11 + 2 * NCH };
 // TMEM columns
 constexpr uint32_t TM_BUF = 0;           // 2 x 128: pre (fp32) -> a_hi (64 cols) | a_lo (64 cols)
-constexpr uint32_t TM_OUT = 256;         // 2 x 64 : output halves (features 0-63, 64-127)
+constexpr uint32_t TM_OUT = 256;         // 128: output accumulator of MMA2
 constexpr uint32_t TM_GHI = 384;         // 48 columns = 96 f16
 constexpr uint32_t TM_GLO = 432;         // 40 columns = 80 f16
 constexpr uint32_t TM_COLS = 512;
@@ -370,16 +370,17 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         float* my = s_sm + lane * 17;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar(B_ACC2 + h), (uint32_t)(k & 1));
-          tc_fence_after();
+          if (h == 0) { mbar_wait(bar(B_ACC2), (uint32_t)(k & 1)); tc_fence_after(); }
           if (warp == 4) TC_STAMP(k, 7 + h);
           uint32_t r[2][32];
           tmem_ld32_nowait(t_lane + TM_OUT + 64u * h, r[0]);
           tmem_ld32_nowait(t_lane + TM_OUT + 64u * h + 32u, r[1]);
           tmem_wait_ld();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar(B_ACC2FREE + h));
+          if (h == 1) {      // the whole accumulator row is in registers: MMA2 of the next tile may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(B_ACC2FREE));
+          }
 #pragma unroll
           for (int hh = 0; hh < 8; ++hh) {
             const float4 q0 = *reinterpret_cast<const float4*>(qs + 64 * h + 8 * hh);
@@ -422,18 +423,17 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          mbar_wait(bar(B_ACC2 + h), (uint32_t)(k & 1));
-          tc_fence_after();
+          if (h == 0) { mbar_wait(bar(B_ACC2), (uint32_t)(k & 1)); tc_fence_after(); }
           if (warp == 4) TC_STAMP(k, 7 + h);
 #pragma unroll
           for (int qq = 0; qq < 2; ++qq) {           // 32 columns at a time: features 64h + 32qq + (0..31)
             uint32_t r[32];
             tmem_ld32_nowait(t_lane + TM_OUT + 64u * h + 32u * qq, r);
             tmem_wait_ld();
-            if (qq == 1) {
+            if (h == 1 && qq == 1) {      // last piece of the accumulator row is in registers
               tc_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(bar(B_ACC2FREE + h));
+              if (lane == 0) mbar_arrive(bar(B_ACC2FREE));
             }
             // (v + b1v) * w -> this lane's row of the transpose buffer (stride 36 words: 16-byte stores conflict free),
             // then lane l sums column l over the node's 32 edges (fixed order: deterministic)
@@ -553,27 +553,24 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       // single issuing thread, not the tensor pipe, the limiter of the whole kernel).
       const uint64_t dg_hi = smem_desc(sbase + SM_WG, LBO, WG_SBO), dg_lo = smem_desc(sbase + SM_WG + WG_IMG, LBO, WG_SBO);
       const uint64_t d1_hi = smem_desc(sbase + SM_W1, LBO, W1_SBO), d1_lo = smem_desc(sbase + SM_W1 + W1_IMG, LBO, W1_SBO);
-      constexpr uint64_t kHalfRows = (uint64_t)((8u * W1_SBO) >> 4);      // output features 64..127 of W1: 8 row groups further
       auto issue_mma2 = [&](int kk) {
         const int bb = kk & 1;
         mbar_wait(bar(B_AREADY + bb), (uint32_t)((kk >> 1) & 1));
         tc_fence_after();
         TC_STAMP(kk, 12);
         const uint32_t a_hi = tmem + TM_BUF + 128u * (uint32_t)bb, a_lo = a_hi + 64u;
+        // one N = 128 accumulator: an MMA costs ~64 cycles whether N is 64 or 128 (measured: two N = 64 halves took 3.0K
+        // cycles per tile, twice the N = 128 figure), so the output is not split
+        if (kk > 0) { mbar_wait(bar(B_ACC2FREE), (uint32_t)((kk - 1) & 1)); tc_fence_after(); }
+        const uint32_t d = tmem + TM_OUT;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (kk > 0) { mbar_wait(bar(B_ACC2FREE + h), (uint32_t)((kk - 1) & 1)); tc_fence_after(); }
-          const uint32_t d = tmem + TM_OUT + 64u * (uint32_t)h;
-          const uint64_t bh = d1_hi + (uint64_t)h * kHalfRows, bl = d1_lo + (uint64_t)h * kHalfRows;
+        for (int ks = 0; ks < 8; ++ks)     // small terms first
+          umma_f16_ts(d, a_lo + 8u * ks, d1_hi + 16u * ks, IDESC128, ks > 0 ? 1u : 0u);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)     // small terms first
-            umma_f16_ts(d, a_lo + 8u * ks, bh + 16u * ks, IDESC64, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, d1_lo + 16u * ks, IDESC128, 1u);
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, bl + 16u * ks, IDESC64, 1u);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, bh + 16u * ks, IDESC64, 1u);
-          umma_commit(bar(B_ACC2 + h));
-        }
+        for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, d1_hi + 16u * ks, IDESC128, 1u);
+        umma_commit(bar(B_ACC2));
         TC_STAMP(kk, 13);
       };
       for (int k = 0; k < n_my; ++k) {
