@@ -19,20 +19,19 @@
 // packer) stay resident in shared memory for the whole persistent CTA.  Nothing of size [E, 128] touches HBM and no
 // R-cache is needed: the only per-edge gather is the 512-byte Pj row (cp.async, L2 resident).
 //
-// Warp roles (16 warps x 128 registers; the scheduler prefers higher warp ids, so the critical S1 warps come last):
-//   warp 0      TMEM allocation / release only
-//   warps 1-2   PROD      one tile ahead, two node slots each: the node's Pi row into its K column of the Wg images, then
-//                         cp.async of the node's 32 Pj rows into the slot's chunk
-//   warp 3      MMA       one lane issues every tcgen05.mma / commit (fully unrolled, tile-invariant descriptors)
-//   warps 4-7   EPI       thread = edge row, inputs prefetched one tile ahead.  k: <q_i, k> per head, softmax over the
+// Warp roles (16 warps x 128 registers; the scheduler prefers higher warp ids, hence the order):
+//   warps 0-3   EPI       thread = edge row, inputs prefetched one tile ahead.  k: <q_i, k> per head, softmax over the
 //                         node's 32 edges through a shared-memory transpose, w = alpha * e_w;
 //                         v: (v + b1v) * w, sum over the node's 32 edges, h_i += .
-//   warps 8-15  S1        thread = (edge row, column half).  S1(tile t): TMEM(pre) + Pj -> LayerNorm (mean-free: the
+//   warps 4-11  S1        thread = (edge row, column half).  S1(tile t): TMEM(pre) + Pj -> LayerNorm (mean-free: the
 //                         packer centres the first Linear over the feature axis) -> ReLU -> (hi, lo) f16 -> TMEM (in
-//                         place).  The half-0 warps also build the G rows of tile t+1 (geometry, type, Gaussian
-//                         smearing -> TMEM) right after MMA1(t) has completed, from coordinates prefetched a tile ahead
-// Pipelining: TMEM holds two pre/activation buffers and two 64-column output halves, so MMA1 of tile t+1 and MMA2 of
-// tile t-1 run while S1 works on tile t and EPI on tile t-1.
+//                         place).  Each thread also builds its half of the G row of tile t+1 (geometry, type, Gaussian
+//                         smearing -> TMEM): values before, stores right after MMA1(t) has completed
+//   warp 12     MMA       one lane issues every tcgen05.mma / commit (fully unrolled, tile-invariant descriptors)
+//   warps 13-14 PROD      one tile ahead, two node slots each: the node's Pi row into its K column of the Wg images, then
+//                         one 512-byte bulk copy (TMA) per edge of the node's Pj rows into the slot's chunk
+// Pipelining: TMEM holds two pre/activation buffers, so MMA1 of tile t+1 and MMA2 of tile t-1 run while S1 works on
+// tile t and EPI on tile t-1.
 #include <math.h>
 #include "cbg_kernels.cuh"
 #include "cbg_tc.cuh"
@@ -139,7 +138,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       mbar_init(bar(B_ACC2 + b), 1);
       mbar_init(bar(B_ACC2FREE + b), 4);
     }
-    for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 32); mbar_init(bar(B_PJFREE + c), 2); }
+    for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 1); mbar_init(bar(B_PJFREE + c), 2); }
     fence_mbar_init();
   }
   {   // LayerNorm affine (pre-multiplied by the activation scale) and the value bias
@@ -155,13 +154,13 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 8) {
-    // ===================================== S1 (tile k); half-0 warps also build G of tile k + 1 ==================
+  if (warp >= 4 && warp < 12) {
+    // ===================================== S1 (tile k) + this thread's half of the G row of tile k + 1 ==================
     // thread = (edge row, column half hf).  S1: pre = TMEM + Pj -> LayerNorm -> ReLU -> (hi, lo) f16 -> TMEM.  The
     // first Linear is centred over the feature axis by the packer, so pre has zero mean and LayerNorm needs only the
     // sum of squares.  Right after MMA1(k) has completed (the wait below) the G region of TMEM may be rewritten: the
     // hf = 0 warps build the next tile's G rows there from coordinates prefetched one tile ahead.
-    const int wq = warp & 3, hf = (warp >> 2) & 1;      // warps 8-11: column half 0, 12-15: half 1 (lane quarter = warp % 4)
+    const int wq = warp & 3, hf = (warp >> 2) - 1;      // warps 4-7: column half 0, 8-11: half 1 (lane quarter = warp % 4)
     const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
     const float* s_ln = reinterpret_cast<const float*>(smem + SM_LN) + 64 * hf;
     float* s_x = reinterpret_cast<float*>(smem + SM_XCH);
@@ -251,10 +250,10 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       }
       mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready AND G may be rewritten
       tc_fence_after();
-      if (warp == 8) TC_STAMP(k, 0);
-      if (warp == 12) TC_STAMP(k, 5);
+      if (warp == 4) TC_STAMP(k, 0);
+      if (warp == 8) TC_STAMP(k, 5);
       if (k + 1 < n_my) store_g(k + 1);
-      if (warp == 8) TC_STAMP(k, 1);
+      if (warp == 4) TC_STAMP(k, 1);
       mbar_wait(bar(B_PJFULL + c), (uint32_t)(k & 1));
       // ---- S1
       const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
@@ -276,7 +275,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
           v[4 * j] = a0.x; v[4 * j + 1] = a0.y; v[4 * j + 2] = a1.x; v[4 * j + 3] = a1.y;
         }
       }
-      if (warp == 8) TC_STAMP(k, 2);
+      if (warp == 4) TC_STAMP(k, 2);
       float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < 32; ++j) q2 = __ffma2_rn(make_float2(v[2 * j], v[2 * j + 1]), make_float2(v[2 * j], v[2 * j + 1]), q2);
@@ -285,7 +284,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_PJFREE + c));          // this warp is done with the ring chunk
       asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");   // the two half-row warps of this row quarter
-      if (warp == 8) TC_STAMP(k, 3);
+      if (warp == 4) TC_STAMP(k, 3);
       const float qo = s_x[256 * b + 128 * (hf ^ 1) + row];
       float rstd = rsqrtf((qs + qo) * (1.f / 128.f) + 1e-5f);      // MUFU.RSQ + one Newton step: < 1 ulp
       rstd = rstd * (1.5f - 0.5f * ((qs + qo) * (1.f / 128.f) + 1e-5f) * rstd * rstd);
@@ -314,12 +313,12 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_AREADY + b));
-      if (warp == 8) TC_STAMP(k, 4);
-      if (warp == 12) TC_STAMP(k, 6);
+      if (warp == 4) TC_STAMP(k, 4);
+      if (warp == 8) TC_STAMP(k, 6);
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
     // ===================================== EPI (tile k), inputs prefetched one tile ahead ========================
-    const int wq = warp - 4;
+    const int wq = warp;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
     const float* s_b1 = reinterpret_cast<const float*>(smem + SM_B1);
     float* s_q = reinterpret_cast<float*>(smem + SM_QBUF) + wq * 256;          // [tile parity][128]: q row of the node
@@ -371,7 +370,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 0) { mbar_wait(bar(B_ACC2), (uint32_t)(k & 1)); tc_fence_after(); }
-          if (warp == 4) TC_STAMP(k, 7 + h);
+          if (warp == 0) TC_STAMP(k, 7 + h);
           uint32_t r[2][32];
           tmem_ld32_nowait(t_lane + TM_OUT + 64u * h, r[0]);
           tmem_ld32_nowait(t_lane + TM_OUT + 64u * h + 32u, r[1]);
@@ -424,7 +423,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 0) { mbar_wait(bar(B_ACC2), (uint32_t)(k & 1)); tc_fence_after(); }
-          if (warp == 4) TC_STAMP(k, 7 + h);
+          if (warp == 0) TC_STAMP(k, 7 + h);
 #pragma unroll
           for (int qq = 0; qq < 2; ++qq) {           // 32 columns at a time: features 64h + 32qq + (0..31)
             uint32_t r[32];
@@ -467,9 +466,9 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
           }
         }
       }
-      if (warp == 4) TC_STAMP(k, 9);
+      if (warp == 0) TC_STAMP(k, 9);
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp == 13 || warp == 14) {
     // ===================================== PROD: Pj rows and Pi columns, ahead of the tiles =========================
     // Warp 13 serves node slots 0 and 2, warp 14 slots 1 and 3 (no TMEM access here, so no lane-quarter rule).  Every
     // chunk / barrier has ONE producer warp that walks the tiles in order: a parity wait is only sound while the waiter
@@ -479,7 +478,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     // (84 + slot + 4 * tile parity) of the Wg images (hi, lo), which MMA1 of tile - 2 was the last to read.
     const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
     const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
-    const int s0 = warp - 1;                        // slots s0 and s0 + 2
+    const int s0 = warp - 13;                       // slots s0 and s0 + 2
     int i_c[2], jn_c[2], i_n[2];
     float4 pi_c[2];
 #pragma unroll
@@ -490,7 +489,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       i_n[q] = n_my > 1 ? tile_node(1, s0 + 2 * q) : 0;
     }
     for (int kk = 0; kk < n_my; ++kk) {
-      if (warp == 1) TC_STAMP(kk, 14);
+      if (warp == 13) TC_STAMP(kk, 14);
       int jj_s[2];
       // ---- Pi columns of both slots first: nothing is in flight, so the proxy fence is cheap, and MMA1 of this tile
       // never waits on the producers.  The column of this tile parity was last read by MMA1(kk - 2), which is complete
@@ -530,17 +529,15 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       for (int q = 0; q < 2; ++q) {
         const int slot = s0 + 2 * q;
         if (kk >= 1) mbar_wait(bar(B_PJFREE + slot), (uint32_t)((kk - 1) & 1));
-        const uint32_t dst = sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + 16u * (uint32_t)lane;
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const int jr = __shfl_sync(CBG_FULL, jj_s[q], r);
-          cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
-        }
-        cp_async_arrive(bar(B_PJFULL + slot));
+        // one bulk copy (TMA engine) per lane: lane = edge, its neighbour's 512-byte row -> its padded row of the chunk
+        if (lane == 0) mbar_expect_tx(bar(B_PJFULL + slot), 32u * 512u);
+        __syncwarp();
+        bulk_g2s(sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + (uint32_t)lane * PJ_ROW, pj_plane + (size_t)jj_s[q] * CBG_H, 512u,
+                 bar(B_PJFULL + slot));
       }
-      if (warp == 1) TC_STAMP(kk, 15);
+      if (warp == 13) TC_STAMP(kk, 15);
     }
-  } else if (warp == 3) {
+  } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================
     if (lane == 0) {
       mbar_expect_tx(bar(B_WFULL), 2 * W1_IMG + 2 * WG_IMG);
