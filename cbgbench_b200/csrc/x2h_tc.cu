@@ -28,8 +28,8 @@
 //                         place).  Each thread also builds its half of the G row of tile t+1 (geometry, type, Gaussian
 //                         smearing -> TMEM): values before, stores right after MMA1(t) has completed
 //   warp 12     MMA       one lane issues every tcgen05.mma / commit (fully unrolled, tile-invariant descriptors)
-//   warps 13-14 PROD      one tile ahead, two node slots each: the node's Pi row into its K column of the Wg images, then
-//                         one 512-byte bulk copy (TMA) per edge of the node's Pj rows into the slot's chunk
+//   warp 13     PROD-Pi   up to two tiles ahead: the Pi rows of the tile's four nodes into their K columns of the Wg images
+//   warps 14-15 PROD-Pj   one tile ahead, two node slots each: cp.async of the node's 32 Pj rows into the slot's chunk
 // Pipelining: TMEM holds two pre/activation buffers, so MMA1 of tile t+1 and MMA2 of tile t-1 run while S1 works on
 // tile t and EPI on tile t-1.
 #include <math.h>
@@ -130,15 +130,15 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
     mbar_init(bar(B_GREADY), 8);
-    mbar_init(bar(B_PIREADY), 2);
-    mbar_init(bar(B_PIREADY + 1), 2);
+    mbar_init(bar(B_PIREADY), 1);
+    mbar_init(bar(B_PIREADY + 1), 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(B_ACC1 + b), 1);
       mbar_init(bar(B_AREADY + b), 8);
       mbar_init(bar(B_ACC2 + b), 1);
       mbar_init(bar(B_ACC2FREE + b), 4);
     }
-    for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 1); mbar_init(bar(B_PJFREE + c), 2); }
+    for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 32); mbar_init(bar(B_PJFREE + c), 2); }
     fence_mbar_init();
   }
   {   // LayerNorm affine (pre-multiplied by the activation scale) and the value bias
@@ -468,47 +468,31 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       }
       if (warp == 0) TC_STAMP(k, 9);
     }
-  } else if (warp == 13 || warp == 14) {
-    // ===================================== PROD: Pj rows and Pi columns, ahead of the tiles =========================
-    // Warp 13 serves node slots 0 and 2, warp 14 slots 1 and 3 (no TMEM access here, so no lane-quarter rule).  Every
-    // chunk / barrier has ONE producer warp that walks the tiles in order: a parity wait is only sound while the waiter
-    // can never be two phases ahead of the barrier, which a shared ring with several producers does not guarantee.
-    // Per (tile, slot): cp.async of the node's 32 Pj rows into the slot's chunk as soon as the slot's S1 warps have
-    // consumed the previous tile (row-coalesced 512-byte copies), then the node's Pi row -> its K column
-    // (84 + slot + 4 * tile parity) of the Wg images (hi, lo), which MMA1 of tile - 2 was the last to read.
-    const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
+  } else if (warp == 13) {
+    // ===================================== PROD-Pi: the Pi rows of the tile's four nodes, up to two tiles ahead =======
+    // The node's Pi row goes into its K column (84 + slot + 4 * tile parity) of the Wg images (hi, lo); the columns of a
+    // tile parity were last read by MMA1 of tile - 2 (the wait below is always for the NEXT completion of that barrier,
+    // so the parity wait is sound).  This warp never has copies in flight, which keeps its proxy fence cheap.
     const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
-    const int s0 = warp - 13;                       // slots s0 and s0 + 2
-    int i_c[2], jn_c[2], i_n[2];
-    float4 pi_c[2];
+    float4 pi_c[4];
+    int i_n[4];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      i_c[q] = tile_node(0, s0 + 2 * q);
-      jn_c[q] = p.nbr[(size_t)i_c[q] * CBG_KMAX + lane];
-      pi_c[q] = ldg4(pi_plane + (size_t)i_c[q] * CBG_H + 4 * lane);
-      i_n[q] = n_my > 1 ? tile_node(1, s0 + 2 * q) : 0;
+    for (int sl = 0; sl < 4; ++sl) {
+      pi_c[sl] = ldg4(pi_plane + (size_t)tile_node(0, sl) * CBG_H + 4 * lane);
+      i_n[sl] = n_my > 1 ? tile_node(1, sl) : 0;
     }
     for (int kk = 0; kk < n_my; ++kk) {
-      if (warp == 13) TC_STAMP(kk, 14);
-      int jj_s[2];
-      // ---- Pi columns of both slots first: nothing is in flight, so the proxy fence is cheap, and MMA1 of this tile
-      // never waits on the producers.  The column of this tile parity was last read by MMA1(kk - 2), which is complete
-      // because this warp's slots have already consumed tile kk - 2 (the Pj wait of the previous iteration).
+      TC_STAMP(kk, 14);
       if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
       else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int slot = s0 + 2 * q;
-        const int i = i_c[q];
-        jj_s[q] = jn_c[q] >= 0 ? jn_c[q] : i;
-        const float4 pi4 = pi_c[q];
-        if (kk + 1 < n_my) {      // next tile's loads (its node id was fetched one tile earlier: no dependent load is waited on)
-          i_c[q] = i_n[q];
-          jn_c[q] = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
-          pi_c[q] = ldg4(pi_plane + (size_t)i_n[q] * CBG_H + 4 * lane);
-          if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
+      for (int sl = 0; sl < 4; ++sl) {
+        const float4 pi4 = pi_c[sl];
+        if (kk + 1 < n_my) {      // next tile's row (its node id was fetched one tile earlier)
+          pi_c[sl] = ldg4(pi_plane + (size_t)i_n[sl] * CBG_H + 4 * lane);
+          if (kk + 2 < n_my) i_n[sl] = tile_node(kk + 2, sl);
         }
-        const int kcol = 84 + slot + 4 * (kk & 1);
+        const int kcol = 84 + sl + 4 * (kk & 1);
         const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
         const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
 #pragma unroll
@@ -524,18 +508,43 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
-      // ---- Pj rows of both slots, each as soon as the slot's S1 warps have consumed the previous tile
+      TC_STAMP(kk, 15);
+    }
+  } else if (warp >= 14) {
+    // ===================================== PROD-Pj: the Pj rows of two node slots, one tile ahead ====================
+    // Warp 14 serves node slots 0 and 2, warp 15 slots 1 and 3: every chunk has ONE producer warp that walks the tiles in
+    // order (a parity wait is only sound while the waiter can never be two phases ahead of the barrier).  Per (tile,
+    // slot): cp.async of the node's 32 Pj rows into the slot's chunk as soon as the slot's S1 warps have consumed the
+    // previous tile (warp = one row-coalesced 512-byte copy per instruction).
+    const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
+    const int s0 = warp - 14;                       // slots s0 and s0 + 2
+    int jj_c[2], i_n[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i0 = tile_node(0, s0 + 2 * q);
+      const int jn = p.nbr[(size_t)i0 * CBG_KMAX + lane];
+      jj_c[q] = jn >= 0 ? jn : i0;
+      i_n[q] = n_my > 1 ? tile_node(1, s0 + 2 * q) : 0;
+    }
+    for (int kk = 0; kk < n_my; ++kk) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int slot = s0 + 2 * q;
+        const int jj = jj_c[q];
+        if (kk + 1 < n_my) {      // next tile's neighbours (its node id was fetched one tile earlier)
+          const int jn = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
+          jj_c[q] = jn >= 0 ? jn : i_n[q];
+          if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
+        }
         if (kk >= 1) mbar_wait(bar(B_PJFREE + slot), (uint32_t)((kk - 1) & 1));
-        // one bulk copy (TMA engine) per lane: lane = edge, its neighbour's 512-byte row -> its padded row of the chunk
-        if (lane == 0) mbar_expect_tx(bar(B_PJFULL + slot), 32u * 512u);
-        __syncwarp();
-        bulk_g2s(sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + (uint32_t)lane * PJ_ROW, pj_plane + (size_t)jj_s[q] * CBG_H, 512u,
-                 bar(B_PJFULL + slot));
+        const uint32_t dst = sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + 16u * (uint32_t)lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int jr = __shfl_sync(CBG_FULL, jj, r);
+          cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
+        }
+        cp_async_arrive(bar(B_PJFULL + slot));
       }
-      if (warp == 13) TC_STAMP(kk, 15);
     }
   } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================
