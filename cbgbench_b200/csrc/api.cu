@@ -5,6 +5,8 @@
 #include <string.h>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges show up in Nsight Systems, cost nothing without a tool attached
+
 #include "../../include/cbg_b200.h"
 #include "cbg_kernels.cuh"
 
@@ -12,6 +14,11 @@ long long g_cbg_launches = 0;
 int g_cbg_prof_on = 0;
 
 namespace {
+// RAII NVTX range (tracing)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 struct ProfMark { int family; int is_end; cudaEvent_t ev; };
 std::vector<ProfMark> g_prof_marks;
 const char* const kFamilyNames[CBG_K_COUNT] = {"knn", "edge_gate", "node_gemm", "x2h_k", "x2h_v", "h2x",
@@ -193,6 +200,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
              float r_max, const float* rcache, const int* cls_idx, int n_cls, bool prune, cudaStream_t st,
              bool static_lists = false) {
   static_lists = static_lists || rcache != nullptr;      // the R-cache is indexed by the static lists
+  NvtxRange nvtx_core("cbg:denoiser");
   if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
   if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, static_lists ? ws.snbr : nullptr, ws.nbr, st)) return rc;
   const float* layers = blob + cbg_layout::kGlobalFloats;
@@ -220,6 +228,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
   bool x_pending = false;                          // an apply_dx on sx has not been joined yet
   for (int l = 0; l < num_layers; ++l) {
     const float* L = layers + (size_t)l * cbg_layout::kLayerFloats;
+    NvtxRange nvtx_layer("cbg:layer");
     // ---- X2H: node planes, attention weights, aggregation (h updated in place)
     NodeGemmArgs g{};
     g.a = ws.h; g.row_idx = nullptr; g.n_rows = (int)n_nodes;
@@ -594,6 +603,7 @@ int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* co
                             const float* c_t, const float* pos_noise, const float* type_uniform, float* x_next,
                             float* c_next, int64_t* v_next, float* x0_pred, float* logits, void* stream) {
   if (!plan || !coef) { cbg_set_error("null plan/coef"); return 1; }
+  NvtxRange nvtx_step("cbg:sample_step");
   Workspace ws;
   if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
