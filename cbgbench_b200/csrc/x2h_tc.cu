@@ -29,8 +29,7 @@
 //                         smearing -> TMEM): values before, stores right after MMA1(t) has completed
 //   warp 12     MMA       one lane issues every tcgen05.mma / commit (fully unrolled, tile-invariant descriptors)
 //   warp 13     PROD-Pi   up to two tiles ahead: the Pi rows of the tile's four nodes into their K columns of the Wg images
-//   (warps 14-15 idle: the S1 warps of a quarter refill their own Pj chunk - cp.async of the node's 32 rows, 16 per
-//    warp - right after both have consumed it, so no quarter ever waits on another warp for its rows)
+//   warps 14-15 PROD-Pj   one tile ahead, two node slots each: cp.async of the node's 32 Pj rows into the slot's chunk
 // Pipelining: TMEM holds two pre/activation buffers, so MMA1 of tile t+1 and MMA2 of tile t-1 run while S1 works on
 // tile t and EPI on tile t-1.
 #include <math.h>
@@ -139,7 +138,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       mbar_init(bar(B_ACC2 + b), 1);
       mbar_init(bar(B_ACC2FREE + b), 4);
     }
-    for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 64); mbar_init(bar(B_PJFREE + c), 2); }
+    for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 32); mbar_init(bar(B_PJFREE + c), 2); }
     fence_mbar_init();
   }
   {   // LayerNorm affine (pre-multiplied by the activation scale) and the value bias
@@ -225,25 +224,12 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       if (lane == 0) mbar_arrive(bar(B_GREADY));
     };
     // prefetch state of the G builders: coordinates of tile k+1 (C), node + neighbour of tile k+2 (B), node of tile k+3 (A)
-    int iA = 0, iB = 0, jnB = -1, jjC = 0;
+    int iA = 0, iB = 0, jnB = -1;
     float4 xiC = make_float4(0.f, 0.f, 0.f, 0.f), xjC = xiC;
-    auto fetch_geo = [&](int i, int jn) { jjC = jn >= 0 ? jn : i; xiC = p.x4[i]; xjC = p.x4[jjC]; };
-    // this warp's half (16 rows) of the quarter's 32 Pj rows of a tile -> the quarter's chunk: one row-coalesced 512-byte
-    // cp.async per instruction; the chunk's barrier counts the 64 deferred arrivals of the two half-row warps
-    const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
-    auto copy_pj = [&](int jj) {
-      const uint32_t dst = sbase + SM_PJ + (uint32_t)wq * PJ_CHUNK + 16u * (uint32_t)lane;
-#pragma unroll 8
-      for (int r = 16 * hf; r < 16 * hf + 16; ++r) {
-        const int jr = __shfl_sync(CBG_FULL, jj, r);
-        cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr * CBG_H + 4 * lane);
-      }
-      cp_async_arrive(bar(B_PJFULL + wq));
-    };
+    auto fetch_geo = [&](int i, int jn) { xiC = p.x4[i]; xjC = p.x4[jn >= 0 ? jn : i]; };
     {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
       const int i0 = tile_node(0, wq);
       fetch_geo(i0, p.nbr[(size_t)i0 * CBG_KMAX + lane]);
-      copy_pj(jjC);
       compute_g(xiC, xjC);
       store_g(0);
       if (n_my > 1) {
@@ -256,7 +242,6 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     for (int k = 0; k < n_my; ++k) {
       const int b = k & 1;
       const int c = wq;                                   // this quarter's Pj chunk, refilled once per tile
-      const int jj_next = jjC;                            // neighbours of tile k + 1 (copied after this tile's Pj phase)
       {      // G values of tile k + 1 into registers, then rotate the prefetch registers (the loads land during S1)
         if (k + 1 < n_my) compute_g(xiC, xjC);
         if (k + 2 < n_my) fetch_geo(iB, jnB);
@@ -296,8 +281,9 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       for (int j = 0; j < 32; ++j) q2 = __ffma2_rn(make_float2(v[2 * j], v[2 * j + 1]), make_float2(v[2 * j], v[2 * j + 1]), q2);
       const float qs = q2.x + q2.y;
       s_x[256 * b + 128 * hf + row] = qs;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_PJFREE + c));          // this warp is done with the ring chunk
       asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory");   // the two half-row warps of this row quarter
-      if (k + 1 < n_my) copy_pj(jj_next);                 // both warps are done with the chunk: refill it for the next tile
       if (warp == 4) TC_STAMP(k, 3);
       const float qo = s_x[256 * b + 128 * (hf ^ 1) + row];
       float rstd = rsqrtf((qs + qo) * (1.f / 128.f) + 1e-5f);      // MUFU.RSQ + one Newton step: < 1 ulp
@@ -523,6 +509,42 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
       TC_STAMP(kk, 15);
+    }
+  } else if (warp >= 14) {
+    // ===================================== PROD-Pj: the Pj rows of two node slots, one tile ahead ====================
+    // Warp 14 serves node slots 0 and 2, warp 15 slots 1 and 3: every chunk has ONE producer warp that walks the tiles in
+    // order (a parity wait is only sound while the waiter can never be two phases ahead of the barrier).  Per (tile,
+    // slot): cp.async of the node's 32 Pj rows into the slot's chunk as soon as the slot's S1 warps have consumed the
+    // previous tile (warp = one row-coalesced 512-byte copy per instruction).
+    const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
+    const int s0 = warp - 14;                       // slots s0 and s0 + 2
+    int jj_c[2], i_n[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i0 = tile_node(0, s0 + 2 * q);
+      const int jn = p.nbr[(size_t)i0 * CBG_KMAX + lane];
+      jj_c[q] = jn >= 0 ? jn : i0;
+      i_n[q] = n_my > 1 ? tile_node(1, s0 + 2 * q) : 0;
+    }
+    for (int kk = 0; kk < n_my; ++kk) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int slot = s0 + 2 * q;
+        const int jj = jj_c[q];
+        if (kk + 1 < n_my) {      // next tile's neighbours (its node id was fetched one tile earlier)
+          const int jn = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
+          jj_c[q] = jn >= 0 ? jn : i_n[q];
+          if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
+        }
+        if (kk >= 1) mbar_wait(bar(B_PJFREE + slot), (uint32_t)((kk - 1) & 1));
+        const uint32_t dst = sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + 16u * (uint32_t)lane;
+        int jr[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) jr[r] = __shfl_sync(CBG_FULL, jj, r);       // all shuffles first: no per-row latency chain
+#pragma unroll
+        for (int r = 0; r < 32; ++r) cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr[r] * CBG_H + 4 * lane);
+        cp_async_arrive(bar(B_PJFULL + slot));
+      }
     }
   } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================
