@@ -370,7 +370,6 @@ int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_
 int32_t cbg_set_option(const char* key, int32_t value) {
   if (key && strcmp(key, "static_fast") == 0) { g_static_fast = value ? 1 : 0; return 0; }
   if (key && strcmp(key, "dyn_sched") == 0) { g_dyn_sched = value ? 1 : 0; return 0; }
-  if (key && strcmp(key, "h2x_impl") == 0) return cbg_edge_set_h2x_impl(value);
   if (key && strcmp(key, "x2h_trace_off") == 0) { cbg_x2h_tc_set_trace(nullptr, 0); return 0; }
   cbg_set_error("cbg_set_option: unknown key '%s'", key ? key : "(null)");
   return 1;

@@ -89,7 +89,6 @@ int cbg_launch_umma_selftest(const void* a, const void* b, float* d, int a_from_
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st);
 int cbg_edge_init(void);  // sets max-dynamic-smem attributes once
 int cbg_edge_set_impl(int impl, int warps);  // X2H implementation switch (cbg_set_edge_impl)
-int cbg_edge_set_h2x_impl(int impl);         // H2X implementation switch (cbg_set_option "h2x_impl")
 
 // misc.cu
 int cbg_launch_pack_x4(const float* x, const unsigned char* lig_flag, const unsigned char* gen_flag,

@@ -51,14 +51,11 @@ const char* cbg_profile_family_name(int32_t i);
 int32_t cbg_profile_enable(int32_t on);
 int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family);
 
-/* Tuning / testing hook: implementation of the two fused X2H edge kernels (the dominant kernels of a step).
- *   impl 4 (default, fastest measured): attention-weight kernel with the per-node head contraction AND the RBF mat-vec of
- *           the non-cached edges on the tensor cores (mma.sync m16n8k8 TF32, 3xTF32 split, fp32 accumulate) + SIMT
- *           aggregation kernel;  5: the same + tensor-core aggregation kernel
- *   impl 1 / 2 / 3: first tensor-core generation (contraction only): both kernels / attention-weight kernel only /
- *           aggregation kernel only;  impl 0: fp32 SIMT kernels
- * warps = CTA size in warps (8, 12, 16; 0 keeps the current value).  Process-wide; also env CBG_EDGE_IMPL,
- * CBG_EDGE_MMA_WARPS, CBG_EDGE_WARPS.  Needs a current CUDA device. */
+/* TESTING hook (process-wide, not thread-safe; production code never calls it): implementation of the two fused X2H
+ * edge kernels.  impl 6 (default): tcgen05 kernels (csrc/x2h_tc.cu: A operands in tensor memory, f16 hi/lo split);
+ * impl 0: the fp32 SIMT kernels (csrc/edge.cu), kept as an independent implementation for the parity tests - the only
+ * consumer of the optional R-cache.  warps = CTA size of the SIMT kernels (8, 12, 16; 0 keeps the current value).
+ * Also env CBG_EDGE_IMPL / CBG_EDGE_WARPS.  Needs a current CUDA device. */
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);
 /* Hardware self-test of the tcgen05 operand conventions the X2H kernels rely on (tests only):
  * d[128][128] (fp32) = a[128][32] * b[128][32]^T with f16 row-major device inputs; a_from_smem = 0 feeds A from
@@ -67,12 +64,10 @@ int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_
 /* Debugging: later launches of the tcgen05 attention-weight kernel stamp the pipeline events of CTA 0 (SM clock) into
  * buf_dev[max_tiles][16] (int64, device memory); NULL turns it off.  Process-wide. */
 int32_t cbg_debug_x2h_trace(int64_t* buf_dev, int32_t max_tiles);
-/* Other process-wide switches (testing): "static_fast" = 1 (default; env CBG_STATIC_FAST) lets the X2H kernels skip the
- * coordinate gathers / RBF set-up of nodes whose 32 in-edges are all served from the R-cache (bit-identical results);
- * "dyn_sched" = 1 (default; env CBG_DYN_SCHED): warps of the X2H kernels draw their next node from a work counter instead
- * of a static round-robin (bit-identical results, better balance);
- * "h2x_impl" = 0 (default; env CBG_H2X_IMPL): fp32 SIMT H2X edge kernel (one warp per generated node), 1 = two warps per
- * node with both edge MLPs on the tensor cores (tested alternative; slower at the c2 shape). */
+/* Other TESTING switches of the SIMT kernels (process-wide): "static_fast" = 1 (default; env CBG_STATIC_FAST) lets them
+ * skip the coordinate gathers / RBF set-up of nodes whose 32 in-edges are all served from the R-cache (bit-identical);
+ * "dyn_sched" = 1 (default; env CBG_DYN_SCHED): their warps draw the next node from a work counter instead of a static
+ * round-robin (bit-identical). */
 int32_t cbg_set_option(const char* key, int32_t value);
 
 /* ---- packed weight blob layout (single source of truth: csrc/cbg_layout.h) -------------------

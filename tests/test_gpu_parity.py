@@ -367,10 +367,11 @@ def test_node_projections_match_float64(impl, sublayer):
             assert torch.isnan(planes.cpu()[:, mask]).all()
 
 
-def test_rcache_matches_uncached_path():
-    """Streaming the cached first-Linear terms of static edges (R-cache) must not change results:
+def test_rcache_matches_uncached_path(edge_impl_reset):
+    """SIMT kernels: streaming the cached first-Linear terms of static edges (R-cache) must not change results:
     same atom types, coordinates equal to summation-order rounding."""
     T = 5
+    _lib.check(_lib.lib().cbg_set_edge_impl(0, 0))
     for gen_mode, sizes in (('denovo', ([140, 60, 20], [20, 9, 5])), ('partial', ([90, 70], [18, 12]))):
         model, sd = make_model(T, device=dev())
         batch = synthetic.make_batch(*sizes, seed=101, gen_mode=gen_mode)
@@ -490,22 +491,21 @@ def test_sample_driver_single_gpu(tmp_path):
 
 
 # ---------------------------------------------------------------------------------------------
-# the two implementations of the fused X2H edge kernels (tensor-core mma.sync 3xTF32 vs fp32 SIMT)
-EDGE_IMPLS = {0: 'simt', 1: 'mma', 2: 'mma_k+simt_v', 3: 'simt_k+mma_v', 4: 'mma2_k+simt_v', 5: 'mma2_k+mma_v'}
+# the two implementations of the fused X2H edge kernels: tcgen05 (default) and fp32 SIMT (independent cross-check)
+EDGE_IMPLS = {0: 'simt', 6: 'tcgen05'}
 
 
 @pytest.fixture
 def edge_impl_reset():
     yield
-    _lib.check(_lib.lib().cbg_set_edge_impl(1, 8))
     _lib.check(_lib.lib().cbg_set_edge_impl(0, 12))
     _lib.check(_lib.lib().cbg_set_edge_impl(_lib.DEFAULT_EDGE_IMPL, 0))     # library default
 
 
 @pytest.mark.parametrize('case', FORWARD_CASES, ids=[c[0] for c in FORWARD_CASES])
 def test_edge_kernel_implementations_agree(case, edge_impl_reset):
-    """Every implementation of the X2H kernels (and the two mixed pairings, which localise a mismatch to the
-    attention-weight or the aggregation kernel) must match the reference golden and each other."""
+    """Both implementations of the X2H kernels (and the SIMT kernels at every CTA size) must match the reference golden
+    and each other."""
     name, n_prot, n_lig, seed, gen_mode, enc = case
     gold = golden('forward_cases.npz')
     model, sd = make_model(10, device=dev(), **enc)
@@ -514,14 +514,14 @@ def test_edge_kernel_implementations_agree(case, edge_impl_reset):
     args = [t.to(dev()) for t in (x, h, bidx, lig, gen)]
     outs, report = {}, []
     for impl, label in EDGE_IMPLS.items():
-        for warps in ((8, 12) if impl == 1 else (0,)):
+        for warps in ((8, 12, 16) if impl == 0 else (0,)):
             _lib.check(_lib.lib().cbg_set_edge_impl(impl, warps))
             h1 = model.denoiser(*args, stop_after_layers=1)[1].cpu()
             xg, hg, cg = (t.cpu() for t in model.denoiser(*args))
             outs[(impl, warps)] = (h1, xg, hg, cg)
             errs = [rel_err(a, gold[f'{name}/{k}']) for a, k in ((xg, 'x'), (hg, 'h'), (cg, 'c'))]
             report.append(f'{label}/w{warps}: x {errs[0]:.1e} h {errs[1]:.1e} c {errs[2]:.1e}')
-    base = outs[(0, 0)]
+    base = outs[(0, 12)]
     bad = []
     for key, o in outs.items():
         d1, dx, dh = rel_err(o[0], base[0]), rel_err(o[1], base[1]), rel_err(o[2], base[2])
@@ -535,85 +535,49 @@ def test_edge_kernel_implementations_agree(case, edge_impl_reset):
 
 
 def test_edge_kernel_implementations_agree_on_the_sampling_path(edge_impl_reset):
-    """Sampling path (R-cache, static lists, pruning on): tensor-core and SIMT kernels give the same atom types and
-    coordinates equal to rounding; also with the R-cache off (every block takes the in-register RBF path)."""
+    """Sampling path (static lists, pruning on): tcgen05 and SIMT kernels give the same atom types and coordinates equal
+    to rounding; the SIMT kernels also with their R-cache on (streamed first-Linear terms of static edges)."""
     T = 5
     for gen_mode, sizes in (('denovo', ([140, 60, 20], [20, 9, 5])), ('partial', ([90, 70], [18, 12]))):
         model, sd = make_model(T, device=dev())
         batch = synthetic.make_batch(*sizes, seed=131, gen_mode=gen_mode)
         n_lig = int(batch['ligand_pos'].shape[0])
         pn, tu = synthetic.make_noise(T, n_lig, 13, seed=19)
-        for rcache in (True, False):
+        res = {}
+        for key, impl, rcache in (('tc', 6, False), ('simt', 0, False), ('simt+rcache', 0, True)):
             model.use_rcache = rcache
-            res = {}
-            for impl in (0, 1, 4):
-                _lib.check(_lib.lib().cbg_set_edge_impl(impl, 0))
-                res[impl] = model.sample(batch, pos_noise=pn, type_uniform=tu)
-            for impl in (1, 4):
-                for t in range(-1, T):
-                    assert torch.equal(res[0][t][1].cpu().argmax(-1), res[impl][t][1].cpu().argmax(-1)), (gen_mode, rcache, impl, t)
-                    e = rel_err(res[impl][t][0].cpu(), res[0][t][0].cpu())
-                    assert e < 1e-5, (gen_mode, rcache, impl, t, e)
+            _lib.check(_lib.lib().cbg_set_edge_impl(impl, 0))
+            res[key] = model.sample(batch, pos_noise=pn, type_uniform=tu)
+        for key in ('tc', 'simt+rcache'):
+            for t in range(-1, T):
+                assert torch.equal(res['simt'][t][1].cpu().argmax(-1), res[key][t][1].cpu().argmax(-1)), (gen_mode, key, t)
+                e = rel_err(res[key][t][0].cpu(), res['simt'][t][0].cpu())
+                assert e < 1e-5, (gen_mode, key, t, e)
 
 
 def test_static_fast_path_and_dynamic_scheduling_are_bit_identical(edge_impl_reset):
-    """Nodes whose 32 in-edges are all static skip the coordinate gathers / RBF set-up of the X2H kernels, and warps draw
-    nodes from a work counter instead of a round-robin; neither may change a single bit of the sampled coordinates and
-    types, for every implementation of the kernels."""
+    """SIMT kernels with the R-cache: nodes whose 32 in-edges are all static skip the coordinate gathers / RBF set-up, and
+    warps draw nodes from a work counter instead of a round-robin; neither may change a single bit of the sampled
+    coordinates and types."""
     T = 4
     L = _lib.lib()
     try:
         for gen_mode, sizes in (('denovo', ([300, 120, 40], [24, 10, 6])), ('partial', ([200, 150], [18, 12]))):
             model, sd = make_model(T, device=dev())
+            model.use_rcache = True
             batch = synthetic.make_batch(*sizes, seed=141, gen_mode=gen_mode)
             n_lig = int(batch['ligand_pos'].shape[0])
             pn, tu = synthetic.make_noise(T, n_lig, 13, seed=23)
-            for impl in (0, 1, 2, 4):
-                _lib.check(L.cbg_set_edge_impl(impl, 0))
-                res = {}
-                for fast, dyn in ((1, 1), (0, 1), (1, 0), (0, 0)):
-                    _lib.check(L.cbg_set_option(b'static_fast', fast))
-                    _lib.check(L.cbg_set_option(b'dyn_sched', dyn))      # work-counter vs round-robin node scheduling
-                    res[(fast, dyn)] = model.sample(batch, pos_noise=pn, type_uniform=tu)
-                for key in ((0, 1), (1, 0), (0, 0)):
-                    for t in range(-1, T):
-                        assert torch.equal(res[key][t][0].cpu(), res[(1, 1)][t][0].cpu()), (gen_mode, impl, key, t)
-                        assert torch.equal(res[key][t][1].cpu(), res[(1, 1)][t][1].cpu()), (gen_mode, impl, key, t)
+            _lib.check(L.cbg_set_edge_impl(0, 0))
+            res = {}
+            for fast, dyn in ((1, 1), (0, 1), (1, 0), (0, 0)):
+                _lib.check(L.cbg_set_option(b'static_fast', fast))
+                _lib.check(L.cbg_set_option(b'dyn_sched', dyn))      # work-counter vs round-robin node scheduling
+                res[(fast, dyn)] = model.sample(batch, pos_noise=pn, type_uniform=tu)
+            for key in ((0, 1), (1, 0), (0, 0)):
+                for t in range(-1, T):
+                    assert torch.equal(res[key][t][0].cpu(), res[(1, 1)][t][0].cpu()), (gen_mode, key, t)
+                    assert torch.equal(res[key][t][1].cpu(), res[(1, 1)][t][1].cpu()), (gen_mode, key, t)
     finally:
         _lib.check(L.cbg_set_option(b'static_fast', 1))
         _lib.check(L.cbg_set_option(b'dyn_sched', 1))
-
-
-def test_h2x_implementations_agree(edge_impl_reset):
-    """H2X edge kernel: tensor-core pair kernel (two warps per generated node) vs the fp32 SIMT kernel - same goldens, equal
-    to rounding, on de-novo, partial-generation, tiny and k=8 graphs; and along a short sampled trajectory."""
-    L = _lib.lib()
-    gold = golden('forward_cases.npz')
-    try:
-        for case in FORWARD_CASES:
-            name, n_prot, n_lig, seed, gen_mode, enc = case
-            model, sd = make_model(10, device=dev(), **enc)
-            batch = synthetic.make_batch(n_prot, n_lig, seed=seed, gen_mode=gen_mode)
-            x, h, bidx, lig, gen = composed_inputs(sd, batch)
-            args = [t.to(dev()) for t in (x, h, bidx, lig, gen)]
-            outs = {}
-            for impl in (0, 1):
-                _lib.check(L.cbg_set_option(b'h2x_impl', impl))
-                outs[impl] = [t.cpu() for t in model.denoiser(*args)]
-                for a, k in zip(outs[impl], ('x', 'h', 'c')):
-                    assert rel_err(a, gold[f'{name}/{k}']) < TOL, (name, impl, k)
-            assert rel_err(outs[1][0], outs[0][0]) < 1e-5 and rel_err(outs[1][1], outs[0][1]) < 1e-5, name
-            assert torch.equal(outs[1][0][~gen], x[~gen])
-        T = 5
-        model, sd = make_model(T, device=dev())
-        batch = synthetic.make_batch([140, 60, 20], [20, 9, 5], seed=151)
-        pn, tu = synthetic.make_noise(T, 34, 13, seed=29)
-        res = {}
-        for impl in (0, 1):
-            _lib.check(L.cbg_set_option(b'h2x_impl', impl))
-            res[impl] = model.sample(batch, pos_noise=pn, type_uniform=tu)
-        for t in range(-1, T):
-            assert torch.equal(res[0][t][1].cpu().argmax(-1), res[1][t][1].cpu().argmax(-1)), t
-            assert rel_err(res[1][t][0].cpu(), res[0][t][0].cpu()) < 1e-5, t
-    finally:
-        _lib.check(L.cbg_set_option(b'h2x_impl', 0))      # library default
