@@ -74,6 +74,7 @@ struct Workspace {
   float* dx;
   int* tickets;                // 64 work counters of the X2H launches of one step (dynamic node scheduling)
   unsigned char* fstat;        // per node: all 32 in-edges static this step (written by the edge gate when an R-cache is used)
+  StepIO* io;                  // per-step pointers / coefficients of a graph-replayed step (cbg_sample_step_graph_f32)
   size_t bytes;
 };
 
@@ -97,6 +98,7 @@ Workspace carve(void* base, long long n_nodes, long long n_gen) {
   ws.dx = (float*)take((size_t)(n_gen > 0 ? n_gen : 1) * 16);
   ws.fstat = (unsigned char*)take((size_t)n_nodes);
   ws.tickets = (int*)take(64 * sizeof(int));
+  ws.io = (StepIO*)take(sizeof(StepIO));
   ws.bytes = off;
   return ws;
 }
@@ -627,6 +629,134 @@ int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* co
   if (x0_pred) {   // predicted ligand coordinates (testing / trajectory inspection)
     if (int rc = cbg_launch_gather_x(ws.x4, plan->lig_node, plan->n_lig, x0_pred, st)) return rc;
   }
+  return 0;
+}
+
+// ---- the same step, replayed from a CUDA graph ---------------------------------------------------------------------
+// Shapes and device pointers of a plan do not change over the T steps (the pruning / neighbour-list lengths live on the
+// device), so the ~85 launches, fork/join events and memsets of a step are captured ONCE per plan and replayed with one
+// cudaGraphLaunch per step.  What changes per step - the trajectory slots, the noise tensors, eight schedule
+// coefficients - goes through a StepIO block in the workspace that the first and the last kernel of the graph read; it
+// is refreshed by one small H2D copy (from a ring of pinned host slots) in front of every launch.
+namespace {
+constexpr int kIoRing = 64;
+struct StepGraph {
+  unsigned long long key = 0;
+  int dev = -1;
+  cudaStream_t stream = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  long long kernel_nodes = 0;
+  int warm = 0;                      // eager steps seen for this plan (the first one also performs one-time kernel setup)
+  StepIO* pinned = nullptr;          // [kIoRing]
+  cudaEvent_t ev[kIoRing] = {};
+  bool ev_used[kIoRing] = {};
+  int next = 0;
+  unsigned long long stamp = 0;
+};
+std::vector<StepGraph*> g_graphs;
+unsigned long long g_graph_clock = 0;
+
+unsigned long long fnv1a(const void* p, size_t n, unsigned long long h = 1469598103934665603ull) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+void destroy_graph(StepGraph* g) {
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  for (int i = 0; i < kIoRing; ++i) if (g->ev[i]) cudaEventDestroy(g->ev[i]);
+  if (g->pinned) cudaFreeHost(g->pinned);
+  delete g;
+}
+}  // namespace
+
+int32_t cbg_sample_step_graph_f32(const cbg_sample_plan* plan, const cbg_step_coef* coef, const float* x_t,
+                                  const float* c_t, const float* pos_noise, const float* type_uniform, float* x_next,
+                                  float* c_next, int64_t* v_next, void* stream) {
+  if (!plan || !coef) { cbg_set_error("null plan/coef"); return 1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = -1;
+  CBG_CUDA_OK(cudaGetDevice(&dev));
+  if (g_cbg_prof_on)      // per-kernel event profiling brackets every launch: not capturable, run eagerly
+    return cbg_sample_step_f32(plan, coef, x_t, c_t, pos_noise, type_uniform, x_next, c_next, v_next, nullptr, nullptr, stream);
+  unsigned long long key = fnv1a(plan, sizeof(*plan));
+  key = fnv1a(&st, sizeof(st), key);
+  StepGraph* g = nullptr;
+  for (StepGraph* c : g_graphs) if (c->key == key && c->dev == dev && c->stream == st) { g = c; break; }
+  if (!g) {
+    if (g_graphs.size() >= 8) {      // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < g_graphs.size(); ++i) if (g_graphs[i]->stamp < g_graphs[lru]->stamp) lru = i;
+      destroy_graph(g_graphs[lru]);
+      g_graphs.erase(g_graphs.begin() + (long)lru);
+    }
+    g = new StepGraph();
+    g->key = key; g->dev = dev; g->stream = st;
+    g_graphs.push_back(g);
+  }
+  g->stamp = ++g_graph_clock;
+  if (g->warm < 1) {                 // first step of a plan: eager (sets kernel attributes, validates the arguments)
+    g->warm += 1;
+    return cbg_sample_step_f32(plan, coef, x_t, c_t, pos_noise, type_uniform, x_next, c_next, v_next, nullptr, nullptr, stream);
+  }
+  Workspace ws;
+  if (int rc = check_ws(plan->workspace, plan->workspace_bytes, plan->n_nodes, plan->n_gen, &ws)) return rc;
+  const int K = plan->num_classes;
+  if (!g->exec) {
+    CBG_CUDA_OK(cudaMallocHost((void**)&g->pinned, sizeof(StepIO) * kIoRing));
+    for (int i = 0; i < kIoRing; ++i) CBG_CUDA_OK(cudaEventCreateWithFlags(&g->ev[i], cudaEventDisableTiming));
+    const long long launches0 = g_cbg_launches;
+    // capture on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
+    // instantiated graph is launched into the caller's stream
+    cudaStream_t cs = nullptr;
+    CBG_CUDA_OK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    CBG_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+    int rc = cbg_launch_step_init_io(ws.io, plan->lig_node, plan->n_lig, K, plan->emb_wt, plan->h_lig_bias, plan->h_static,
+                                     plan->n_nodes, ws.x4, ws.h, cs);
+    if (!rc) rc = run_core(plan->blob, plan->num_layers, ws, plan->graph_ptr, plan->n_graphs, plan->max_graph_nodes,
+                           plan->n_nodes, plan->gen_node, plan->n_gen, plan->mode, plan->k, plan->r_max, plan->rcache,
+                           plan->lig_node, plan->n_lig, plan->prune != 0 && prune_enabled(), cs, plan->static_lists != 0);
+    if (!rc) rc = cbg_launch_classifier(plan->blob, ws.h, plan->lig_node, plan->n_lig, K, ws.w, cs);
+    if (!rc) {
+      ReverseArgs r{};
+      r.x0 = (const float*)ws.x4; r.x0_stride = 4; r.x0_idx = plan->lig_node;
+      r.logits = ws.w; r.gen = plan->gen_lig; r.n_lig = plan->n_lig; r.num_classes = K;
+      rc = cbg_launch_reverse_io(r, ws.io, cs);
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    cudaStreamDestroy(cs);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) { cbg_set_error("cudaStreamEndCapture -> %s", cudaGetErrorString(ce)); return 2; }
+    g->graph = graph;
+    g->kernel_nodes = g_cbg_launches - launches0;      // the launchers counted their (captured) launches
+    g_cbg_launches = launches0;
+    CBG_CUDA_OK(cudaGraphInstantiate(&g->exec, graph, 0));
+  }
+  const int slot = g->next++ % kIoRing;
+  if (g->ev_used[slot]) CBG_CUDA_OK(cudaEventSynchronize(g->ev[slot]));      // the copy that read this slot 64 steps ago
+  StepIO& io = g->pinned[slot];
+  io.x_t = x_t; io.c_t = c_t; io.pos_noise = pos_noise; io.type_u = type_uniform;
+  io.x_next = x_next; io.c_next = c_next; io.v_next = (long long*)v_next;
+  io.c0 = coef->pos_c0; io.ct = coef->pos_ct;
+  io.lac_prev = coef->log_alphas_cumprod_prev; io.l1mac_prev = coef->log_one_minus_alphas_cumprod_prev;
+  io.la = coef->log_alpha; io.l1ma = coef->log_one_minus_alpha;
+  io.logvar = coef->pos_logvar; io.nonzero = coef->pos_nonzero;
+  CBG_CUDA_OK(cudaMemcpyAsync(ws.io, &io, sizeof(StepIO), cudaMemcpyHostToDevice, st));
+  CBG_CUDA_OK(cudaEventRecord(g->ev[slot], st));
+  g->ev_used[slot] = true;
+  CBG_CUDA_OK(cudaGraphLaunch(g->exec, st));
+  g_cbg_launches += g->kernel_nodes;
+  return 0;
+}
+
+int64_t cbg_sample_step_graph_nodes(const cbg_sample_plan* plan, void* stream) {
+  if (!plan) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long key = fnv1a(plan, sizeof(*plan));
+  key = fnv1a(&st, sizeof(st), key);
+  for (StepGraph* c : g_graphs) if (c->key == key && c->exec) return c->kernel_nodes;
   return 0;
 }
 

@@ -121,6 +121,24 @@ struct ReverseArgs {
 // logvar = posterior_logvar[t]; nonzero = 0 at t == 0 else 1
 int cbg_launch_reverse(const ReverseArgs& a, float logvar, float nonzero, cudaStream_t st);
 
+// Per-step inputs / outputs of the TargetDiff step in DEVICE memory: what changes from step to step when the step is
+// replayed from a CUDA graph (cbg_sample_step_graph_f32): the graph's kernels read these through one pointer.
+struct StepIO {
+  const float* x_t;
+  const float* c_t;
+  const float* pos_noise;
+  const float* type_u;
+  float* x_next;
+  float* c_next;
+  long long* v_next;
+  float c0, ct, lac_prev, l1mac_prev, la, l1ma, logvar, nonzero;
+};
+int cbg_launch_step_init_io(const StepIO* io, const int* lig_node, int n_lig, int num_classes, const float* emb_wt,
+                            const float* h_lig_bias, const float* h_static, long long n_nodes, float4* x4, float* h,
+                            cudaStream_t st);
+// the step-invariant members of `a` are used, the per-step ones (x_t, c_t, noise, outputs, coefficients) come from *io
+int cbg_launch_reverse_io(const ReverseArgs& a, const StepIO* io, cudaStream_t st);
+
 // DiffSBDD reverse step: one CTA per graph.
 //   mode 0  zs = z_t / a - b * eps_pred + s * noise              (sample_p_zs_given_zt, diffusion_scheduler.py:1005-1039)
 //   mode 1  zs = a * (z_t - b * eps_pred) + s * noise            (sample_p_xh_given_z0, diffsbdd.py:323-360; a = 1/alpha_0)

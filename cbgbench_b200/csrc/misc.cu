@@ -91,11 +91,11 @@ __global__ void __launch_bounds__(256) classifier_kernel(const float* __restrict
 //   h = W_atom c_lig + (b_atom + indicator)   (PLContextEmbedder.forward, context_emb.py:201-222;
 // the c_lig-independent part is precomputed per atom in h_lig_bias); other rows copy the
 // step-invariant protein embedding h_static.
-__global__ void __launch_bounds__(256) step_init_kernel(const float* __restrict__ x_lig, const float* __restrict__ c_lig,
-                                                        const int* __restrict__ lig_node, int n_lig, int num_classes,
-                                                        const float* __restrict__ emb_wt,   // [K][128]
-                                                        const float* __restrict__ h_lig_bias,  // [n_lig][128]
-                                                        float4* __restrict__ x4, float* __restrict__ h) {
+__device__ __forceinline__ void step_init_body(const float* __restrict__ x_lig, const float* __restrict__ c_lig,
+                                               const int* __restrict__ lig_node, int n_lig, int num_classes,
+                                               const float* __restrict__ emb_wt,   // [K][128]
+                                               const float* __restrict__ h_lig_bias,  // [n_lig][128]
+                                               float4* __restrict__ x4, float* __restrict__ h) {
   const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (a >= n_lig) return;
@@ -109,6 +109,19 @@ __global__ void __launch_bounds__(256) step_init_kernel(const float* __restrict_
     x4[i] = v;
   }
 }
+__global__ void __launch_bounds__(256) step_init_kernel(const float* __restrict__ x_lig, const float* __restrict__ c_lig,
+                                                        const int* __restrict__ lig_node, int n_lig, int num_classes,
+                                                        const float* __restrict__ emb_wt, const float* __restrict__ h_lig_bias,
+                                                        float4* __restrict__ x4, float* __restrict__ h) {
+  step_init_body(x_lig, c_lig, lig_node, n_lig, num_classes, emb_wt, h_lig_bias, x4, h);
+}
+// graph replay: the step's x_t / c_t pointers come from device memory
+__global__ void __launch_bounds__(256) step_init_io_kernel(const StepIO* __restrict__ io, const int* __restrict__ lig_node,
+                                                           int n_lig, int num_classes, const float* __restrict__ emb_wt,
+                                                           const float* __restrict__ h_lig_bias, float4* __restrict__ x4,
+                                                           float* __restrict__ h) {
+  step_init_body(io->x_t, io->c_t, lig_node, n_lig, num_classes, emb_wt, h_lig_bias, x4, h);
+}
 
 // Fused reverse step for one ligand atom per thread.
 //   positions: CTNVPScheduler.backward_remove_noise(type='denoise') diffusion_scheduler.py:144-165
@@ -120,7 +133,7 @@ __device__ __forceinline__ float log_add_exp(float a, float b) {
   return m + logf(expf(a - m) + expf(b - m));
 }
 
-__global__ void __launch_bounds__(128) reverse_kernel(ReverseArgs p, float logvar, float nonzero) {
+__device__ __forceinline__ void reverse_body(const ReverseArgs& p, float logvar, float nonzero) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= p.n_lig) return;
   const int K = p.num_classes;
@@ -169,6 +182,15 @@ __global__ void __launch_bounds__(128) reverse_kernel(ReverseArgs p, float logva
   const int v = gen ? arg : arg_ct;
   p.v_next[a] = v;
   for (int c = 0; c < K; ++c) p.c_next[(size_t)a * K + c] = (c == v) ? 1.f : 0.f;
+}
+
+__global__ void __launch_bounds__(128) reverse_kernel(ReverseArgs p, float logvar, float nonzero) { reverse_body(p, logvar, nonzero); }
+// graph replay: per-step pointers and schedule coefficients come from device memory
+__global__ void __launch_bounds__(128) reverse_io_kernel(ReverseArgs p, const StepIO* __restrict__ io) {
+  p.x_t = io->x_t; p.c_t = io->c_t; p.pos_noise = io->pos_noise; p.type_u = io->type_u;
+  p.x_next = io->x_next; p.c_next = io->c_next; p.v_next = io->v_next;
+  p.c0 = io->c0; p.ct = io->ct; p.lac_prev = io->lac_prev; p.l1mac_prev = io->l1mac_prev; p.la = io->la; p.l1ma = io->l1ma;
+  reverse_body(p, io->logvar, io->nonzero);
 }
 
 // DiffSBDD reverse step + COM projection, one CTA per graph (see SbddArgs)
@@ -409,6 +431,25 @@ int cbg_launch_step_init(const float* x_lig, const float* c_lig, const int* lig_
   step_init_kernel<<<(n_lig + 7) / 8, 256, 0, st>>>(x_lig, c_lig, lig_node, n_lig, num_classes, emb_wt,
                                                     h_lig_bias, x4, h);
   CBG_LAUNCHED(CBG_K_STEP_INIT, st);
+  return 0;
+}
+
+int cbg_launch_step_init_io(const StepIO* io, const int* lig_node, int n_lig, int num_classes, const float* emb_wt,
+                            const float* h_lig_bias, const float* h_static, long long n_nodes, float4* x4, float* h,
+                            cudaStream_t st) {
+  CBG_CUDA_OK(cudaMemcpyAsync(h, h_static, (size_t)n_nodes * CBG_H * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (n_lig <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_STEP_INIT, st);
+  step_init_io_kernel<<<(n_lig + 7) / 8, 256, 0, st>>>(io, lig_node, n_lig, num_classes, emb_wt, h_lig_bias, x4, h);
+  CBG_LAUNCHED(CBG_K_STEP_INIT, st);
+  return 0;
+}
+
+int cbg_launch_reverse_io(const ReverseArgs& a, const StepIO* io, cudaStream_t st) {
+  if (a.n_lig <= 0) return 0;
+  CBG_PROF_BEGIN(CBG_K_REVERSE, st);
+  reverse_io_kernel<<<(a.n_lig + 127) / 128, 128, 0, st>>>(a, io);
+  CBG_LAUNCHED(CBG_K_REVERSE, st);
   return 0;
 }
 

@@ -108,6 +108,8 @@ class BaseDiffB200(nn.Module):
         self.use_rcache = self.allow_rcache and os.environ.get('CBG_RCACHE', '0') == '1'
         # receptive-field pruning of the per-step denoiser (exact for the sampled ligand rows)
         self.use_prune = os.environ.get('CBG_PRUNE', '1') != '0'
+        # replay each denoise step from a CUDA graph captured once per batch (TargetDiff; exact)
+        self.use_graph = os.environ.get('CBG_GRAPH', '1') != '0'
 
     def _build_networks(self, cfg):
         """context_embedder + denoiser, registered AFTER the schedulers like the reference constructors do
@@ -248,6 +250,9 @@ class TargetDiffB200(BaseDiffB200):
         st = _lib.stream_ptr(dev)
         v_scratch = V if V is not None else torch.empty(n_lig, dtype=torch.int64, device=dev)
         launches0 = L.cbg_launch_count()
+        # CUDA-graph replay of the step (bit-identical; CBG_GRAPH=0 or a debug output request keeps the eager path)
+        use_graph = self.use_graph and x0_out is None and logits_out is None
+        keep = []
         with torch.cuda.device(dev):
             for t_idx in t_seq:
                 x_t, c_t = X[t_idx + 1], Cc[t_idx + 1]
@@ -260,6 +265,14 @@ class TargetDiffB200(BaseDiffB200):
                 else:
                     uni = type_uniform[t_idx].to(dev, torch.float32).contiguous()
                 coef = self.step_coef(t_idx)
+                if use_graph:
+                    _lib.check(L.cbg_sample_step_graph_f32(
+                        C.byref(plan), C.byref(coef), x_t.data_ptr(), c_t.data_ptr(), eps.data_ptr(), uni.data_ptr(),
+                        X[t_idx].data_ptr(), Cc[t_idx].data_ptr(), v_scratch.data_ptr(), st))
+                    keep.append((eps, uni))          # the graph reads them after this Python iteration is over
+                    if len(keep) > 80:
+                        keep.pop(0)
+                    continue
                 _lib.check(L.cbg_sample_step_f32(
                     C.byref(plan), C.byref(coef), x_t.data_ptr(), c_t.data_ptr(), eps.data_ptr(), uni.data_ptr(),
                     X[t_idx].data_ptr(), Cc[t_idx].data_ptr(), v_scratch.data_ptr(),

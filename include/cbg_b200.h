@@ -209,6 +209,16 @@ int32_t cbg_sample_step_f32(const cbg_sample_plan* plan, const cbg_step_coef* co
                             float* x0_pred /*[n_lig,3] or NULL*/, float* logits /*[n_lig,K] or NULL*/,
                             void* stream);
 
+/* cbg_sample_step_f32 replayed from a CUDA graph: the first call for a plan runs eagerly, the second captures the step
+ * (its ~85 kernel launches, fork/join events and memsets) on `stream`, later calls cost one small H2D copy of the per-step
+ * pointers / schedule coefficients plus one cudaGraphLaunch.  Results are bit-identical to cbg_sample_step_f32 (same
+ * kernels, same order).  The plan must be unchanged between calls (same contents); x0_pred / logits outputs are not
+ * available on this path.  cbg_sample_step_graph_nodes: kernel launches inside the captured graph (0: not captured yet). */
+int32_t cbg_sample_step_graph_f32(const cbg_sample_plan* plan, const cbg_step_coef* coef,
+                                  const float* x_t, const float* c_t, const float* pos_noise, const float* type_uniform,
+                                  float* x_next, float* c_next, int64_t* v_next, void* stream);
+int64_t cbg_sample_step_graph_nodes(const cbg_sample_plan* plan, void* stream);
+
 /* the reverse step alone (testing / integration hook) */
 int32_t cbg_reverse_step_f32(const cbg_step_coef* coef, const float* x0_pred /*[n,3]*/, const float* logits /*[n,K]*/,
                              const float* x_t, const float* c_t, const uint8_t* gen /*[n]*/,

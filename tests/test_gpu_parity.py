@@ -581,3 +581,24 @@ def test_static_fast_path_and_dynamic_scheduling_are_bit_identical(edge_impl_res
     finally:
         _lib.check(L.cbg_set_option(b'static_fast', 1))
         _lib.check(L.cbg_set_option(b'dyn_sched', 1))
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """cbg_sample_step_graph_f32 (first step eager, second captured, the rest replayed from one CUDA graph) must give
+    the trajectory of the eager per-step path bit for bit - coordinates, one-hot types - on de-novo and
+    partial-generation batches, and report the graph's kernel count as launches."""
+    T = 9
+    for gen_mode, sizes in (('denovo', ([140, 60, 20], [20, 9, 5])), ('partial', ([90, 70], [18, 12]))):
+        model, sd = make_model(T, device=dev())
+        batch = synthetic.make_batch(*sizes, seed=171, gen_mode=gen_mode)
+        n_lig = int(batch['ligand_pos'].shape[0])
+        pn, tu = synthetic.make_noise(T, n_lig, 13, seed=37)
+        model.use_graph = False
+        a = model.sample(batch, pos_noise=pn, type_uniform=tu)
+        eager_launches = model.last_launches
+        model.use_graph = True
+        b = model.sample(batch, pos_noise=pn, type_uniform=tu)
+        for t in range(-1, T):
+            assert torch.equal(a[t][0].cpu(), b[t][0].cpu()), (gen_mode, t)
+            assert torch.equal(a[t][1].cpu(), b[t][1].cpu()), (gen_mode, t)
+        assert model.last_launches == eager_launches          # graph nodes are counted like launches
