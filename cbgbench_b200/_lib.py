@@ -52,6 +52,7 @@ SIGNATURES = {
     'cbg_set_edge_impl': (_I32, [_I32, _I32]),
     'cbg_selftest_umma_f16': (_I32, [_P, _P, _P, _I32, _P]),
     'cbg_debug_x2h_trace': (_I32, [_P, _I32]),
+    'cbg_debug_node_gemm_trace': (_I32, [_P]),
     'cbg_set_option': (_I32, [C.c_char_p, _I32]),
     'cbg_profile_num_families': (_I32, []),
     'cbg_profile_family_name': (C.c_char_p, [_I32]),

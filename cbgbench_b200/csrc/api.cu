@@ -247,9 +247,13 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     g.tch_planes = L + cbg_layout::layer_offset(CBG_LF_X2H_NODE_TCH);
     if (!prune) {
       if (int rc = launch_node_gemm(g, st)) return rc;          // reads h only: may overlap the previous H2X chain
+    } else if (node_gemm_impl() == 2) {
+      // one launch: source planes Pj for every node a needed destination can gather (depth >= l-1), destination planes
+      // Pi / q for the needed destinations only (depth >= l); both lists are prefixes of ws.order
+      NodeGemmArgs gm = g;
+      gm.row_idx = ws.order; gm.n_rows_dev = ws.cnt + l; gm.n_dst_dev = ws.cnt + l + 1;
+      if (int rc = launch_node_gemm(gm, st)) return rc;
     } else {
-      // source planes Pj for every node a needed destination can gather (depth >= l-1), destination planes
-      // Pi / q only for the needed destinations (depth >= l); both lists are prefixes of ws.order
       NodeGemmArgs gp = g;
       gp.row_idx = ws.order; gp.n_rows_dev = ws.cnt + l; gp.n_planes = 2; gp.has_q = 0;
       const bool fork_p = overlap;          // the two X2H GEMMs only read h: run them side by side
@@ -363,6 +367,10 @@ int64_t cbg_launch_count(void) { return g_cbg_launches; }
 int32_t cbg_set_edge_impl(int32_t impl, int32_t warps) { return cbg_edge_set_impl(impl, warps); }
 int32_t cbg_debug_x2h_trace(int64_t* buf_dev, int32_t max_tiles) {
   cbg_x2h_tc_set_trace((long long*)buf_dev, max_tiles);
+  return 0;
+}
+int32_t cbg_debug_node_gemm_trace(int64_t* buf_dev) {
+  cbg_node_gemm_f16_set_trace((long long*)buf_dev);
   return 0;
 }
 int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_from_smem, void* stream) {

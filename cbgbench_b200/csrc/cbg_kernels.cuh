@@ -46,12 +46,17 @@ struct NodeGemmArgs {
   const float* tc_planes;  // plane 0 of the sub-layer
   int tc_first_plane;      // index of this launch's first plane (q second Linear is always plane 5)
   const float* tch_planes; // f16 (hi | lo) images of the same six planes (node_gemm_f16.cu)
+  // f16 kernel only: merged launch - planes >= CBG_NODE_SRC_PLANES (destination planes Pi, q) are computed for the first
+  // min(n_rows, *n_dst_dev) rows of the list only, the source planes Pj for all n_rows (nullptr = no second limit)
+  const int* n_dst_dev;
+  long long* trace;        // debug: globaltimer stamps of CTA 0 (cbg_debug_node_gemm_trace)
 };
 int cbg_launch_node_gemm(const NodeGemmArgs& a, cudaStream_t st);      // fp32 SIMT
 // tcgen05 3xTF32; cluster = 1/2/4 CTAs sharing weight chunks by multicast, 0 = default (env CBG_GEMM_CLUSTER)
 int cbg_launch_node_gemm_tc(const NodeGemmArgs& a, cudaStream_t st, int cluster = 0);
 // tcgen05 kind::f16 with the (hi, lo) split: default
 int cbg_launch_node_gemm_f16(const NodeGemmArgs& a, cudaStream_t st);
+void cbg_node_gemm_f16_set_trace(long long* buf_dev);
 
 // edge.cu
 struct EdgeArgs {

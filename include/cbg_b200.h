@@ -64,6 +64,9 @@ int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_
 /* Debugging: later launches of the tcgen05 attention-weight kernel stamp the pipeline events of CTA 0 (SM clock) into
  * buf_dev[max_tiles][16] (int64, device memory); NULL turns it off.  Process-wide. */
 int32_t cbg_debug_x2h_trace(int64_t* buf_dev, int32_t max_tiles);
+/* debug: %globaltimer stamps (ns) of CTA 0 of every following f16 node-GEMM launch into buf_dev[32] (NULL = off):
+ * [0] start, [1] A tile staged, [2+g] accumulator g complete, [10+g] epilogue of g done, [20] end */
+int32_t cbg_debug_node_gemm_trace(int64_t* buf_dev);
 /* Other TESTING switches of the SIMT kernels (process-wide): "static_fast" = 1 (default; env CBG_STATIC_FAST) lets them
  * skip the coordinate gathers / RBF set-up of nodes whose 32 in-edges are all served from the R-cache (bit-identical);
  * "dyn_sched" = 1 (default; env CBG_DYN_SCHED): their warps draw the next node from a work counter instead of a static
