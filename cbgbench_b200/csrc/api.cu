@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 
 #include <nvtx3/nvToolsExt.h>     // header-only NVTX v3: ranges show up in Nsight Systems, cost nothing without a tool attached
@@ -72,6 +73,7 @@ struct Workspace {
   int* cnt;
   float* ew;
   float* dx;
+  float* hw;                   // H2X on the tcgen05 kernel: alpha * e_w of the generated nodes' edges, compact [n_gen,32,16]
   int* tickets;                // 64 work counters of the X2H launches of one step (dynamic node scheduling)
   unsigned char* fstat;        // per node: all 32 in-edges static this step (written by the edge gate when an R-cache is used)
   StepIO* io;                  // per-step pointers / coefficients of a graph-replayed step (cbg_sample_step_graph_f32)
@@ -96,6 +98,7 @@ Workspace carve(void* base, long long n_nodes, long long n_gen) {
   ws.cnt = (int*)take(96 * 4);
   ws.ew = (float*)take((size_t)n_nodes * CBG_KMAX * 4);
   ws.dx = (float*)take((size_t)(n_gen > 0 ? n_gen : 1) * 16);
+  ws.hw = (float*)take((size_t)(n_gen > 0 ? n_gen : 1) * CBG_KMAX * CBG_HEADS * 4);
   ws.fstat = (unsigned char*)take((size_t)n_nodes);
   ws.tickets = (int*)take(64 * sizeof(int));
   ws.io = (StepIO*)take(sizeof(StepIO));
@@ -202,6 +205,11 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
              float r_max, const float* rcache, const int* cls_idx, int n_cls, bool prune, cudaStream_t st,
              bool static_lists = false) {
   static_lists = static_lists || rcache != nullptr;      // the R-cache is indexed by the static lists
+  // One set of side streams / fork-join events per device (g_aux_dev): two host threads enqueueing denoiser passes on the
+  // same GPU must not interleave their cudaEventRecord / cudaStreamWaitEvent pairs.  Enqueueing is serialised here; the
+  // GPU work itself still overlaps across the callers' streams.
+  static std::mutex core_mutex;
+  std::lock_guard<std::mutex> core_lock(core_mutex);
   NvtxRange nvtx_core("cbg:denoiser");
   if (n_nodes > 0x7fffffffLL / (CBG_KMAX * CBG_HEADS)) { cbg_set_error("n_nodes too large for 32-bit indexing"); return 1; }
   if (int rc = cbg_launch_knn(ws.x4, graph_ptr, n_graphs, max_graph_nodes, mode, k, r_max, 0, static_lists ? ws.snbr : nullptr, ws.nbr, st)) return rc;
@@ -319,6 +327,7 @@ int run_core(const float* blob, int num_layers, const Workspace& ws, const int* 
     EdgeArgs x = e;
     x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
     x.node_idx = gen_idx; x.n_nodes = n_gen; x.n_nodes_dev = nullptr; x.dx = ws.dx; x.rc_k = nullptr; x.rc_v = nullptr; x.fstat = nullptr;
+    x.w = ws.hw;        // the X2H kernels of the next layer use ws.w while this chain runs
     x.ticket = (tickets && num_layers <= 16) ? ws.tickets + 32 + l : nullptr;      // used by the pair kernel only (x2h: 0 .. 2L-1)
     if (int rc = cbg_launch_h2x(x, sx)) return rc;
     if (int rc = cbg_launch_apply_dx(ws.x4, gen_idx, ws.dx, n_gen, sx)) return rc;
@@ -852,7 +861,7 @@ int32_t cbg_bp_step_f32(const cbg_sample_plan* plan, const float* com_blob, int3
       EdgeArgs x{};
       x.x4 = ws.x4; x.nbr = ws.nbr; x.ew = ws.ew;
       x.pj_k = ws.hplane[0]; x.pj_v = ws.hplane[1]; x.pi_k = ws.hplane[2]; x.pi_v = ws.hplane[3]; x.q = ws.hplane[4];
-      x.layer = L; x.w = nullptr; x.h = ws.h; x.node_idx = plan->gen_node; x.n_nodes = n_gen; x.dx = ws.dx;
+      x.layer = L; x.w = ws.hw; x.h = ws.h; x.node_idx = plan->gen_node; x.n_nodes = n_gen; x.dx = ws.dx;
       if (int rc = cbg_launch_h2x(x, st)) return rc;
       if (int rc = cbg_launch_apply_dx(ws.x4, plan->gen_node, ws.dx, n_gen, st)) return rc;
     }

@@ -81,6 +81,7 @@ struct EdgeArgs {
   const unsigned char* fstat;  // x2h with an R-cache: 1 = all 32 in-edges of the node are static (nbr row == its static list)
   long long* trace;      // x2h_tc debugging: per-tile SM-clock stamps of CTA 0 ([tile][16 events]) or nullptr
   int trace_tiles;
+  int w_compact;         // x2h_tc: 1 = w is indexed by the position in node_idx ([n_nodes,32,16], H2X), 0 = by node id
 };
 int cbg_launch_rcache(const float* layers, int num_layers, const float4* x4, const int* snbr, int n_nodes,
                       float* rcache, cudaStream_t st);
@@ -90,6 +91,8 @@ int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st);
 // hardware self-test of the tcgen05 operand conventions (tests): d[128][128] = a[128][32] * b[128][32]^T, f16 inputs
 // debugging: x2h_tc kernels of later launches stamp CTA 0's pipeline events into buf ([max_tiles][16] int64; nullptr = off)
 void cbg_x2h_tc_set_trace(long long* buf, int max_tiles);
+// H2X on the same tcgen05 kernel (generated nodes only): a.w = compact [n_nodes,32,16] scratch, a.dx = [n_nodes,4] out
+int cbg_launch_h2x_tc(const EdgeArgs& a, cudaStream_t st);
 int cbg_launch_umma_selftest(const void* a, const void* b, float* d, int a_from_smem, cudaStream_t st);
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st);
 int cbg_edge_init(void);  // sets max-dynamic-smem attributes once

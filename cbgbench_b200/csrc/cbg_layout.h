@@ -76,7 +76,13 @@
   /* node GEMM weights for the f16 tcgen05 path (node_gemm_f16.cu): the 6 planes of X2H_NODE_TC / H2X_NODE_TC, each as   \
      2 K-chunks x (hi | lo) x [128 n][64 k] f16 of 256 * W in the UMMA canonical K-major layout.  Sizes in floats. */   \
   X(X2H_NODE_TCH, 6 * 2 * 2 * 128 * 64 / 2)                                              \
-  X(H2X_NODE_TCH, 6 * 2 * 2 * 128 * 64 / 2)
+  X(H2X_NODE_TCH, 6 * 2 * 2 * 128 * 64 / 2)                                              \
+  /* tcgen05 H2X kernels (x2h_tc.cu, modes H2X-k / H2X-v): same images for the xk / xv edge MLPs of H2XAttention; the    \
+     second Linear of xv has 16 outputs (one per head): TCW1 = 64 * W1xv as a [16 n][128 k] (hi | lo) image */          \
+  X(H2X_K_TCW1, 2 * 128 * 128 / 2)                                                       \
+  X(H2X_K_TCWG, 2 * 128 * 96 / 2)                                                        \
+  X(H2X_V_TCW1, 2 * 16 * 128 / 2)                                                        \
+  X(H2X_V_TCWG, 2 * 128 * 96 / 2)
 
 // ---- global (per-denoiser) fields -------------------------------------------------------
 #define CBG_GLOBAL_FIELDS(X)                                                             \

@@ -662,6 +662,7 @@ __global__ void __launch_bounds__(256) rcache_kernel(const float* __restrict__ l
 
 int g_num_sms = 0;
 int g_edge_warps = 12;
+int g_h2x_impl = -1;       // -1: follow g_edge_impl; CBG_H2X_IMPL=simt|tc overrides
 int g_edge_impl = 6;       // 6 (default): tcgen05 kernels (x2h_tc.cu); 0: the fp32 SIMT kernels above (tested alternative, R-cache capable)
 int g_h2x_warps = 12;
 
@@ -717,6 +718,10 @@ int cbg_edge_init(void) {
     if (strcmp(e, "simt") == 0 || strcmp(e, "0") == 0) g_edge_impl = 0;
     else if (strcmp(e, "6") == 0 || strcmp(e, "tc") == 0) g_edge_impl = 6;
   }
+  if (const char* e = getenv("CBG_H2X_IMPL")) {
+    if (strcmp(e, "simt") == 0 || strcmp(e, "0") == 0) g_h2x_impl = 0;
+    else if (strcmp(e, "6") == 0 || strcmp(e, "tc") == 0) g_h2x_impl = 6;
+  }
   if (const char* e = getenv("CBG_H2X_WARPS")) {
     const int w = atoi(e);
     if (w == 8 || w == 12 || w == 16) g_h2x_warps = w;
@@ -759,6 +764,9 @@ int cbg_launch_x2h(const EdgeArgs& a, cudaStream_t st) {
 int cbg_launch_h2x(const EdgeArgs& a, cudaStream_t st) {
   if (a.n_nodes <= 0) return 0;
   if (int rc = cbg_edge_init()) return rc;
+  // default: the tcgen05 tile kernel (x2h_tc.cu, needs the compact w scratch); the fp32 SIMT kernel below stays as the
+  // independent cross-check (cbg_set_edge_impl(0) or CBG_H2X_IMPL=simt)
+  if ((g_h2x_impl < 0 ? g_edge_impl : g_h2x_impl) == 6 && a.w != nullptr) return cbg_launch_h2x_tc(a, st);
   switch (g_h2x_warps) {
     case 8: return launch_h2x<8>(a, st);
     case 16: return launch_h2x<16>(a, st);

@@ -46,10 +46,10 @@ __global__ void __launch_bounds__(256) knn_kernel(const float4* __restrict__ x4,
                                                   float r2max, int static_only, const int* __restrict__ snbr,
                                                   int* __restrict__ nbr) {
   extern __shared__ float4 xs[];
-  const int g = blockIdx.y;
+  const int g = blockIdx.x;          // graphs on x (2^31 - 1 blocks), 64-centre chunks on y (<= 200)
   const int s = graph_ptr[g];
   const int n = graph_ptr[g + 1] - s;
-  const int c0 = blockIdx.x * 64;
+  const int c0 = blockIdx.y * 64;
   if (c0 >= n) return;
   for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = x4[s + i];
   __syncthreads();
@@ -342,10 +342,11 @@ int cbg_launch_knn(const float4* x4, const int* graph_ptr, int n_graphs, int max
     CBG_CUDA_OK(cudaFuncSetAttribute(knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_attr = smem;
   }
-  dim3 grid((max_graph_nodes + 63) / 64, n_graphs);
+  dim3 grid(n_graphs, (max_graph_nodes + 63) / 64);
   CBG_PROF_BEGIN(CBG_K_KNN, st);
   knn_kernel<<<grid, 256, smem, st>>>(x4, graph_ptr, k, mode, r_max * r_max, static_only, snbr, nbr);
   CBG_LAUNCHED(CBG_K_KNN, st);
+  if (cudaError_t e = cudaPeekAtLastError()) { cbg_set_error("knn_kernel launch failed: %s", cudaGetErrorString(e)); return 2; }
   return 0;
 }
 

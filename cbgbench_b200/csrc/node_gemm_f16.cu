@@ -5,9 +5,13 @@
 //
 // One CTA = one 128-row tile.  A (rows of h, scaled by 16) is split once per CTA into hi/lo f16 tiles in shared memory
 // (UMMA canonical K-major layout); the weight planes (scaled by 256) are pre-split and pre-laid-out by the packer in
-// 64-wide K chunks (hi | lo = 32 KB) and stream through a 3-stage ring with cp.async.bulk + mbarrier; warp-specialised:
-// 8 staging/epilogue warps, a copy thread, an MMA thread, two TMEM accumulators (plane g+1 accumulates while plane g
+// 64-wide K chunks (hi | lo = 32 KB) and stream through a 2-stage ring with cp.async.bulk + mbarrier; warp-specialised:
+// 8 staging/epilogue warps, a copy thread, an MMA thread, four TMEM accumulators (plane g+1 accumulates while plane g
 // drains).  LayerNorm + ReLU of the q MLP is done out of TMEM and fed back as the A operand of its second Linear.
+// Epilogue: a thread owns one accumulator ROW (tcgen05.ld 32x32b), but a plane row is 512 contiguous bytes in global
+// memory, so each warp transposes its 32 x 32 block through a swizzled shared-memory tile and stores full 128-byte
+// lines (4 rows per instruction).  Storing straight from the TMEM layout (16 B per lane into 32 different rows, half a
+// sector each) made the epilogue, not the MMAs, the per-plane cost: 3.2 us against 0.9 us of tensor time.
 #include "cbg_kernels.cuh"
 #include "cbg_tc.cuh"
 
@@ -18,7 +22,7 @@ namespace {
 constexpr int TM = 128;                        // rows per CTA (UMMA M)
 constexpr int KC = 64;                         // K elements per weight chunk
 constexpr int NKC = CBG_H / KC;                // 2 chunks per plane
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
 constexpr int NACC = 4;                        // TMEM accumulators (128 columns each)
 constexpr uint32_t A_TILE = TM * CBG_H * 2;                // 32 KB per (hi | lo)
 constexpr uint32_t B_CHUNK = 128 * KC * 2;                 // 16 KB per (hi | lo)
@@ -28,7 +32,8 @@ constexpr uint32_t SM_Q = 2 * A_TILE;                      // relu(LN(q hidden))
 constexpr uint32_t SM_B0 = 4 * A_TILE;
 constexpr uint32_t SM_BARS = SM_B0 + STAGES * B_STAGE;
 constexpr uint32_t SM_RED = SM_BARS + 256;                 // [2 passes][2 halves][128 rows] floats
-constexpr uint32_t SM_TOTAL = SM_RED + 2 * 2 * TM * 4;
+constexpr uint32_t SM_STG = SM_RED + 2 * 2 * TM * 4;      // epilogue transpose: [8 warps][32 rows][32 cols] fp32, 16-byte groups XOR-swizzled by row
+constexpr uint32_t SM_TOTAL = SM_STG + 8 * 32 * 32 * 4;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
 constexpr uint32_t A_SBO = (CBG_H / 8) * 128, B_SBO = (KC / 8) * 128, LBO = 128;
 constexpr uint32_t TMEM_COLS = 512;
@@ -126,17 +131,16 @@ __global__ void __launch_bounds__(320, 1) node_gemm_f16_kernel(const __grid_cons
     const bool live = row < n_rows;
     const float* arow = p.a + (size_t)(live ? (p.row_idx ? p.row_idx[row] : row) : 0) * CBG_H;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    {                                              // thread handles k8 = (tid >> 7) + 2 * j, j < 8: all 16 loads in flight
+      float4 v[16];
 #pragma unroll
-    for (int it = 0; it < 8; it += 4) {            // thread handles k8 = (tid >> 7) + 2 * j, j < 8
-      float4 v[8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k8 = (tid >> 7) + 2 * (it + j);
+      for (int j = 0; j < 8; ++j) {
+        const int k8 = (tid >> 7) + 2 * j;
         v[2 * j] = live ? ldg4(arow + 8 * k8) : z;
         v[2 * j + 1] = live ? ldg4(arow + 8 * k8 + 4) : z;
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) store_split8(smem + SM_A_HI, r, (tid >> 7) + 2 * (it + j), v[2 * j], v[2 * j + 1]);
+      for (int j = 0; j < 8; ++j) store_split8(smem + SM_A_HI, r, (tid >> 7) + 2 * j, v[2 * j], v[2 * j + 1]);
     }
     fence_proxy_async();
   }
@@ -194,6 +198,12 @@ __global__ void __launch_bounds__(320, 1) node_gemm_f16_kernel(const __grid_cons
     const int grow = row0 + my_row;
     const int node = (grow < n_rows) ? (p.row_idx ? p.row_idx[grow] : grow) : -1;
     float* red = reinterpret_cast<float*>(smem + SM_RED);
+    float* stg = reinterpret_cast<float*>(smem + SM_STG) + warp * (32 * 32);
+    // store phase of the transpose: lane = (row lane / 8 + 4 i, 16-byte column group lane % 8)
+    const int c4s = lane & 7;
+    int node_s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) node_s[i] = __shfl_sync(CBG_FULL, node, (lane >> 3) + 4 * i);
     for (int g = 0; g < sc.n_gemm; ++g) {
       const int buf = g & (NACC - 1);
       const int kind = sc.kind(g), rel = sc.rel(p, g);
@@ -211,14 +221,26 @@ __global__ void __launch_bounds__(320, 1) node_gemm_f16_kernel(const __grid_cons
         float* out = kind == 2 ? p.out_q : p.out[rel];
         // destination planes / q of a merged launch stop at n_dst
         const bool dst_plane = kind == 2 || p.tc_first_plane + rel >= CBG_NODE_SRC_PLANES;
-        if (node >= 0 && (!dst_plane || grow < n_dst)) {
-          float* o = out + (size_t)node * CBG_H + chalf * 64;
+        const int row_lim = dst_plane ? n_dst : n_rows;      // rows of this tile that exist for this plane
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+        for (int piece = 0; piece < 2; ++piece) {             // 32 columns at a time through the warp's staging tile
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const int j = 8 * piece + c4;
             const float4 b = ldg4(bias + 4 * j);
-            st4(o + 4 * j, make_float4(fmaf(RR(4 * j), kInvAcc, b.x), fmaf(RR(4 * j + 1), kInvAcc, b.y),
-                                       fmaf(RR(4 * j + 2), kInvAcc, b.z), fmaf(RR(4 * j + 3), kInvAcc, b.w)));
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+                make_float4(fmaf(RR(4 * j), kInvAcc, b.x), fmaf(RR(4 * j + 1), kInvAcc, b.y),
+                            fmaf(RR(4 * j + 2), kInvAcc, b.z), fmaf(RR(4 * j + 3), kInvAcc, b.w));
           }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = (lane >> 3) + 4 * i;
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * 32 + ((c4s ^ (rr & 7)) << 2));
+            if (node_s[i] >= 0 && row0 + 32 * q4 + rr < row_lim)
+              st4(out + (size_t)node_s[i] * CBG_H + chalf * 64 + piece * 32 + 4 * c4s, v);
+          }
+          __syncwarp();
         }
       } else {
         // q hidden: + bias, LayerNorm over the row (two halves meet through shared memory; mean first, then the squared

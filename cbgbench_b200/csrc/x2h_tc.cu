@@ -32,6 +32,12 @@
 //   warps 14-15 PROD-Pj   one tile ahead, two node slots each: cp.async of the node's 32 Pj rows into the slot's chunk
 // Pipelining: TMEM holds two pre/activation buffers, so MMA1 of tile t+1 and MMA2 of tile t-1 run while S1 works on
 // tile t and EPI on tile t-1.
+//
+// H2X (repo/modules/attention/h2x_attention.py:34-73) runs on the same kernel over the list of generated nodes:
+//   launch 1  MODE_K with the xk / xq weights -> w = alpha * e_w (compact buffer, indexed by list position)
+//   launch 2  MODE_XV with the xv weights: the second Linear has one output per head (N = 16 MMA), and the epilogue forms
+//             dx_i = (1/16) sum_e (sum_hd w_e,hd (v_e,hd + b1_hd)) (x_i - x_j)     (mean over heads of alpha * v * e_w * rel_x)
+// replacing the fp32 SIMT h2x_kernel (edge.cu), whose 4 GFLOP per launch ran at ~65 % of the fp32 pipe.
 #include <math.h>
 #include "cbg_kernels.cuh"
 #include "cbg_tc.cuh"
@@ -49,6 +55,24 @@ constexpr long long kOffKLn = cbg_layout::layer_offset(CBG_LF_X2H_K_LN);
 constexpr long long kOffVLn = cbg_layout::layer_offset(CBG_LF_X2H_V_LN);
 constexpr long long kOffVB1 = cbg_layout::layer_offset(CBG_LF_X2H_V_B1);
 constexpr long long kOffRbf = cbg_layout::layer_offset(CBG_LF_X2H_K_RBF);
+constexpr long long kOffXKW1 = cbg_layout::layer_offset(CBG_LF_H2X_K_TCW1);
+constexpr long long kOffXKWg = cbg_layout::layer_offset(CBG_LF_H2X_K_TCWG);
+constexpr long long kOffXVW1 = cbg_layout::layer_offset(CBG_LF_H2X_V_TCW1);
+constexpr long long kOffXVWg = cbg_layout::layer_offset(CBG_LF_H2X_V_TCWG);
+constexpr long long kOffXKLn = cbg_layout::layer_offset(CBG_LF_H2X_K_LN);
+constexpr long long kOffXVLn = cbg_layout::layer_offset(CBG_LF_H2X_V_LN);
+constexpr long long kOffXVB1 = cbg_layout::layer_offset(CBG_LF_H2X_V_B1);
+constexpr long long kOffXRbf = cbg_layout::layer_offset(CBG_LF_H2X_RBF);
+
+// what a launch computes; the weight fields it uses travel in TcWeights (filled by the launcher)
+enum { MODE_K = 0, MODE_V = 1, MODE_XV = 2 };
+struct TcWeights {
+  const float* w1;     // (hi | lo) image of the second Linear: [128 n][128 k], MODE_XV [16 n][128 k]
+  const float* wg;     // (hi | lo) image of [Wrf ; c ; Pi columns]
+  const float* ln;     // gamma[128], beta[128]
+  const float* b1;     // second-Linear bias (MODE_V: 128, MODE_XV: 16; unused by MODE_K - it cancels in the softmax)
+  const float* rbf;    // Gaussian offsets [20], coefficient at [20]
+};
 
 // ---- scales (exact powers of two; must match modules.py: tc_f16_image) ----------------------------------------
 constexpr float kScaleG = 1024.f;        // g(d) and the type one-hot in G
@@ -67,6 +91,7 @@ constexpr int NCH = 4;                   // Pj buffers: one 32-row chunk per nod
 constexpr uint32_t PJ_ROW = 528;         // padded row stride: 16-byte row-per-lane reads are bank-conflict free
 constexpr uint32_t PJ_CHUNK = 32 * PJ_ROW;
 constexpr uint32_t W1_IMG = 128 * 128 * 2;            // one (hi | lo) image, bytes
+constexpr uint32_t W1X_IMG = 16 * 128 * 2;            // MODE_XV: 16 output rows
 constexpr uint32_t WG_IMG = 128 * KG * 2;
 constexpr uint32_t W1_SBO = (128 / 8) * 128, WG_SBO = (KG / 8) * 128, LBO = 128;
 constexpr uint32_t SM_W1 = 0;                         // hi | lo
@@ -79,7 +104,8 @@ constexpr uint32_t SM_XCH = SM_RBF + 128;              // sum-of-squares exchang
 constexpr uint32_t SM_QBUF = SM_XCH + 2048;             // EPI: [warp][tile parity][128] q row of the warp's node
 constexpr uint32_t SM_SOFT = SM_QBUF + 4096;            // EPI: [warp][32 edges][17] logits <-> weights transpose
 constexpr uint32_t SM_VRED = SM_QBUF;                   // EPI of the v kernel (aliases QBUF / SOFT): [warp][32 edges][36] transpose
-constexpr uint32_t SM_BAR = SM_QBUF + 4 * 32 * 36 * 4;
+constexpr uint32_t SM_JN = SM_QBUF + 4 * 32 * 36 * 4;   // S1: per-thread slot of the neighbour id prefetched two tiles ahead (cp.async)
+constexpr uint32_t SM_BAR = SM_JN + 2 * 256 * 4;       // [0]: neighbour id, [256 + t]: node id of the tile three ahead
 constexpr int NBAR = 13 + 2 * NCH;
 constexpr uint32_t SM_TOTAL = SM_BAR + 8 * NBAR + 16;
 static_assert(SM_TOTAL <= 232448, "shared memory budget");
@@ -91,7 +117,7 @@ constexpr uint32_t TM_OUT = 256;         // 128: output accumulator of MMA2
 constexpr uint32_t TM_GHI = 384;         // 48 columns = 96 f16
 constexpr uint32_t TM_GLO = 432;         // 40 columns = 80 f16
 constexpr uint32_t TM_COLS = 512;
-constexpr uint32_t IDESC128 = idesc_f16(128), IDESC64 = idesc_f16(64);
+constexpr uint32_t IDESC128 = idesc_f16(128), IDESC16 = idesc_f16(16);
 
 __device__ __forceinline__ int list_len(const EdgeArgs& p) {
   int n = p.n_nodes;
@@ -102,6 +128,11 @@ __device__ __forceinline__ int node_of(const EdgeArgs& p, int n, int n_list) {
   const int nc = n < n_list ? n : n_list - 1;
   return p.node_idx ? p.node_idx[nc] : nc;
 }
+__device__ __forceinline__ float warp_sum_x(float v) {      // fixed butterfly order: deterministic
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CBG_FULL, v, o);
+  return v;
+}
 
 // pipeline event stamps of CTA 0 (debugging; p.trace == nullptr in production: one predicated-off branch per event)
 #define TC_STAMP(k, ev)                                                                                  \
@@ -110,8 +141,9 @@ __device__ __forceinline__ int node_of(const EdgeArgs& p, int n, int n_list) {
   } while (0)
 
 // =================================================================================================================
-template <bool IS_V>
-__global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
+template <int MODE>
+__global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W) {
+  constexpr bool IS_V = MODE == MODE_V, IS_XV = MODE == MODE_XV;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int n_list = list_len(p);
   const int n_tiles = (n_list + 3) >> 2;
@@ -121,10 +153,14 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   const uint32_t bars = sbase + SM_BAR;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * NBAR);
-  const float* L = p.layer;
   const int n_my = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;     // tiles of this CTA: blockIdx.x + k * gridDim.x
   // node of slot `slot` of this CTA's kk-th tile (clamped to the list: surplus slots of the last tile redo the last node)
   auto tile_node = [&](int kk, int slot) { return node_of(p, 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + slot, n_list); };
+  // row of the w buffer: the node id (X2H: [N, 32, 16]) or the list position (H2X: compact [n_list, 32, 16])
+  auto w_row = [&](int kk, int slot, int i) {
+    const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + slot;
+    return p.w_compact ? (n < n_list ? n : n_list - 1) : i;
+  };
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   if (tid == 32) {
@@ -144,10 +180,9 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   {   // LayerNorm affine (pre-multiplied by the activation scale) and the value bias
     float* s_ln = reinterpret_cast<float*>(smem + SM_LN);
     float* s_b1 = reinterpret_cast<float*>(smem + SM_B1);
-    const float* ln = L + (IS_V ? kOffVLn : kOffKLn);
-    if (tid < 256) s_ln[tid] = ln[tid] * kScaleA;
-    else if (tid < 384) s_b1[tid - 256] = IS_V ? L[kOffVB1 + tid - 256] : 0.f;
-    else if (tid < 384 + 24) reinterpret_cast<float*>(smem + SM_RBF)[tid - 384] = L[kOffRbf + tid - 384];
+    if (tid < 256) s_ln[tid] = W.ln[tid] * kScaleA;
+    else if (tid < 384) s_b1[tid - 256] = (IS_V || (IS_XV && tid - 256 < CBG_HEADS)) ? W.b1[tid - 256] : 0.f;
+    else if (tid < 384 + 24) reinterpret_cast<float*>(smem + SM_RBF)[tid - 384] = W.rbf[tid - 384];
   }
   tc_fence_before();
   __syncthreads();
@@ -178,7 +213,9 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     int t_e = 0;
     auto compute_g = [&](const float4 xi, const float4 xj) {
       const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
-      const float d = sqrtf(rx * rx + ry * ry + rz * rz);
+      // explicit operation order: this lambda is inlined at two sites (tile 0 / the pipelined tiles) and the compiler
+      // contracted x*x + y*y + z*z differently at each, so a node's result depended on its position in the CTA's tile list
+      const float d = sqrtf(__fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx))));
       const int fi = node_flags(xi), fj = node_flags(xj);
       t_e = ((fj & 1) ? 0 : 2) + ((fi & 1) ? 0 : 1);
 #pragma unroll
@@ -223,10 +260,34 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_GREADY));
     };
-    // prefetch state of the G builders: coordinates of tile k+1 (C), node + neighbour of tile k+2 (B), node of tile k+3 (A)
-    int iA = 0, iB = 0, jnB = -1;
+    // prefetch state of the G builders: coordinates of tile k+1 (C), node + neighbour of tile k+2 (B), node of tile k+3 (A).
+    // The neighbour id of stage B travels through a per-thread shared-memory slot filled by a 4-byte cp.async: as a
+    // register it was spilled right behind its LDG, and the spill store parked the warp on the load's latency once per
+    // tile (ncu: long-scoreboard stalls on STL in the S1 loop).
+    int iB = 0;
     float4 xiC = make_float4(0.f, 0.f, 0.f, 0.f), xjC = xiC;
     auto fetch_geo = [&](int i, int jn) { xiC = p.x4[i]; xjC = p.x4[jn >= 0 ? jn : i]; };
+    const uint32_t s_jn = sbase + SM_JN + 4u * (uint32_t)(tid - 128);
+    auto issue_jn = [&](int i) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_jn), "l"(p.nbr + (size_t)i * CBG_KMAX + lane) : "memory");
+    };
+    auto take_jn = [&]() {
+      int v;
+      asm volatile("cp.async.wait_all;\n\tld.shared.s32 %0, [%1];" : "=r"(v) : "r"(s_jn) : "memory");
+      return v;
+    };
+    // node id of slot wq of this CTA's kk-th tile, the same way (stage A)
+    auto issue_node = [&](int kk) {
+      const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + wq;
+      const int nc = n < n_list ? n : n_list - 1;
+      if (p.node_idx) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_jn + 1024u), "l"(p.node_idx + nc) : "memory");
+      else asm volatile("st.shared.s32 [%0], %1;" ::"r"(s_jn + 1024u), "r"(nc) : "memory");
+    };
+    auto take_node = [&]() {
+      int v;
+      asm volatile("cp.async.wait_all;\n\tld.shared.s32 %0, [%1];" : "=r"(v) : "r"(s_jn + 1024u) : "memory");
+      return v;
+    };
     {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
       const int i0 = tile_node(0, wq);
       fetch_geo(i0, p.nbr[(size_t)i0 * CBG_KMAX + lane]);
@@ -236,23 +297,19 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         const int i1 = tile_node(1, wq);
         fetch_geo(i1, p.nbr[(size_t)i1 * CBG_KMAX + lane]);
       }
-      if (n_my > 2) { iB = tile_node(2, wq); jnB = p.nbr[(size_t)iB * CBG_KMAX + lane]; }
-      if (n_my > 3) iA = tile_node(3, wq);
+      if (n_my > 2) { iB = tile_node(2, wq); issue_jn(iB); }
+      if (n_my > 3) issue_node(3);
     }
     for (int k = 0; k < n_my; ++k) {
       const int b = k & 1;
       const int c = wq;                                   // this quarter's Pj chunk, refilled once per tile
-      {      // G values of tile k + 1 into registers, then rotate the prefetch registers (the loads land during S1)
-        if (k + 1 < n_my) compute_g(xiC, xjC);
-        if (k + 2 < n_my) fetch_geo(iB, jnB);
-        if (k + 3 < n_my) { iB = iA; jnB = p.nbr[(size_t)iA * CBG_KMAX + lane]; }
-        if (k + 4 < n_my) iA = tile_node(k + 4, wq);
-      }
+      if (k + 1 < n_my) compute_g(xiC, xjC);      // G values of tile k + 1 into registers
       mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready AND G may be rewritten
       tc_fence_after();
       if (warp == 4) TC_STAMP(k, 0);
       if (warp == 8) TC_STAMP(k, 5);
       if (k + 1 < n_my) store_g(k + 1);
+      if (k + 2 < n_my) fetch_geo(iB, take_jn());  // coordinates of tile k + 2: in flight during the S1 body below
       if (warp == 4) TC_STAMP(k, 1);
       mbar_wait(bar(B_PJFULL + c), (uint32_t)(k & 1));
       // ---- S1
@@ -313,6 +370,9 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_AREADY + b));
+      // rotate the index prefetch after the register-pressure peak of the S1 body; consumed after the next tile's MMA1 wait
+      if (k + 3 < n_my) { iB = take_node(); issue_jn(iB); }
+      if (k + 4 < n_my) issue_node(k + 4);
       if (warp == 4) TC_STAMP(k, 4);
       if (warp == 8) TC_STAMP(k, 6);
     }
@@ -326,22 +386,29 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     float* s_vr = reinterpret_cast<float*>(smem + SM_VRED) + wq * (32 * 36);   // v kernel: [edge][36] transpose (aliases the two above)
     // prefetched inputs of the next tile
     int i_n = tile_node(0, wq), i_nn = n_my > 1 ? tile_node(1, wq) : 0;
-    bool valid_n = false;
+    int jn_n = -1;          // raw neighbour id of the next tile's edge (compared where it is used: no stall on the load)
     float ew_n = 0.f, h_n[4] = {0.f, 0.f, 0.f, 0.f};
     float4 w_n[4];
     auto prefetch = [&](int kk, int i) {
       const size_t eoff = (size_t)i * CBG_KMAX + lane;
-      if constexpr (!IS_V) {
-        valid_n = p.nbr[eoff] >= 0;
+      const size_t woff = ((size_t)w_row(kk, wq, i) * CBG_KMAX + lane) * CBG_HEADS;
+      if constexpr (MODE == MODE_K) {
+        jn_n = p.nbr[eoff];
         ew_n = p.ew[eoff];
         cp_async16(smem_u32(s_q + 128 * (kk & 1)) + 16u * (uint32_t)lane, p.q + (size_t)i * CBG_H + 4 * lane);
         asm volatile("cp.async.commit_group;" ::: "memory");
       } else {
-        const float* wi = p.w + eoff * CBG_HEADS;
+        const float* wi = p.w + woff;
 #pragma unroll
         for (int j = 0; j < 4; ++j) w_n[j] = ld4(wi + 4 * j);
+        if constexpr (IS_V) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) h_n[j] = p.h[(size_t)i * CBG_H + 32 * j + lane];
+          for (int j = 0; j < 4; ++j) h_n[j] = p.h[(size_t)i * CBG_H + 32 * j + lane];
+        } else {      // MODE_XV: x_i - x_j of this lane's edge (padded slots: j = i, and their w is zero)
+          const int jn = p.nbr[eoff];
+          const float4 xi = p.x4[i], xj = p.x4[jn >= 0 ? jn : i];
+          h_n[0] = xi.x - xj.x; h_n[1] = xi.y - xj.y; h_n[2] = xi.z - xj.z;
+        }
       }
     };
     prefetch(0, i_n);
@@ -351,10 +418,11 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       const int i = i_n;
       const size_t eoff = (size_t)i * CBG_KMAX + lane;
       // take over this tile's inputs, start the next tile's
-      const bool valid = valid_n;
+      const bool valid = jn_n >= 0;
       const float ew = ew_n;
       float wv[CBG_HEADS], hv[4];
-      if constexpr (IS_V) {
+      const size_t woff = ((size_t)w_row(k, wq, i) * CBG_KMAX + lane) * CBG_HEADS;
+      if constexpr (MODE != MODE_K) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) { wv[4 * j] = w_n[j].x; wv[4 * j + 1] = w_n[j].y; wv[4 * j + 2] = w_n[j].z; wv[4 * j + 3] = w_n[j].w; hv[j] = h_n[j]; }
       } else {
@@ -364,7 +432,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
       i_n = i_nn;
       if (k + 1 < n_my) prefetch(k + 1, i_n);
       if (k + 2 < n_my) i_nn = tile_node(k + 2, wq);
-      if constexpr (!IS_V) {
+      if constexpr (MODE == MODE_K) {
         const float* qs = s_q + 128 * (k & 1);
         float* my = s_sm + lane * 17;
 #pragma unroll
@@ -413,12 +481,28 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         __syncwarp();
         if (live) {      // w = alpha * e_w, this lane's edge row
           const float sc = valid ? ew : 0.f;
-          float* wo = p.w + eoff * CBG_HEADS;
+          float* wo = p.w + woff;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             st4(wo + 4 * j, make_float4(my[4 * j] * sc, my[4 * j + 1] * sc, my[4 * j + 2] * sc, my[4 * j + 3] * sc));
         }
         __syncwarp();
+      } else if constexpr (IS_XV) {
+        // H2X coordinate update: s_e = sum_hd w_e,hd (v_e,hd + b1_hd), dx_i = (1/16) sum_e s_e (x_i - x_j)
+        mbar_wait(bar(B_ACC2), (uint32_t)(k & 1));
+        tc_fence_after();
+        if (warp == 0) TC_STAMP(k, 7);
+        uint32_t r[16];
+        tmem_ld16_nowait(t_lane + TM_OUT, r);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_ACC2FREE));
+        float sacc = 0.f;
+#pragma unroll
+        for (int hd = 0; hd < CBG_HEADS; ++hd) sacc = fmaf(fmaf(__uint_as_float(r[hd]), kInvOut, s_b1[hd]), wv[hd], sacc);
+        const float ax = warp_sum_x(sacc * hv[0]), ay = warp_sum_x(sacc * hv[1]), az = warp_sum_x(sacc * hv[2]);
+        if (live && lane == 0) st4(p.dx + 4 * (size_t)n, make_float4(ax * (1.f / 16.f), ay * (1.f / 16.f), az * (1.f / 16.f), 0.f));
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -473,7 +557,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     // The node's Pi row goes into its K column (84 + slot + 4 * tile parity) of the Wg images (hi, lo); the columns of a
     // tile parity were last read by MMA1 of tile - 2 (the wait below is always for the NEXT completion of that barrier,
     // so the parity wait is sound).  This warp never has copies in flight, which keeps its proxy fence cheap.
-    const float* pi_plane = IS_V ? p.pi_v : p.pi_k;
+    const float* pi_plane = MODE != MODE_K ? p.pi_v : p.pi_k;
     float4 pi_c[4];
     int i_n[4];
 #pragma unroll
@@ -516,24 +600,26 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
     // order (a parity wait is only sound while the waiter can never be two phases ahead of the barrier).  Per (tile,
     // slot): cp.async of the node's 32 Pj rows into the slot's chunk as soon as the slot's S1 warps have consumed the
     // previous tile (warp = one row-coalesced 512-byte copy per instruction).
-    const float* pj_plane = IS_V ? p.pj_v : p.pj_k;
+    const float* pj_plane = MODE != MODE_K ? p.pj_v : p.pj_k;
     const int s0 = warp - 14;                       // slots s0 and s0 + 2
-    int jj_c[2], i_n[2];
+    // neighbour ids are fetched one tile ahead and kept RAW (jn, i): the select jn >= 0 ? jn : i happens where the value is
+    // consumed, one iteration later - selecting right after the load parked this warp on the load's latency (two
+    // dependent global loads per slot) before it could serve the slot's copies (ncu: long-scoreboard stall at the select)
+    int jn_c[2], ic_c[2], i_n[2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      const int i0 = tile_node(0, s0 + 2 * q);
-      const int jn = p.nbr[(size_t)i0 * CBG_KMAX + lane];
-      jj_c[q] = jn >= 0 ? jn : i0;
+      ic_c[q] = tile_node(0, s0 + 2 * q);
+      jn_c[q] = p.nbr[(size_t)ic_c[q] * CBG_KMAX + lane];
       i_n[q] = n_my > 1 ? tile_node(1, s0 + 2 * q) : 0;
     }
     for (int kk = 0; kk < n_my; ++kk) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int slot = s0 + 2 * q;
-        const int jj = jj_c[q];
+        const int jj = jn_c[q] >= 0 ? jn_c[q] : ic_c[q];
         if (kk + 1 < n_my) {      // next tile's neighbours (its node id was fetched one tile earlier)
-          const int jn = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
-          jj_c[q] = jn >= 0 ? jn : i_n[q];
+          ic_c[q] = i_n[q];
+          jn_c[q] = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
           if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
         }
         if (kk >= 1) mbar_wait(bar(B_PJFREE + slot), (uint32_t)((kk - 1) & 1));
@@ -549,16 +635,18 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
   } else if (warp == 12) {
     // ===================================== MMA issuer ============================================================
     if (lane == 0) {
-      mbar_expect_tx(bar(B_WFULL), 2 * W1_IMG + 2 * WG_IMG);
-      bulk_g2s(sbase + SM_W1, L + (IS_V ? kOffVW1 : kOffKW1), 2 * W1_IMG, bar(B_WFULL));
-      bulk_g2s(sbase + SM_WG, L + (IS_V ? kOffVWg : kOffKWg), 2 * WG_IMG, bar(B_WFULL));
+      constexpr uint32_t W1B = IS_XV ? W1X_IMG : W1_IMG;      // bytes of one second-Linear image
+      constexpr uint32_t IDESC2 = IS_XV ? IDESC16 : IDESC128;
+      mbar_expect_tx(bar(B_WFULL), 2 * W1B + 2 * WG_IMG);
+      bulk_g2s(sbase + SM_W1, W.w1, 2 * W1B, bar(B_WFULL));
+      bulk_g2s(sbase + SM_WG, W.wg, 2 * WG_IMG, bar(B_WFULL));
       mbar_wait(bar(B_WFULL), 0u);
       // Descriptors are tile-invariant: build the four bases once; a K step of 16 f16 (two core matrices, 256 bytes)
       // adds 16 to the 14-bit start-address field, so every MMA below costs one integer add and the issue itself
       // (the loops are fully unrolled - a rolled loop spends ~100 cycles per MMA on the uniform datapath, which made the
       // single issuing thread, not the tensor pipe, the limiter of the whole kernel).
       const uint64_t dg_hi = smem_desc(sbase + SM_WG, LBO, WG_SBO), dg_lo = smem_desc(sbase + SM_WG + WG_IMG, LBO, WG_SBO);
-      const uint64_t d1_hi = smem_desc(sbase + SM_W1, LBO, W1_SBO), d1_lo = smem_desc(sbase + SM_W1 + W1_IMG, LBO, W1_SBO);
+      const uint64_t d1_hi = smem_desc(sbase + SM_W1, LBO, W1_SBO), d1_lo = smem_desc(sbase + SM_W1 + W1B, LBO, W1_SBO);
       auto issue_mma2 = [&](int kk) {
         const int bb = kk & 1;
         mbar_wait(bar(B_AREADY + bb), (uint32_t)((kk >> 1) & 1));
@@ -571,11 +659,11 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p) {
         const uint32_t d = tmem + TM_OUT;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)     // small terms first
-          umma_f16_ts(d, a_lo + 8u * ks, d1_hi + 16u * ks, IDESC128, ks > 0 ? 1u : 0u);
+          umma_f16_ts(d, a_lo + 8u * ks, d1_hi + 16u * ks, IDESC2, ks > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, d1_lo + 16u * ks, IDESC128, 1u);
+        for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, d1_lo + 16u * ks, IDESC2, 1u);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, d1_hi + 16u * ks, IDESC128, 1u);
+        for (int ks = 0; ks < 8; ++ks) umma_f16_ts(d, a_hi + 8u * ks, d1_hi + 16u * ks, IDESC2, 1u);
         umma_commit(bar(B_ACC2));
         TC_STAMP(kk, 13);
       };
@@ -674,8 +762,9 @@ int tc_init() {
   int dev = 0;
   CBG_CUDA_OK(cudaGetDevice(&dev));
   CBG_CUDA_OK(cudaDeviceGetAttribute(&g_tc_sms, cudaDevAttrMultiProcessorCount, dev));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<MODE_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<MODE_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<MODE_XV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
   done = true;
   return 0;
 }
@@ -688,14 +777,42 @@ int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st) {
   const int tiles = (a.n_nodes + 3) / 4;
   const int grid = tiles < g_tc_sms ? tiles : g_tc_sms;
   EdgeArgs ak = a;
+  ak.w_compact = 0;
   ak.trace = g_tc_trace; ak.trace_tiles = g_tc_trace_tiles;          // debugging hook: one-shot, the next k kernel launch only
   g_tc_trace = nullptr;
+  EdgeArgs av = a;
+  av.w_compact = 0;
+  const float* L = a.layer;
+  const TcWeights wk{L + kOffKW1, L + kOffKWg, L + kOffKLn, nullptr, L + kOffRbf};
+  const TcWeights wv{L + kOffVW1, L + kOffVWg, L + kOffVLn, L + kOffVB1, L + kOffRbf};
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
-  x2h_tc_kernel<false><<<grid, 512, SM_TOTAL, st>>>(ak);
+  x2h_tc_kernel<MODE_K><<<grid, 512, SM_TOTAL, st>>>(ak, wk);
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
-  x2h_tc_kernel<true><<<grid, 512, SM_TOTAL, st>>>(a);
+  x2h_tc_kernel<MODE_V><<<grid, 512, SM_TOTAL, st>>>(av, wv);
   CBG_LAUNCHED(CBG_K_X2H_V, st);
+  return 0;
+}
+
+// H2X for the listed (generated) nodes: attention weights with the xk / xq weights into the compact buffer a.w
+// ([n_nodes, 32, 16]), then the value head + coordinate update into a.dx ([n_nodes, 4])
+int cbg_launch_h2x_tc(const EdgeArgs& a, cudaStream_t st) {
+  if (a.n_nodes <= 0) return 0;
+  if (int rc = tc_init()) return rc;
+  if (a.node_idx == nullptr || a.w == nullptr || a.dx == nullptr) { cbg_set_error("h2x_tc: node list, w and dx buffers are required"); return 1; }
+  const int tiles = (a.n_nodes + 3) / 4;
+  const int grid = tiles < g_tc_sms ? tiles : g_tc_sms;
+  EdgeArgs ax = a;
+  ax.w_compact = 1; ax.trace = nullptr; ax.trace_tiles = 0;
+  const float* L = a.layer;
+  const TcWeights wk{L + kOffXKW1, L + kOffXKWg, L + kOffXKLn, nullptr, L + kOffXRbf};
+  const TcWeights wv{L + kOffXVW1, L + kOffXVWg, L + kOffXVLn, L + kOffXVB1, L + kOffXRbf};
+  CBG_PROF_BEGIN(CBG_K_H2X, st);
+  x2h_tc_kernel<MODE_K><<<grid, 512, SM_TOTAL, st>>>(ax, wk);
+  CBG_LAUNCHED(CBG_K_H2X, st);
+  CBG_PROF_BEGIN(CBG_K_H2X, st);
+  x2h_tc_kernel<MODE_XV><<<grid, 512, SM_TOTAL, st>>>(ax, wv);
+  CBG_LAUNCHED(CBG_K_H2X, st);
   return 0;
 }
 

@@ -95,6 +95,7 @@ class DiffBPB200(BaseDiffB200):
     def run_steps(self, state, t_seq, X, Cc, pos_noise=None, type_uniform=None, eps_out=None):
         """Enqueue the reverse steps ``t_seq`` (descending t): one ``cbg_bp_step_f32`` call each.  X / Cc as in
         TargetDiffB200.run_steps (slot t+1 = state entering step t, slot t = its result)."""
+        self.check_state(state)
         dev, n_lig, plan = state['device'], state['n_lig'], state['plan']
         com_blob = self.com_head.packed_blob(dev)
         v_scratch = torch.empty(n_lig, dtype=torch.int64, device=dev)

@@ -85,6 +85,7 @@ class DiffSBDDB200(BaseDiffB200):
     @torch.no_grad()
     def run_steps(self, state, t_seq, noise=None):
         """Enqueue the reverse steps ``t_seq`` (descending t): one ``cbg_sbdd_step_f32`` call each."""
+        self.check_state(state)
         K, dev, n_lig, plan = self.num_classes, state['device'], state['n_lig'], state['plan']
         X, Cc = state['X'], state['C']
         to = lambda t: t.to(dev, torch.float32).contiguous()
@@ -106,6 +107,7 @@ class DiffSBDDB200(BaseDiffB200):
     @torch.no_grad()
     def finish(self, state, noise=None):
         """sample_p_xh_given_z0 (diffsbdd.py:323-352): one more denoiser pass at t = 0 -> (x_lig, 4 * c_lig)."""
+        self.check_state(state)
         K, dev, n_lig, plan = self.num_classes, state['device'], state['n_lig'], state['plan']
         X, Cc = state['X'], state['C']
         to = lambda t: t.to(dev, torch.float32).contiguous()

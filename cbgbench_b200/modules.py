@@ -130,17 +130,17 @@ def tc_weight_plane(w):
 
 
 def tc_f16_image(w):
-    """[128 n][K k] matrix (float64, already scaled by its power of two) -> the (hi | lo) f16 operand images of the
+    """[n][K k] matrix (n = 128, or 16 for the H2X value head; float64, already scaled by its power of two) -> the (hi | lo) f16 operand images of the
     tcgen05 X2H kernels (csrc/x2h_tc.cu): w ~= hi + lo, each image in the UMMA canonical K-major / no-swizzle layout
     for 16-bit types (8-row x 8-element core matrices, 128 B apart along K, K/8 * 128 B between 8-row groups).
     Returns the raw bits as an int32 tensor (two f16 per word)."""
     import numpy as np
     w = np.asarray(w, dtype=np.float64)
     n, k = w.shape
-    assert n == 128 and k % 16 == 0
+    assert n % 8 == 0 and k % 16 == 0
     hi = w.astype(np.float16)
     lo = (w - hi.astype(np.float64)).astype(np.float16)
-    imgs = [m.reshape(16, 8, k // 8, 8).transpose(0, 2, 1, 3).reshape(-1) for m in (hi, lo)]
+    imgs = [m.reshape(n // 8, 8, k // 8, 8).transpose(0, 2, 1, 3).reshape(-1) for m in (hi, lo)]
     assert np.isfinite(np.concatenate(imgs).astype(np.float32)).all(), 'f16 overflow in a tensor-core weight image'
     return torch.from_numpy(np.concatenate(imgs).view(np.int32).copy())
 
@@ -219,14 +219,13 @@ def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
             sp = p + sub
             w0k, w0v = _t(sd[sp + kname + '.net.0.weight']), _t(sd[sp + vname + '.net.0.weight'])
             b0k, b0v = _t(sd[sp + kname + '.net.0.bias']), _t(sd[sp + vname + '.net.0.bias'])
-            if tag == 'X2H':
-                # Centre the first Linear of the X2H edge MLPs over the OUTPUT-feature axis: LayerNorm follows it
-                # directly (common.py:151-171), so pre - mean_f(pre) is all that is ever used, and with
-                # W0 <- W0 - mean_f W0, b0 <- b0 - mean_f b0 every piece (Pi, Pj, Wrf g, c) has zero feature mean by
-                # itself.  Exact; the tcgen05 kernels then need only the sum of squares (the other kernels subtract
-                # a mean that is zero up to rounding).
-                w0k, w0v = w0k - w0k.mean(0, keepdim=True), w0v - w0v.mean(0, keepdim=True)
-                b0k, b0v = b0k - b0k.mean(), b0v - b0v.mean()
+            # Centre the first Linear of the edge MLPs (X2H and H2X alike) over the OUTPUT-feature axis: LayerNorm follows
+            # it directly (common.py:151-171), so pre - mean_f(pre) is all that is ever used, and with
+            # W0 <- W0 - mean_f W0, b0 <- b0 - mean_f b0 every piece (Pi, Pj, Wrf g, c) has zero feature mean by
+            # itself.  Exact; the tcgen05 kernels then need only the sum of squares (the SIMT kernels subtract
+            # a mean that is zero up to rounding).
+            w0k, w0v = w0k - w0k.mean(0, keepdim=True), w0v - w0v.mean(0, keepdim=True)
+            b0k, b0v = b0k - b0k.mean(), b0v - b0v.mean()
             wrf_k, c_k, wi_k, wj_k = first_layer_split(w0k)
             wrf_v, c_v, wi_v, wj_v = first_layer_split(w0v)
             wq0_t = _t(sd[sp + qname + '.net.0.weight']).t().contiguous()
@@ -255,15 +254,16 @@ def pack_denoiser_blob(sd, prefix, num_layers, num_classes, com_head=False):
             if tag == 'X2H':
                 put(base, lf, 'X2H_K_RBF', rbf)
                 put(base, lf, 'X2H_V_RBF', rbf)
-                for kv, w0, w1 in (('K', w0k, _t(sd[sp + kname + '.net.3.weight'])),
-                                   ('V', w0v, _t(sd[sp + vname + '.net.3.weight']))):
-                    wg = torch.zeros(HIDDEN, TC_KG, dtype=torch.float64)     # [f][k]: k = 20 t + m | 80 + t | Pi columns
-                    wg[:, 0:80] = w0[:, 4:84]
-                    wg[:, 80:84] = w0[:, 0:4]
-                    put_raw(base, lf, f'X2H_{kv}_TCWG', tc_f16_image((wg * TC_SCALE_WG).numpy()))
-                    put_raw(base, lf, f'X2H_{kv}_TCW1', tc_f16_image((w1 * TC_SCALE_W1).numpy()))
             else:
                 put(base, lf, 'H2X_RBF', rbf)
+            # operand images of the tcgen05 edge kernels (H2X: xv's second Linear has one output per head -> 16 rows)
+            for kv, w0, w1 in (('K', w0k, _t(sd[sp + kname + '.net.3.weight'])),
+                               ('V', w0v, _t(sd[sp + vname + '.net.3.weight']))):
+                wg = torch.zeros(HIDDEN, TC_KG, dtype=torch.float64)     # [f][k]: k = 20 t + m | 80 + t | Pi columns
+                wg[:, 0:80] = w0[:, 4:84]
+                wg[:, 80:84] = w0[:, 0:4]
+                put_raw(base, lf, f'{tag}_{kv}_TCWG', tc_f16_image((wg * TC_SCALE_WG).numpy()))
+                put_raw(base, lf, f'{tag}_{kv}_TCW1', tc_f16_image((w1 * TC_SCALE_W1).numpy()))
     blob32 = blob.to(torch.float32)
     bits = blob32.view(torch.int32)
     for off, b in raw:

@@ -98,6 +98,7 @@ class BaseDiffB200(nn.Module):
         self.num_classes = cfg.num_atomtype
         self._ws = _Workspace()
         self._rc = _Workspace()
+        self._plan_generation = 0      # the workspace is shared by every prepare() of this model: newest plan wins
         self.last_launches = 0
         # Static lists: atoms without gen_flag never move, so their static-only neighbour lists / edge gates are built
         # once per batch (incremental kNN, cached gates; exact).  On by default wherever the pocket is static.
@@ -117,6 +118,13 @@ class BaseDiffB200(nn.Module):
         cfg.embedder.num_atomtype = cfg.num_atomtype
         self.context_embedder = PLContextEmbedderB200(cfg.embedder)
         self.denoiser = get_e3_gnn(cfg.encoder, num_classes=self.num_classes)
+
+    def check_state(self, state):
+        """A state returned by ``prepare`` owns the model's (single, grow-only) device workspace until the next
+        ``prepare``: using an older state would read coordinates / neighbour lists of another batch, so it raises."""
+        if state.get('generation') != self._plan_generation:
+            raise RuntimeError('stale sampling state: prepare() was called again on this model (its device workspace now '
+                               'belongs to the newer batch); finish one batch before preparing the next, or use a second model')
 
     def forward(self, batch):
         raise NotImplementedError(f'{type(self).__name__} is a forward-only sampling build: the training / '
@@ -207,7 +215,8 @@ class BaseDiffB200(nn.Module):
                     lig_node=lig_node, gen_lig8=gen_lig8, gen_node=gen_node, x_nodes=x_nodes,
                     lig_nodes=lig_nodes, gen_nodes_flag=gen_nodes_flag)
         c_lig = F.one_hot(v_lig, num_classes=self.num_classes).float().contiguous()
-        return dict(plan=plan, keep=keep, device=dev, x_lig=x_lig, c_lig=c_lig, batch_idx_lig=bl,
+        self._plan_generation += 1
+        return dict(plan=plan, keep=keep, device=dev, generation=self._plan_generation, x_lig=x_lig, c_lig=c_lig, batch_idx_lig=bl,
                     batch_idx_rec=br, n_lig=n_lig, n_nodes=N, n_graphs=B)
 
 
@@ -243,6 +252,7 @@ class TargetDiffB200(BaseDiffB200):
         """Enqueue the denoise steps ``t_seq`` (descending t).  X [T+1,n_lig,3] / Cc [T+1,n_lig,K]
         hold the trajectory on the device: slot t+1 is the state ENTERING step t, slot t its
         result (slot 0 = traj[-1])."""
+        self.check_state(state)
         L = _lib.lib()
         dev = state['device']
         plan = state['plan']

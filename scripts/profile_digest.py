@@ -22,32 +22,43 @@ def raw_metrics(rep):
     return dict(zip(rows[0], rows[2]))
 
 
+def dram_bytes(rep):
+    """[(kernel name, dram bytes, duration us)] per captured launch of an .ncu-rep"""
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], dict(zip(rows[0], rows[1]))
+    scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    res = []
+    for vals in rows[2:]:
+        m = dict(zip(hdr, vals))
+        tot = sum(float(m[k].replace(',', '')) * scale.get(units[k], 1) for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        res.append((m['Kernel Name'], int(tot), float(m['gpu__time_duration.sum'].replace(',', ''))))
+    return res
+
+
 def main():
+    """python scripts/profile_digest.py <tag> [round]   (round defaults to r02: reads gpurun_out/prof_<round>_*.ncu-rep,
+    launches_<round>.csv, bench_full.json, pytest_gpu.log written by scripts/gpu_r2_validate.sh)"""
     tag = sys.argv[1] if len(sys.argv) > 1 else 'vX'
-    traffic = {'_source': f'ncu --set full --clock-control none, one launch each, bench.py c2 shape (profiles/r01_ncu_*_{tag}.txt)'}
-    for kernel, fam in (('x2h_k_mma2_kernel', 'x2h_k'), ('x2h_v_kernel', 'x2h_v'), ('node_gemm_ws_kernel', None), ('h2x_kernel', None)):
-        rep = os.path.join(OUT, f'prof3_{kernel}.ncu-rep')
-        if not os.path.exists(rep):
+    rnd = sys.argv[2] if len(sys.argv) > 2 else 'r02'
+    traffic = {'_source': f'ncu --set full --clock-control none, bench.py c2 shape (profiles/{rnd}_ncu_*_{tag}.txt)'}
+    for fn in sorted(os.listdir(OUT)):
+        if not (fn.startswith(f'prof_{rnd}_') and fn.endswith('.ncu-rep')):
             continue
+        kernel = fn[len(f'prof_{rnd}_'):-len('.ncu-rep')]
+        rep = os.path.join(OUT, fn)
         txt = subprocess.run([sys.executable, os.path.join(ROOT, 'scripts', 'ncu_summary.py'), rep], capture_output=True, text=True).stdout
-        with open(os.path.join(PROF, f'r01_ncu_{kernel}_{tag}.txt'), 'w') as f:
-            f.write(txt)
-        if fam:
-            m = raw_metrics(rep)
-            scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
-            out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-            rows = list(csv.reader(io.StringIO(out)))
-            units = dict(zip(rows[0], rows[1]))
-            tot = 0.0
-            for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
-                tot += float(m[key].replace(',', '')) * scale.get(units[key], 1)
-            traffic[fam] = {'dram_bytes_per_launch': int(tot), 'duration_us': float(m['gpu__time_duration.sum'].replace(',', '')),
-                            'kernel': kernel}
-    with open(os.path.join(PROF, 'ncu_traffic.json'), 'w') as f:
-        json.dump(traffic, f, indent=1)
-    lst = os.path.join(OUT, 'launches_final.csv')
+        with open(os.path.join(PROF, f'{rnd}_ncu_{kernel}_{tag}.txt'), 'w') as f:
+            f.write(txt.replace(OUT + os.sep, 'gpurun_out/'))
+        if kernel == 'x2h_tc_kernel':       # launch 0 = attention weights (mode 0), launch 1 = aggregation (mode 1)
+            for (name, nbytes, us), fam in zip(dram_bytes(rep), ('x2h_k_tc', 'x2h_v_tc')):
+                traffic[fam] = {'dram_bytes_per_launch': nbytes, 'duration_us': us, 'kernel': name}
+    if len(traffic) > 1:
+        with open(os.path.join(PROF, 'ncu_traffic.json'), 'w') as f:
+            json.dump(traffic, f, indent=1)
+    lst = os.path.join(OUT, f'launches_{rnd}.csv')
     if os.path.exists(lst):
-        shutil.copy(lst, os.path.join(PROF, f'r01_launches_{tag}.csv'))
+        shutil.copy(lst, os.path.join(PROF, f'{rnd}_launches_{tag}.csv'))
         rows = list(csv.reader(open(lst)))
         for i, r in enumerate(rows):
             if 'Kernel Name' in r:
@@ -57,23 +68,29 @@ def main():
         cnt, tot = collections.Counter(), collections.Counter()
         for r in rows[start:]:
             if len(r) > iv:
-                name = r[ik].split('(')[0].replace('void ', '').replace('<unnamed>::', '')[:44]
+                name = r[ik].replace('void ', '').replace('<unnamed>::', '').split('(EdgeArgs')[0].split('(NodeGemm')[0][:52]
                 cnt[name] += 1
                 tot[name] += float(r[iv].replace(',', '')) / 1000.0
         total = sum(tot.values())
-        with open(os.path.join(PROF, f'r01_launch_shares_{tag}.txt'), 'w') as f:
-            f.write('# ncu launch list of `python bench.py --steps 3 --warmup 3 ...` (c2; cold-cache, serialised: compare SHARES)\n')
+        with open(os.path.join(PROF, f'{rnd}_launch_shares_{tag}.txt'), 'w') as f:
+            f.write('# ncu launch list of `CBG_GRAPH=0 python bench.py --steps 3 --warmup 3 ...` (c2; cold-cache, serialised: compare SHARES)\n')
             f.write(f'total {total:.1f} us over {sum(cnt.values())} launches\n')
             for name, v in tot.most_common():
-                f.write(f'{name:44s} n={cnt[name]:3d} total {v:9.1f} us  avg {v / cnt[name]:7.1f}  {100 * v / total:5.1f}%\n')
-    for src, dst in (('bench_full.log', f'r01_bench_{tag}_full.json'), ('bench_f3.log', f'r01_bench_{tag}_f3.json'), ('bench_f2.log', f'r01_bench_{tag}_f2.jsonl'),
-                     ('pytest_gpu.log', f'r01_pytest_gpu_{tag}.log')):
+                f.write(f'{name:52s} n={cnt[name]:3d} total {v:9.1f} us  avg {v / cnt[name]:7.1f}  {100 * v / total:5.1f}%\n')
+    for src, dst in (('bench_full.json', f'{rnd}_bench_{tag}_full.json'), ('pytest_gpu.log', f'{rnd}_pytest_gpu_{tag}.log'),
+                     ('smoke.log', None), ('trace_node_gemm.txt', f'{rnd}_trace_node_gemm_{tag}.txt'),
+                     ('trace_x2h_tc.txt', f'{rnd}_trace_x2h_tc_{tag}.txt')):
         p = os.path.join(OUT, src)
-        if os.path.exists(p):
-            lines = open(p).read().strip().splitlines()
-            with open(os.path.join(PROF, dst), 'w') as f:
-                f.write((lines[-1] if dst.endswith('.json') else '\n'.join(l for l in lines[-6:] if not dst.endswith('.jsonl') or l.startswith('{'))) + '\n')
-    print('profiles updated for', tag)
+        if not os.path.exists(p):
+            continue
+        lines = open(p).read().strip().splitlines()
+        if dst is None:          # smoke line goes to the end of the pytest log
+            with open(os.path.join(PROF, f'{rnd}_pytest_gpu_{tag}.log'), 'a') as f:
+                f.write(lines[-1] + '\n')
+            continue
+        with open(os.path.join(PROF, dst), 'w') as f:
+            f.write((lines[-1] if dst.endswith('.json') else '\n'.join(lines[-40:])) + '\n')
+    print('profiles updated for', rnd, tag)
 
 
 if __name__ == '__main__':

@@ -22,6 +22,7 @@ T = 1000
 model = TargetDiffB200(synthetic.targetdiff_config(num_steps=T))
 model.load_state_dict(synthetic.seeded_state_dict(model, seed=0), strict=True)
 model = model.to(dev).eval()
+model.use_graph = False            # the one-shot trace hook applies to an eager launch, not to a replayed graph
 batch = synthetic.make_batch([300] * 64, [24] * 64, seed=2024)
 state = model.prepare(batch)
 n_lig, K = state['n_lig'], model.num_classes

@@ -343,10 +343,9 @@ def test_node_projections_match_float64(impl, sublayer):
     w0k, w0v = d(kn + '.net.0.weight'), d(vn + '.net.0.weight')
     want = [h64 @ w0k[:, 212:340].T, h64 @ w0v[:, 212:340].T,
             h64 @ w0k[:, 84:212].T + d(kn + '.net.0.bias'), h64 @ w0v[:, 84:212].T + d(vn + '.net.0.bias')]
-    if sublayer == 0:
-        # the packer centres the first Linear of the X2H edge MLPs over the feature axis (exact: LayerNorm follows
-        # it directly), so every plane comes out minus its row mean
-        want = [w - w.mean(-1, keepdim=True) for w in want]
+    # the packer centres the first Linear of the edge MLPs (X2H and H2X) over the feature axis (exact: LayerNorm follows
+    # it directly), so every plane comes out minus its row mean
+    want = [w - w.mean(-1, keepdim=True) for w in want]
     qh = F.layer_norm(h64 @ d(qn + '.net.0.weight').T + d(qn + '.net.0.bias'), (128,), d(qn + '.net.1.weight'),
                       d(qn + '.net.1.bias'), 1e-5).relu()
     want.append((qh @ d(qn + '.net.3.weight').T + d(qn + '.net.3.bias')) / np.sqrt(8.0))

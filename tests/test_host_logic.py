@@ -97,11 +97,26 @@ def test_packing_places_reference_weights():
     w1 = unpack(img[:128 * 128], 128) + unpack(img[128 * 128:], 128)
     w1_ref = 64.0 * den['blocks.4.x2h_layers.0.hv_func.net.3.weight'].double().numpy()
     assert np.abs(w1 - w1_ref).max() < 3e-7 * np.abs(w1_ref).max()
-    # the H2X sub-layer is packed as is
+    # the H2X edge MLPs are centred the same way; the second Linears are packed as they are
+    xk0 = den['blocks.4.h2x_layers.0.xk_func.net.0.weight'].double()
+    xk0c = (xk0 - xk0.mean(0, keepdim=True)).float()
     assert torch.equal(blob[base + lay['layer']['H2X_K_C'][0]: base + lay['layer']['H2X_K_C'][0] + 512].view(4, 128)[1],
-                       den['blocks.4.h2x_layers.0.xk_func.net.0.weight'][:, 1])
+                       xk0c[:, 1])
     o, n = lay['layer']['H2X_V_W1']
     assert torch.equal(blob[base + o: base + o + n].view(16, 128), den['blocks.4.h2x_layers.0.xv_func.net.3.weight'])
+    # f16 images of the tcgen05 H2X kernels: the value head's second Linear is a [16 n][128 k] image
+    o, n = lay['layer']['H2X_V_TCW1']
+    assert n == 16 * 128
+    img = blob.view(torch.int32)[base + o: base + o + n].numpy().view(np.float16)
+    unpack16 = lambda a: a.reshape(2, 16, 8, 8).transpose(0, 2, 1, 3).reshape(16, 128).astype(np.float64)
+    w1x = unpack16(img[:16 * 128]) + unpack16(img[16 * 128:])
+    w1x_ref = 64.0 * den['blocks.4.h2x_layers.0.xv_func.net.3.weight'].double().numpy()
+    assert np.abs(w1x - w1x_ref).max() < 3e-7 * np.abs(w1x_ref).max()
+    o, n = lay['layer']['H2X_K_TCWG']
+    img = blob.view(torch.int32)[base + o: base + o + n].numpy().view(np.float16)
+    wgx = unpack(img[:128 * 96], 96) + unpack(img[128 * 96:], 96)
+    xk64 = xk0 - xk0.mean(0, keepdim=True)
+    assert np.abs(wgx[:, 20 * 1 + 3] - 16.0 * xk64[:, 4 + 20 + 3].numpy()).max() < 16.0 * 3e-7 * float(xk64.abs().max())
     o, n = lay['global']['GATE_RBF']
     rbf = blob[o: o + n]
     assert float(rbf[20]) == -0.5 and float(rbf[1]) == 1.0 and float(rbf[19]) == 10.0

@@ -112,3 +112,30 @@ def test_tcgen05_many_tiles_per_cta_and_ragged_tail(edge_impl_reset):
         outs[impl] = [t.cpu() for t in model.denoiser(*args)]
     for a, b, k in zip(outs[6], outs[0], 'xhc'):
         assert rel_err(a, b) < 1e-5, (k, rel_err(a, b))
+
+
+@pytest.mark.parametrize('gen_mode', ['denovo', 'partial'])
+def test_h2x_tcgen05_matches_simt(gen_mode, edge_impl_reset):
+    """H2X on the tile kernel (attention weights into the compact buffer, then the 16-output value head + coordinate
+    update): coordinates after 1, 2 and all layers against the fp32 SIMT h2x_kernel.  > 4 * 148 generated atoms (every
+    CTA loops) and a count that is not a multiple of the 4-node tile."""
+    L = _lib.lib()
+    model, sd = make_model(10, device=dev(), num_layers=3)
+    n_graphs = 31
+    batch = synthetic.make_batch([60 + 3 * g for g in range(n_graphs)], [24 if g else 23 for g in range(n_graphs)],
+                                 seed=405, gen_mode=gen_mode)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    n_gen = int(gen.sum())
+    if gen_mode == 'denovo':
+        assert n_gen > 4 * 148 and n_gen % 4 != 0
+    args = [t.to(dev()) for t in (x, h, bidx, lig, gen)]
+    outs = {}
+    for impl in (0, 6):
+        _lib.check(L.cbg_set_edge_impl(impl, 0))
+        outs[impl] = [model.denoiser(*args, stop_after_layers=s)[0].cpu() for s in (1, 2, -1)]
+    for a, b, s in zip(outs[6], outs[0], (1, 2, 3)):
+        moved = (a - x).abs().max()
+        assert float(moved) > 1e-3, 'H2X moved nothing'
+        assert torch.equal(a[~gen], x[~gen])
+        assert rel_err(a, b) < 1e-5, (s, rel_err(a, b))
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), s
