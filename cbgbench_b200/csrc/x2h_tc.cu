@@ -19,17 +19,17 @@
 // packer) stay resident in shared memory for the whole persistent CTA.  Nothing of size [E, 128] touches HBM and no
 // R-cache is needed: the only per-edge gather is the 512-byte Pj row (cp.async, L2 resident).
 //
-// Warp roles (16 warps x 128 registers; the scheduler prefers higher warp ids, hence the order):
+// Warp roles (17 warps x 120 registers):
 //   warps 0-3   EPI       thread = edge row, inputs prefetched one tile ahead.  k: <q_i, k> per head, softmax over the
 //                         node's 32 edges through a shared-memory transpose, w = alpha * e_w;
 //                         v: (v + b1v) * w, sum over the node's 32 edges, h_i += .
 //   warps 4-11  S1        thread = (edge row, column half).  S1(tile t): TMEM(pre) + Pj -> LayerNorm (mean-free: the
 //                         packer centres the first Linear over the feature axis) -> ReLU -> (hi, lo) f16 -> TMEM (in
-//                         place).  Each thread also builds its half of the G row of tile t+1 (geometry, type, Gaussian
-//                         smearing -> TMEM): values before, stores right after MMA1(t) has completed
-//   warp 12     MMA       one lane issues every tcgen05.mma / commit (fully unrolled, tile-invariant descriptors)
-//   warp 13     PROD-Pi   up to two tiles ahead: the Pi rows of the tile's four nodes into their K columns of the Wg images
-//   warps 14-15 PROD-Pj   one tile ahead, two node slots each: cp.async of the node's 32 Pj rows into the slot's chunk
+//                         place).  Nothing else: this chain is the longest of the pipeline.
+//   warps 12-15 GP        one per TMEM lane quarter / node slot q, one tile ahead of S1: builds the G rows of the slot's 32
+//                         edges (geometry, type, Gaussian smearing -> TMEM, after MMA1 of the previous tile), writes the
+//                         node's Pi row into its K column of the Wg images, and copies the 32 Pj rows into chunk q (cp.async)
+//   warp 16     MMA       one lane issues every tcgen05.mma / commit (fully unrolled, tile-invariant descriptors)
 // Pipelining: TMEM holds two pre/activation buffers, so MMA1 of tile t+1 and MMA2 of tile t-1 run while S1 works on
 // tile t and EPI on tile t-1.
 //
@@ -39,6 +39,7 @@
 //             dx_i = (1/16) sum_e (sum_hd w_e,hd (v_e,hd + b1_hd)) (x_i - x_j)     (mean over heads of alpha * v * e_w * rel_x)
 // replacing the fp32 SIMT h2x_kernel (edge.cu), whose 4 GFLOP per launch ran at ~65 % of the fp32 pipe.
 #include <math.h>
+#include <stdlib.h>
 #include "cbg_kernels.cuh"
 #include "cbg_tc.cuh"
 
@@ -86,9 +87,18 @@ constexpr float kInvOut = 1.f / 4096.f;  // W1 image is scaled by 64 -> out accu
 // ---- shapes -----------------------------------------------------------------------------------------------------
 constexpr int KG = 96;                   // K of MMA1 (84 used + 8 node one-hot columns (2 tile parities x 4) + 4 zero)
 constexpr int KG_LO = 80;                // the lo part of G is non-zero only in the RBF columns
-constexpr int NCH = 4;                   // Pj buffers: one 32-row chunk per node slot of a tile (refilled for tile t+1 as soon
-                                         // as the slot's S1 warps have consumed tile t)
-constexpr uint32_t PJ_ROW = 528;         // padded row stride: 16-byte row-per-lane reads are bank-conflict free
+// Pj ring: 32-row chunks (one node's in-edges), item n = 4 * tile + slot lives in chunk n % R.  With R = 4 the copy of a
+// slot's next rows could only start once the slot's S1 warps had read the current ones, and the 64 KB burst per tile
+// through L2 (~2.7 K cycles) sat on the S1 critical path.  With R = 6 half of a tile's chunks are fetched a whole tile
+// earlier (all quarters consume at the same time, so extra lead comes in whole tiles).  R is what fits beside the weights:
+// 6 for the attention-weight / H2X kernels, 5 for the aggregation kernel (its epilogue scratch is 18 KB).
+constexpr int NCH_MAX = 6;
+__host__ __device__ constexpr int pj_ring_max(int mode) { return mode == 1 ? 5 : 6; }
+// Pj rows: 512 bytes, 128-byte aligned like their source in global memory, the 16-byte pieces of every 128-byte group
+// XOR-swizzled by (row & 7): the row-per-lane reads of S1 are conflict free AND the cp.async row copies take the ideal 4
+// wavefronts (a 528-byte padded stride cost 10.5 on average: the copies alone were 40 % of the kernel's shared-memory
+// wavefronts, and shared memory - LSU traffic + the B operands of 41 MMAs per tile - is the busiest unit of the kernel)
+constexpr uint32_t PJ_ROW = 512;
 constexpr uint32_t PJ_CHUNK = 32 * PJ_ROW;
 constexpr uint32_t W1_IMG = 128 * 128 * 2;            // one (hi | lo) image, bytes
 constexpr uint32_t W1X_IMG = 16 * 128 * 2;            // MODE_XV: 16 output rows
@@ -96,21 +106,21 @@ constexpr uint32_t WG_IMG = 128 * KG * 2;
 constexpr uint32_t W1_SBO = (128 / 8) * 128, WG_SBO = (KG / 8) * 128, LBO = 128;
 constexpr uint32_t SM_W1 = 0;                         // hi | lo
 constexpr uint32_t SM_WG = SM_W1 + 2 * W1_IMG;
-constexpr uint32_t SM_PJ = SM_WG + 2 * WG_IMG;
-constexpr uint32_t SM_LN = SM_PJ + NCH * PJ_CHUNK;    // gamma * 64 [128] | beta * 64 [128]
+constexpr uint32_t SM_LN = SM_WG + 2 * WG_IMG;        // gamma * 64 [128] | beta * 64 [128]
 constexpr uint32_t SM_B1 = SM_LN + 1024;              // b1v [128]
 constexpr uint32_t SM_RBF = SM_B1 + 512;              // Gaussian offsets [20] + coeff
 constexpr uint32_t SM_XCH = SM_RBF + 128;              // sum-of-squares exchange between the two half-row S1 warps
 constexpr uint32_t SM_QBUF = SM_XCH + 2048;             // EPI: [warp][tile parity][128] q row of the warp's node
 constexpr uint32_t SM_SOFT = SM_QBUF + 4096;            // EPI: [warp][32 edges][17] logits <-> weights transpose
 constexpr uint32_t SM_VRED = SM_QBUF;                   // EPI of the v kernel (aliases QBUF / SOFT): [warp][32 edges][36] transpose
-constexpr uint32_t SM_JN = SM_QBUF + 4 * 32 * 36 * 4;   // S1: per-thread slot of the neighbour id prefetched two tiles ahead (cp.async)
-constexpr uint32_t SM_BAR = SM_JN + 2 * 256 * 4;       // [0]: neighbour id, [256 + t]: node id of the tile three ahead
-constexpr int NBAR = 13 + 2 * NCH;
-constexpr uint32_t SM_TOTAL = SM_BAR + 8 * NBAR + 16;
-static_assert(SM_TOTAL <= 232448, "shared memory budget");
+constexpr int NBAR = 13 + 2 * NCH_MAX;
+// mode-dependent tail of the layout: EPI scratch (k: q rows + softmax transpose, v: the 32 x 36 transposes), barriers, Pj ring
+__host__ __device__ constexpr uint32_t sm_bar(int mode) { return SM_QBUF + (mode == 1 ? 4u * 32 * 36 * 4 : 4096u + 4u * 32 * 17 * 4); }
+__host__ __device__ constexpr uint32_t sm_pj(int mode) { return (sm_bar(mode) + 8u * NBAR + 16u + 127u) & ~127u; }
+__host__ __device__ constexpr uint32_t sm_total(int mode, int nch) { return sm_pj(mode) + (uint32_t)nch * PJ_CHUNK; }
+static_assert(sm_total(0, 6) <= 232448 && sm_total(1, 5) <= 232448 && sm_total(2, 6) <= 232448, "shared memory budget");
 enum { B_WFULL = 0, B_GREADY, B_UNUSED, B_ACC1 /*2*/ = 3, B_AREADY /*2*/ = 5, B_ACC2 /*2*/ = 7, B_ACC2FREE /*2*/ = 9,
-       B_PJFULL = 11, B_PJFREE = 11 + NCH, B_PIREADY /*2*/ = 11 + 2 * NCH };
+       B_PJFULL = 11, B_PJFREE = 11 + NCH_MAX, B_PIREADY /*2*/ = 11 + 2 * NCH_MAX };
 // TMEM columns
 constexpr uint32_t TM_BUF = 0;           // 2 x 128: pre (fp32) -> a_hi (64 cols) | a_lo (64 cols)
 constexpr uint32_t TM_OUT = 256;         // 128: output accumulator of MMA2
@@ -141,8 +151,9 @@ __device__ __forceinline__ float warp_sum_x(float v) {      // fixed butterfly o
   } while (0)
 
 // =================================================================================================================
-template <int MODE>
-__global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W) {
+template <int MODE, int NCH>
+__global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W) {
+  static_assert(NCH >= 4 && NCH <= pj_ring_max(MODE), "Pj ring depth");
   constexpr bool IS_V = MODE == MODE_V, IS_XV = MODE == MODE_XV;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int n_list = list_len(p);
@@ -150,6 +161,7 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   if ((int)blockIdx.x >= n_tiles) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
+  constexpr uint32_t SM_BAR = sm_bar(MODE), SM_PJ = sm_pj(MODE);
   const uint32_t bars = sbase + SM_BAR;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * NBAR);
@@ -165,9 +177,9 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
-    mbar_init(bar(B_GREADY), 8);
-    mbar_init(bar(B_PIREADY), 1);
-    mbar_init(bar(B_PIREADY + 1), 1);
+    mbar_init(bar(B_GREADY), 4);
+    mbar_init(bar(B_PIREADY), 4);
+    mbar_init(bar(B_PIREADY + 1), 4);
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar(B_ACC1 + b), 1);
       mbar_init(bar(B_AREADY + b), 8);
@@ -190,128 +202,25 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   const uint32_t tmem = *tmem_slot;
 
   if (warp >= 4 && warp < 12) {
-    // ===================================== S1 (tile k) + this thread's half of the G row of tile k + 1 ==================
+    // ===================================== S1 (tile k) =================================================================
     // thread = (edge row, column half hf).  S1: pre = TMEM + Pj -> LayerNorm -> ReLU -> (hi, lo) f16 -> TMEM.  The
     // first Linear is centred over the feature axis by the packer, so pre has zero mean and LayerNorm needs only the
-    // sum of squares.  Right after MMA1(k) has completed (the wait below) the G region of TMEM may be rewritten: the
-    // hf = 0 warps build the next tile's G rows there from coordinates prefetched one tile ahead.
+    // sum of squares.  (The G rows, the Pj copies and the Pi columns are produced by the GP warps below: with the G build
+    // inside this loop the S1 chain was ~5.1 K of the 5.6 K cycles per tile - the limiter of the kernel.)
     const int wq = warp & 3, hf = (warp >> 2) - 1;      // warps 4-7: column half 0, 8-11: half 1 (lane quarter = warp % 4)
     const uint32_t t_lane = tmem + ((uint32_t)(32 * wq) << 16);
     const float* s_ln = reinterpret_cast<const float*>(smem + SM_LN) + 64 * hf;
     float* s_x = reinterpret_cast<float*>(smem + SM_XCH);
     const int row = 32 * wq + lane;
-    const float* rbf = reinterpret_cast<const float*>(smem + SM_RBF);
-    const float c2 = rbf[20] * 1.4426950408889634f;      // exp(c u^2) = 2^(c log2(e) u^2)
-
-    // G row of a tile, split between the two half-row warps of the quarter: this thread owns the Gaussians
-    // m = 10 hf .. 10 hf + 9 of its edge row.  compute_g: values in registers (geometry, edge type, Gaussian smearing -
-    // x2h_attention.py:46-52, unitransformer.py:88-99; the factor 1024 of the G scale rides in the exponent), BEFORE the
-    // wait for MMA1 of the current tile; store_g: TMEM stores right after it, so MMA1 of the next tile can be issued as
-    // early as possible.  G_hi: 48 columns (96 f16), G_lo: 40 columns; type block tb occupies columns 10 tb .. 10 tb + 9,
-    // the type / node one-hots columns 40 .. 45 of G_hi (written by the half-0 warp).
-    uint32_t ghi[5], glo[5];
-    int t_e = 0;
-    auto compute_g = [&](const float4 xi, const float4 xj) {
-      const float rx = xi.x - xj.x, ry = xi.y - xj.y, rz = xi.z - xj.z;
-      // explicit operation order: this lambda is inlined at two sites (tile 0 / the pipelined tiles) and the compiler
-      // contracted x*x + y*y + z*z differently at each, so a node's result depended on its position in the CTA's tile list
-      const float d = sqrtf(__fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx))));
-      const int fi = node_flags(xi), fj = node_flags(xj);
-      t_e = ((fj & 1) ? 0 : 2) + ((fi & 1) ? 0 : 1);
-#pragma unroll
-      for (int mp = 0; mp < 5; ++mp) {
-        const float u0 = d - rbf[10 * hf + 2 * mp], u1 = d - rbf[10 * hf + 2 * mp + 1];
-        float g0, g1;
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g0) : "f"(fmaf(c2 * u0, u0, 10.f)));
-        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g1) : "f"(fmaf(c2 * u1, u1, 10.f)));
-        split_pair(g0, g1, ghi[mp], glo[mp]);
-      }
-    };
-    auto store_g = [&](int kk) {
-#pragma unroll
-      for (int tb = 0; tb < 4; ++tb) {
-        const bool on = t_e == tb;
-        const uint32_t col = 10u * tb + 5u * (uint32_t)hf;
-        tmem_st4(t_lane + TM_GHI + col, on ? ghi[0] : 0u, on ? ghi[1] : 0u, on ? ghi[2] : 0u, on ? ghi[3] : 0u);
-        tmem_st1(t_lane + TM_GHI + col + 4u, on ? ghi[4] : 0u);
-        tmem_st4(t_lane + TM_GLO + col, on ? glo[0] : 0u, on ? glo[1] : 0u, on ? glo[2] : 0u, on ? glo[3] : 0u);
-        tmem_st1(t_lane + TM_GLO + col + 4u, on ? glo[4] : 0u);
-      }
-      if (hf == 0) {
-        uint32_t w8[8];
-#pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-          const int col = 40 + cc;                   // f16 pair (2*col, 2*col + 1): k = 80 .. 95
-          uint32_t val = 0u;
-          if (col == 40) {
-            val = (t_e == 0) ? kHalfTypeOne : ((t_e == 1) ? (kHalfTypeOne << 16) : 0u);
-          } else if (col == 41) {
-            val = (t_e == 2) ? kHalfTypeOne : ((t_e == 3) ? (kHalfTypeOne << 16) : 0u);
-          } else if (col < 46) {
-            const int kc = 84 + wq + 4 * (kk & 1);
-            val = ((kc >> 1) == col) ? ((kc & 1) ? (kHalfNodeOne << 16) : kHalfNodeOne) : 0u;
-          }
-          w8[cc] = val;
-        }
-        tmem_st8(t_lane + TM_GHI + 40u, w8);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_GREADY));
-    };
-    // prefetch state of the G builders: coordinates of tile k+1 (C), node + neighbour of tile k+2 (B), node of tile k+3 (A).
-    // The neighbour id of stage B travels through a per-thread shared-memory slot filled by a 4-byte cp.async: as a
-    // register it was spilled right behind its LDG, and the spill store parked the warp on the load's latency once per
-    // tile (ncu: long-scoreboard stalls on STL in the S1 loop).
-    int iB = 0;
-    float4 xiC = make_float4(0.f, 0.f, 0.f, 0.f), xjC = xiC;
-    auto fetch_geo = [&](int i, int jn) { xiC = p.x4[i]; xjC = p.x4[jn >= 0 ? jn : i]; };
-    const uint32_t s_jn = sbase + SM_JN + 4u * (uint32_t)(tid - 128);
-    auto issue_jn = [&](int i) {
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_jn), "l"(p.nbr + (size_t)i * CBG_KMAX + lane) : "memory");
-    };
-    auto take_jn = [&]() {
-      int v;
-      asm volatile("cp.async.wait_all;\n\tld.shared.s32 %0, [%1];" : "=r"(v) : "r"(s_jn) : "memory");
-      return v;
-    };
-    // node id of slot wq of this CTA's kk-th tile, the same way (stage A)
-    auto issue_node = [&](int kk) {
-      const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + wq;
-      const int nc = n < n_list ? n : n_list - 1;
-      if (p.node_idx) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_jn + 1024u), "l"(p.node_idx + nc) : "memory");
-      else asm volatile("st.shared.s32 [%0], %1;" ::"r"(s_jn + 1024u), "r"(nc) : "memory");
-    };
-    auto take_node = [&]() {
-      int v;
-      asm volatile("cp.async.wait_all;\n\tld.shared.s32 %0, [%1];" : "=r"(v) : "r"(s_jn + 1024u) : "memory");
-      return v;
-    };
-    {   // tile 0 is produced here (its loads are exposed once per CTA); tiles 1.. through the prefetch pipeline
-      const int i0 = tile_node(0, wq);
-      fetch_geo(i0, p.nbr[(size_t)i0 * CBG_KMAX + lane]);
-      compute_g(xiC, xjC);
-      store_g(0);
-      if (n_my > 1) {
-        const int i1 = tile_node(1, wq);
-        fetch_geo(i1, p.nbr[(size_t)i1 * CBG_KMAX + lane]);
-      }
-      if (n_my > 2) { iB = tile_node(2, wq); issue_jn(iB); }
-      if (n_my > 3) issue_node(3);
-    }
     for (int k = 0; k < n_my; ++k) {
       const int b = k & 1;
-      const int c = wq;                                   // this quarter's Pj chunk, refilled once per tile
-      if (k + 1 < n_my) compute_g(xiC, xjC);      // G values of tile k + 1 into registers
-      mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready AND G may be rewritten
+      const int item = 4 * k + wq;                        // Pj ring: item n lives in chunk n % NCH, use number n / NCH
+      const int c = item % NCH;
+      mbar_wait(bar(B_ACC1 + b), (uint32_t)((k >> 1) & 1));      // MMA1(k) complete: pre is ready
       tc_fence_after();
       if (warp == 4) TC_STAMP(k, 0);
       if (warp == 8) TC_STAMP(k, 5);
-      if (k + 1 < n_my) store_g(k + 1);
-      if (k + 2 < n_my) fetch_geo(iB, take_jn());  // coordinates of tile k + 2: in flight during the S1 body below
-      if (warp == 4) TC_STAMP(k, 1);
-      mbar_wait(bar(B_PJFULL + c), (uint32_t)(k & 1));
+      mbar_wait(bar(B_PJFULL + c), (uint32_t)((item / NCH) & 1));
       // ---- S1
       const uint32_t t_buf = t_lane + TM_BUF + 128u * (uint32_t)b;
       float v[64];
@@ -321,9 +230,12 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
         tmem_ld32_nowait(t_buf + 64u * hf + 32u, r[1]);
         tmem_wait_ld();
         const uint8_t* prow = smem + SM_PJ + (uint32_t)c * PJ_CHUNK + (uint32_t)lane * PJ_ROW + 256u * hf;
+        uint32_t x7 = (uint32_t)(lane & 7);                // swizzle key of this thread's row
+        asm volatile("" : "+r"(x7));                       // recompute the 16 piece offsets per tile (2 ALU ops each): hoisted out of
+                                                           // the tile loop they are spilled and reloaded through L1 instead
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float4 pj = *reinterpret_cast<const float4*>(prow + 16 * j);
+          const float4 pj = *reinterpret_cast<const float4*>(prow + 128u * (j >> 3) + 16u * ((uint32_t)(j & 7) ^ x7));
           const uint32_t* rv = &r[j >> 3][4 * (j & 7)];
           const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(rv[0]), __uint_as_float(rv[1])),
                                        make_float2(kInvPre, kInvPre), make_float2(pj.x, pj.y));
@@ -370,9 +282,6 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_AREADY + b));
-      // rotate the index prefetch after the register-pressure peak of the S1 body; consumed after the next tile's MMA1 wait
-      if (k + 3 < n_my) { iB = take_node(); issue_jn(iB); }
-      if (k + 4 < n_my) issue_node(k + 4);
       if (warp == 4) TC_STAMP(k, 4);
       if (warp == 8) TC_STAMP(k, 6);
     }
@@ -552,87 +461,150 @@ __global__ void __launch_bounds__(512, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
       }
       if (warp == 0) TC_STAMP(k, 9);
     }
-  } else if (warp == 13) {
-    // ===================================== PROD-Pi: the Pi rows of the tile's four nodes, up to two tiles ahead =======
-    // The node's Pi row goes into its K column (84 + slot + 4 * tile parity) of the Wg images (hi, lo); the columns of a
-    // tile parity were last read by MMA1 of tile - 2 (the wait below is always for the NEXT completion of that barrier,
-    // so the parity wait is sound).  This warp never has copies in flight, which keeps its proxy fence cheap.
+  } else if (warp >= 12 && warp < 16) {
+    // ===================================== GP: everything tile t needs from outside the tensor pipe, for lane quarter q ==
+    // Warp 12 + q serves node slot q (= TMEM lane quarter q, Pj chunk q) of every tile of this CTA, one tile ahead of S1:
+    //   G     thread = edge row: geometry, edge type, 20 Gaussians (x2h_attention.py:46-52, unitransformer.py:88-99; the
+    //         factor 1024 of the G scale rides in the exponent), (hi, lo) f16, tcgen05.st once MMA1 of the previous tile
+    //         has completed (the G region of TMEM is single-buffered).  G_hi: 48 columns (96 f16), G_lo: 40 columns; type
+    //         block tb occupies columns 10 tb .. 10 tb + 9, the type / node one-hots columns 40 .. 45 of G_hi.
+    //   Pi    the node's Pi row into its K column (84 + q + 4 * tile parity) of the Wg images (hi, lo); the columns of a
+    //         tile parity were last read by MMA1 of tile t - 2, complete once MMA1(t - 1) is (in-order completion)
+    //   Pj    cp.async of the node's 32 Pj rows into chunk q as soon as the quarter's S1 warps have consumed tile t - 1
+    // Every chunk / lane quarter has ONE producer warp that walks the tiles in order (a parity wait is only sound while the
+    // waiter can never be two phases ahead of the barrier).  Indices and coordinates are prefetched 1 - 3 tiles ahead and
+    // consumed one iteration after their load was issued.
+    const int q = warp - 12;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+    const float* rbf = reinterpret_cast<const float*>(smem + SM_RBF);
+    const float c2 = rbf[20] * 1.4426950408889634f;      // exp(c u^2) = 2^(c log2(e) u^2)
+    const float* pj_plane = MODE != MODE_K ? p.pj_v : p.pj_k;
     const float* pi_plane = MODE != MODE_K ? p.pi_v : p.pi_k;
-    float4 pi_c[4];
-    int i_n[4];
-#pragma unroll
-    for (int sl = 0; sl < 4; ++sl) {
-      pi_c[sl] = ldg4(pi_plane + (size_t)tile_node(0, sl) * CBG_H + 4 * lane);
-      i_n[sl] = n_my > 1 ? tile_node(1, sl) : 0;
+    // current tile (t): node, raw neighbour id, coordinates, Pi row piece; stage C = tile t + 1 (loads in flight),
+    // stage B = tile t + 2 (node + neighbour id), stage A = tile t + 3 (node id)
+    int i_t = tile_node(0, q);
+    int jn_t = p.nbr[(size_t)i_t * CBG_KMAX + lane];
+    float4 xi_t = p.x4[i_t], xj_t = p.x4[jn_t >= 0 ? jn_t : i_t];
+    auto load_pi = [&](int i) {      // Pi[i][lane + 32 e], e < 4 (coalesced 128-byte rows)
+      const float* r = pi_plane + (size_t)i * CBG_H + lane;
+      return make_float4(__ldg(r), __ldg(r + 32), __ldg(r + 64), __ldg(r + 96));
+    };
+    float4 pi_t = load_pi(i_t);
+    int iC = 0, jnC = -1, iB = 0, jnB = -1, iA = 0;
+    float4 xiC = xi_t, xjC = xj_t, piC = pi_t;
+    if (n_my > 1) {
+      iC = tile_node(1, q);
+      jnC = p.nbr[(size_t)iC * CBG_KMAX + lane];
+      xiC = p.x4[iC]; xjC = p.x4[jnC >= 0 ? jnC : iC];
+      piC = load_pi(iC);
     }
-    for (int kk = 0; kk < n_my; ++kk) {
-      TC_STAMP(kk, 14);
-      if (kk >= 2) mbar_wait(bar(B_ACC1 + (kk & 1)), (uint32_t)((((kk - 2) >> 1)) & 1));
-      else mbar_wait(bar(B_WFULL), 0u);          // the columns live in the Wg images: the bulk copy must have landed
+    if (n_my > 2) { iB = tile_node(2, q); jnB = p.nbr[(size_t)iB * CBG_KMAX + lane]; }
+    if (n_my > 3) iA = tile_node(3, q);
+    mbar_wait(bar(B_WFULL), 0u);          // the Pi columns live in the Wg images: the bulk copy must have landed
+    for (int t = 0; t < n_my; ++t) {
+      if (warp == 12) TC_STAMP(t, 14);
+      // ---- G values of this lane's edge row (explicit operation order: position-independent results)
+      uint32_t ghi[10], glo[10];
+      int t_e;
+      {
+        const float rx = xi_t.x - xj_t.x, ry = xi_t.y - xj_t.y, rz = xi_t.z - xj_t.z;
+        const float d = sqrtf(__fmaf_rn(rz, rz, __fmaf_rn(ry, ry, __fmul_rn(rx, rx))));
+        const int fi = node_flags(xi_t), fj = node_flags(xj_t);
+        t_e = ((fj & 1) ? 0 : 2) + ((fi & 1) ? 0 : 1);
 #pragma unroll
-      for (int sl = 0; sl < 4; ++sl) {
-        const float4 pi4 = pi_c[sl];
-        if (kk + 1 < n_my) {      // next tile's row (its node id was fetched one tile earlier)
-          pi_c[sl] = ldg4(pi_plane + (size_t)i_n[sl] * CBG_H + 4 * lane);
-          if (kk + 2 < n_my) i_n[sl] = tile_node(kk + 2, sl);
+        for (int mp = 0; mp < 10; ++mp) {
+          const float u0 = d - rbf[2 * mp], u1 = d - rbf[2 * mp + 1];
+          float g0, g1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g0) : "f"(fmaf(c2 * u0, u0, 10.f)));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g1) : "f"(fmaf(c2 * u1, u1, 10.f)));
+          split_pair(g0, g1, ghi[mp], glo[mp]);
         }
-        const int kcol = 84 + sl + 4 * (kk & 1);
+      }
+      // ---- G rows into TMEM once MMA1(t - 1) has completed
+      if (t >= 1) { mbar_wait(bar(B_ACC1 + ((t - 1) & 1)), (uint32_t)(((t - 1) >> 1) & 1)); tc_fence_after(); }
+      {
+        uint32_t w[32];
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) w[cc] = (t_e == cc / 10) ? ghi[cc % 10] : 0u;          // G_hi columns 0 .. 31
+        tmem_st32(t_lane + TM_GHI, w);
+        uint32_t w16[16];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) w16[cc] = (t_e == 3) ? ghi[2 + cc] : 0u;                // columns 32 .. 39 (type block 3)
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const int col = 40 + cc;                   // f16 pair (2*col, 2*col + 1): k = 80 .. 95
+          uint32_t val = 0u;
+          if (col == 40) {
+            val = (t_e == 0) ? kHalfTypeOne : ((t_e == 1) ? (kHalfTypeOne << 16) : 0u);
+          } else if (col == 41) {
+            val = (t_e == 2) ? kHalfTypeOne : ((t_e == 3) ? (kHalfTypeOne << 16) : 0u);
+          } else if (col < 46) {
+            const int kc = 84 + q + 4 * (t & 1);
+            val = ((kc >> 1) == col) ? ((kc & 1) ? (kHalfNodeOne << 16) : kHalfNodeOne) : 0u;
+          }
+          w16[8 + cc] = val;
+        }
+        tmem_st16(t_lane + TM_GHI + 32u, w16);
+#pragma unroll
+        for (int cc = 0; cc < 32; ++cc) w[cc] = (t_e == cc / 10) ? glo[cc % 10] : 0u;          // G_lo columns 0 .. 31
+        tmem_st32(t_lane + TM_GLO, w);
+        uint32_t w8[8];
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) w8[cc] = (t_e == 3) ? glo[2 + cc] : 0u;                 // columns 32 .. 39
+        tmem_st8(t_lane + TM_GLO + 32u, w8);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_GREADY));
+      if (warp == 12) TC_STAMP(t, 1);
+      // ---- Pi row of node slot q -> K column 84 + q + 4 * (t & 1) of the Wg images.  Lane = output feature n (+ 32 e):
+      // the elements of a K column are 16 bytes apart inside an 8-row group and the groups alias in the banks, so 32
+      // consecutive n cost 4 wavefronts per store - a lane owning 4 consecutive n cost 16
+      {
+        const int kcol = 84 + q + 4 * (t & 1);
         const uint32_t cbase = (uint32_t)(kcol >> 3) * 128u + (uint32_t)(kcol & 7) * 2u;
-        const float pv[4] = {pi4.x, pi4.y, pi4.z, pi4.w};
+        const float pv[4] = {pi_t.x, pi_t.y, pi_t.z, pi_t.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int nn = 4 * lane + e;
+          const int nn = lane + 32 * e;
           const uint32_t off = (uint32_t)(nn >> 3) * WG_SBO + (uint32_t)(nn & 7) * 16u + cbase;
           const __half hh = __float2half_rn(pv[e]);
           const __half hl = __float2half_rn(pv[e] - __half2float(hh));
           *reinterpret_cast<__half*>(smem + SM_WG + off) = hh;
           *reinterpret_cast<__half*>(smem + SM_WG + WG_IMG + off) = hl;
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(B_PIREADY + (t & 1)));
       }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(B_PIREADY + (kk & 1)));
-      TC_STAMP(kk, 15);
-    }
-  } else if (warp >= 14) {
-    // ===================================== PROD-Pj: the Pj rows of two node slots, one tile ahead ====================
-    // Warp 14 serves node slots 0 and 2, warp 15 slots 1 and 3: every chunk has ONE producer warp that walks the tiles in
-    // order (a parity wait is only sound while the waiter can never be two phases ahead of the barrier).  Per (tile,
-    // slot): cp.async of the node's 32 Pj rows into the slot's chunk as soon as the slot's S1 warps have consumed the
-    // previous tile (warp = one row-coalesced 512-byte copy per instruction).
-    const float* pj_plane = MODE != MODE_K ? p.pj_v : p.pj_k;
-    const int s0 = warp - 14;                       // slots s0 and s0 + 2
-    // neighbour ids are fetched one tile ahead and kept RAW (jn, i): the select jn >= 0 ? jn : i happens where the value is
-    // consumed, one iteration later - selecting right after the load parked this warp on the load's latency (two
-    // dependent global loads per slot) before it could serve the slot's copies (ncu: long-scoreboard stall at the select)
-    int jn_c[2], ic_c[2], i_n[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      ic_c[q] = tile_node(0, s0 + 2 * q);
-      jn_c[q] = p.nbr[(size_t)ic_c[q] * CBG_KMAX + lane];
-      i_n[q] = n_my > 1 ? tile_node(1, s0 + 2 * q) : 0;
-    }
-    for (int kk = 0; kk < n_my; ++kk) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int slot = s0 + 2 * q;
-        const int jj = jn_c[q] >= 0 ? jn_c[q] : ic_c[q];
-        if (kk + 1 < n_my) {      // next tile's neighbours (its node id was fetched one tile earlier)
-          ic_c[q] = i_n[q];
-          jn_c[q] = p.nbr[(size_t)i_n[q] * CBG_KMAX + lane];
-          if (kk + 2 < n_my) i_n[q] = tile_node(kk + 2, slot);
-        }
-        if (kk >= 1) mbar_wait(bar(B_PJFREE + slot), (uint32_t)((kk - 1) & 1));
-        const uint32_t dst = sbase + SM_PJ + (uint32_t)slot * PJ_CHUNK + 16u * (uint32_t)lane;
+      // ---- Pj rows of the node's 32 in-edges into chunk q (one row-coalesced 512-byte copy per instruction)
+      {
+        const int jj = jn_t >= 0 ? jn_t : i_t;
+        const int item = 4 * t + q, c = item % NCH;       // the chunk's previous tenant (item - NCH) must have been consumed
+        if (item >= NCH) mbar_wait(bar(B_PJFREE + c), (uint32_t)((item / NCH - 1) & 1));
+        const uint32_t dst = sbase + SM_PJ + (uint32_t)c * PJ_CHUNK + 16u * (uint32_t)(lane & ~7);
+        const uint32_t l7 = (uint32_t)(lane & 7);
         int jr[32];
 #pragma unroll
         for (int r = 0; r < 32; ++r) jr[r] = __shfl_sync(CBG_FULL, jj, r);       // all shuffles first: no per-row latency chain
 #pragma unroll
-        for (int r = 0; r < 32; ++r) cp_async16(dst + (uint32_t)r * PJ_ROW, pj_plane + (size_t)jr[r] * CBG_H + 4 * lane);
-        cp_async_arrive(bar(B_PJFULL + slot));
+        for (int r = 0; r < 32; ++r)
+          cp_async16(dst + (uint32_t)r * PJ_ROW + 16u * (l7 ^ (uint32_t)(r & 7)), pj_plane + (size_t)jr[r] * CBG_H + 4 * lane);
+        cp_async_arrive(bar(B_PJFULL + c));
       }
+      if (warp == 12) TC_STAMP(t, 15);
+      // ---- rotate the prefetch stages (every value is consumed one iteration after its load was issued)
+      i_t = iC; jn_t = jnC; xi_t = xiC; xj_t = xjC; pi_t = piC;
+      if (t + 2 < n_my) {
+        iC = iB; jnC = jnB;
+        xiC = p.x4[iB]; xjC = p.x4[jnB >= 0 ? jnB : iB];
+        piC = load_pi(iB);
+      }
+      if (t + 3 < n_my) { iB = iA; jnB = p.nbr[(size_t)iA * CBG_KMAX + lane]; }
+      if (t + 4 < n_my) iA = tile_node(t + 4, q);
     }
-  } else if (warp == 12) {
+  } else if (warp == 16) {
     // ===================================== MMA issuer ============================================================
     if (lane == 0) {
       constexpr uint32_t W1B = IS_XV ? W1X_IMG : W1_IMG;      // bytes of one second-Linear image
@@ -752,8 +724,16 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(const __half* a, 
 }
 
 int g_tc_sms = 0;
+int g_ring_k = 4, g_ring_v = 5;      // Pj ring depths (measured at c2: the attention-weight kernel is fastest with 4, the aggregation kernel with 5)
 long long* g_tc_trace = nullptr;
 int g_tc_trace_tiles = 0;
+
+template <int MODE>
+void launch_tc(int ring, int grid, cudaStream_t st, const EdgeArgs& a, const TcWeights& w) {
+  if (ring == 4) x2h_tc_kernel<MODE, 4><<<grid, 544, sm_total(MODE, 4), st>>>(a, w);
+  else if (ring == 5 || MODE == MODE_V) x2h_tc_kernel<MODE, 5><<<grid, 544, sm_total(MODE, 5), st>>>(a, w);
+  else x2h_tc_kernel<MODE, (MODE == MODE_V ? 5 : 6)><<<grid, 544, sm_total(MODE, MODE == MODE_V ? 5 : 6), st>>>(a, w);
+}
 
 int tc_init() {
   static bool done_dev[CBG_MAX_DEVICES] = {};
@@ -762,9 +742,16 @@ int tc_init() {
   int dev = 0;
   CBG_CUDA_OK(cudaGetDevice(&dev));
   CBG_CUDA_OK(cudaDeviceGetAttribute(&g_tc_sms, cudaDevAttrMultiProcessorCount, dev));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<MODE_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<MODE_V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
-  CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<MODE_XV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL));
+  {
+    const char* e = getenv("CBG_PJ_RING");          // "<k><v>", e.g. 45: ring depth of the attention-weight (4..6) and aggregation (4..5) kernels
+    if (e && e[0] >= '4' && e[0] <= '6') g_ring_k = e[0] - '0';
+    if (e && e[0] && e[1] >= '4' && e[1] <= '5') g_ring_v = e[1] - '0';
+  }
+#define TC_ATTR(MODE, N) CBG_CUDA_OK(cudaFuncSetAttribute(x2h_tc_kernel<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_total(MODE, N)))
+  TC_ATTR(MODE_K, 4); TC_ATTR(MODE_K, 5); TC_ATTR(MODE_K, 6);
+  TC_ATTR(MODE_V, 4); TC_ATTR(MODE_V, 5);
+  TC_ATTR(MODE_XV, 4); TC_ATTR(MODE_XV, 5); TC_ATTR(MODE_XV, 6);
+#undef TC_ATTR
   done = true;
   return 0;
 }
@@ -786,10 +773,10 @@ int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st) {
   const TcWeights wk{L + kOffKW1, L + kOffKWg, L + kOffKLn, nullptr, L + kOffRbf};
   const TcWeights wv{L + kOffVW1, L + kOffVWg, L + kOffVLn, L + kOffVB1, L + kOffRbf};
   CBG_PROF_BEGIN(CBG_K_X2H_K, st);
-  x2h_tc_kernel<MODE_K><<<grid, 512, SM_TOTAL, st>>>(ak, wk);
+  launch_tc<MODE_K>(g_ring_k, grid, st, ak, wk);
   CBG_LAUNCHED(CBG_K_X2H_K, st);
   CBG_PROF_BEGIN(CBG_K_X2H_V, st);
-  x2h_tc_kernel<MODE_V><<<grid, 512, SM_TOTAL, st>>>(av, wv);
+  launch_tc<MODE_V>(g_ring_v, grid, st, av, wv);
   CBG_LAUNCHED(CBG_K_X2H_V, st);
   return 0;
 }
@@ -808,10 +795,10 @@ int cbg_launch_h2x_tc(const EdgeArgs& a, cudaStream_t st) {
   const TcWeights wk{L + kOffXKW1, L + kOffXKWg, L + kOffXKLn, nullptr, L + kOffXRbf};
   const TcWeights wv{L + kOffXVW1, L + kOffXVWg, L + kOffXVLn, L + kOffXVB1, L + kOffXRbf};
   CBG_PROF_BEGIN(CBG_K_H2X, st);
-  x2h_tc_kernel<MODE_K><<<grid, 512, SM_TOTAL, st>>>(ax, wk);
+  launch_tc<MODE_K>(g_ring_k, grid, st, ax, wk);
   CBG_LAUNCHED(CBG_K_H2X, st);
   CBG_PROF_BEGIN(CBG_K_H2X, st);
-  x2h_tc_kernel<MODE_XV><<<grid, 512, SM_TOTAL, st>>>(ax, wv);
+  launch_tc<MODE_XV>(g_ring_k, grid, st, ax, wv);
   CBG_LAUNCHED(CBG_K_H2X, st);
   return 0;
 }
