@@ -83,6 +83,19 @@ SIGNATURES = {
     'cbg_pocket_stats_f32': (_I32, [_P, _P, _I32, _P, _P, _I32, _P, _P, _P]),
     'cbg_sample_ligand_sizes': (_I32, [_P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     'cbg_build_batch_f32': (_I32, [_P, _P]),
+    'cbg_ipa_head_floats': (_I64, [_I32]),
+    'cbg_ipa_layer_floats': (_I64, [_I32]),
+    'cbg_ipa_head_fields': (_I32, []),
+    'cbg_ipa_layer_fields': (_I32, []),
+    'cbg_ipa_head_field_name': (C.c_char_p, [_I32]),
+    'cbg_ipa_layer_field_name': (C.c_char_p, [_I32]),
+    'cbg_ipa_head_field_offset': (_I64, [_I32, _I32]),
+    'cbg_ipa_head_field_size': (_I64, [_I32, _I32]),
+    'cbg_ipa_layer_field_offset': (_I64, [_I32, _I32]),
+    'cbg_ipa_layer_field_size': (_I64, [_I32, _I32]),
+    'cbg_ipa_workspace_bytes': (_I64, [_I64, _I32]),
+    'cbg_ipa_forward_f32': (_I32, [_P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _I32, _I32, _P, _P, _I64, _I32,
+                                   _P, _P, _P, _P, _P, _P, _I64, _P]),
     'cbg_reverse_step_f32': (_I32, [C.POINTER(StepCoef), _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P]),
 }
 

@@ -427,11 +427,14 @@ class UniTransformerB200(nn.Module):
 
 
 def get_e3_gnn(cfg, num_classes=None, num_edge_classes=None):
-    """Mirror of repo/modules/e3nn/__init__.py:5-18 for the one encoder type on the hot path."""
+    """Mirror of repo/modules/e3nn/__init__.py:5-18 for the encoder types built here."""
     if num_classes is not None:
         cfg.num_classes = num_classes
     if num_edge_classes is not None:
         cfg.num_edge_classes = num_edge_classes
     if cfg_get(cfg, 'type') == 'unitransformer':
         return UniTransformerB200(cfg)
-    raise ValueError(f"cbgbench_b200 implements encoder type 'unitransformer' only, got {cfg_get(cfg, 'type')}")
+    if cfg_get(cfg, 'type') in ('ipatransformer', 'itatransformer'):      # row f4; the shipped D3FG config spells it 'itatransformer'
+        from .ipatransformer import IPATransformerB200
+        return IPATransformerB200(cfg)
+    raise ValueError(f"cbgbench_b200 implements encoder types 'unitransformer' and 'ipatransformer', got {cfg_get(cfg, 'type')}")

@@ -182,3 +182,41 @@ def seeded_state_dict(model, seed=0, skip_prefixes=('pos_scheduler.', 'type_sche
 
 
 __all__ = ['Cfg', 'targetdiff_config', 'diffsbdd_config', 'make_sbdd_noise', 'diffbp_config', 'make_bp_noise', 'make_batch', 'make_noise', 'seeded_state_dict', 'cfg_get']
+
+
+# ---- IPATransformer (D3FG encoder) -----------------------------------------------------------
+# (name, hidden, num_layers, num_classes, nodes per graph, functional-group ("ligand") nodes per graph, data seed, gen mode)
+IPA_CASES = [
+    ('h256_two_graphs', 256, 3, 8, [70, 45], [6, 4], 31, 'denovo'),        # shipped width (d3fg_fg.yml:5), one graph > k + 1
+    ('h256_ragged', 256, 2, 12, [120, 20, 9], [8, 3, 2], 32, 'partial'),   # graphs below k + 1 nodes, partial generation
+    ('h128_single', 128, 2, 8, [90], [7], 33, 'denovo'),
+]
+IPA_WEIGHT_SEED = 5
+
+
+def ipa_config(hidden, num_layers, num_classes, **extra):
+    return Cfg(dict(type='ipatransformer', node_feat_dim=hidden, n_heads=16, num_layers=num_layers,
+                    num_classes=num_classes, **extra))
+
+
+def make_ipa_inputs(hidden, n_nodes, n_lig, seed, gen_mode='denovo'):
+    """Composed node arrays of the D3FG encoder in the layout compose_context produces ([protein | ligand] per graph):
+    (x [N,3], o [N,3] so3 vectors, h [N,hidden], batch_idx, lig_flag, gen_flag)."""
+    rs = np.random.RandomState(seed)
+    xs, os_, hs, bs, ligs, gens = [], [], [], [], [], []
+    for g, (n, nl) in enumerate(zip(n_nodes, n_lig)):
+        x = rs.normal(0.0, 6.0, size=(n, 3))
+        x[n - nl:] = rs.normal(0.0, 1.5, size=(nl, 3))
+        xs.append(x)
+        os_.append(rs.normal(0.0, 0.6, size=(n, 3)))
+        hs.append(rs.normal(0.0, 1.0, size=(n, hidden)))
+        bs.append(np.full(n, g))
+        lig = np.zeros(n, dtype=bool)
+        lig[n - nl:] = True
+        gen = lig.copy()
+        if gen_mode == 'partial':
+            gen[n - nl: n - nl + (2 * nl) // 3] = False
+        ligs.append(lig)
+        gens.append(gen)
+    cat = lambda a, dt: torch.from_numpy(np.concatenate(a, 0).astype(dt))
+    return (cat(xs, np.float32), cat(os_, np.float32), cat(hs, np.float32), cat(bs, np.int64), cat(ligs, bool), cat(gens, bool))

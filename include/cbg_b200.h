@@ -349,6 +349,31 @@ typedef struct cbg_batch_spec {
 
 int32_t cbg_build_batch_f32(const cbg_batch_spec* spec, void* stream);
 
+/* ---- D3FG encoder `IPATransformer` (repo/modules/e3nn/itatransformer.py:14-145) --------------
+ * X2H-only encoder (InvAttentionLayer :147-188, coordinates fixed) at hidden width 128 or 256 (configs/denovo/train/
+ * d3fg_fg.yml:5: 256), then the rotation / translation / type heads and the SO(3) update (:127-145):
+ *   eps_pos [N,3], h [N,H], o_next [N,3] (so3 vector), R_next [N,3,3], logits [N,K]
+ * = IPATransformer.forward(x, o, h, batch_idx, lig_flag, gen_flag).  Weights: one blob = the global block of the denoiser
+ * layout (edge-gate fields) | head block | num_sublayers layer blocks; the field table below is the single source of
+ * truth the Python packer queries (cbgbench_b200/ipatransformer.py). */
+int64_t cbg_ipa_head_floats(int32_t hidden);
+int64_t cbg_ipa_layer_floats(int32_t hidden);
+int32_t cbg_ipa_head_fields(void);
+int32_t cbg_ipa_layer_fields(void);
+const char* cbg_ipa_head_field_name(int32_t field);
+const char* cbg_ipa_layer_field_name(int32_t field);
+int64_t cbg_ipa_head_field_offset(int32_t hidden, int32_t field);
+int64_t cbg_ipa_head_field_size(int32_t hidden, int32_t field);
+int64_t cbg_ipa_layer_field_offset(int32_t hidden, int32_t field);
+int64_t cbg_ipa_layer_field_size(int32_t hidden, int32_t field);
+int64_t cbg_ipa_workspace_bytes(int64_t n_nodes, int32_t hidden);
+int32_t cbg_ipa_forward_f32(const float* blob, int32_t hidden, int32_t num_sublayers /* num_layers * num_x2h */,
+                            int32_t num_blocks, int32_t num_classes, const float* x /*[N,3]*/, const float* o /*[N,3]*/,
+                            const float* h /*[N,hidden]*/, const int32_t* graph_ptr /*[B+1]*/, int32_t n_graphs,
+                            int32_t max_graph_nodes, const uint8_t* lig_flag, const uint8_t* gen_flag, int64_t n_nodes,
+                            int32_t k, float* eps_pos, float* h_out, float* o_next, float* r_next, float* logits,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
