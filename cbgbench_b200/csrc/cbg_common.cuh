@@ -1,5 +1,6 @@
 // Shared device helpers for the cbg_b200 kernels (sm_100a).
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "cbg_layout.h"
@@ -44,6 +45,26 @@ void cbg_prof_mark(int family, int is_end, cudaStream_t st);
     g_cbg_launches += 1;                                      \
     if (g_cbg_prof_on) cbg_prof_mark((family), 1, (st));      \
   } while (0)
+
+// Launch with (or without) programmatic stream serialization: the kernel may be scheduled before the previous kernel of
+// the stream has finished; it must execute griddepcontrol.wait (cbg_tc.cuh: pdl_wait) before touching anything that
+// kernel produces or still reads.  Off unless CBG_PDL=1 (measured at c2 / c1 under graph replay: no gain).
+inline bool cbg_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("CBG_PDL"); on = (e && e[0] == '1') ? 1 : 0; }      // opt-in: measured neutral under graph replay
+  return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t cbg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cbg_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

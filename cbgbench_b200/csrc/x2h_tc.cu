@@ -156,24 +156,17 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   static_assert(NCH >= 4 && NCH <= pj_ring_max(MODE), "Pj ring depth");
   constexpr bool IS_V = MODE == MODE_V, IS_XV = MODE == MODE_XV;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int n_list = list_len(p);
-  const int n_tiles = (n_list + 3) >> 2;
-  if ((int)blockIdx.x >= n_tiles) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   constexpr uint32_t SM_BAR = sm_bar(MODE), SM_PJ = sm_pj(MODE);
+  constexpr uint32_t W1B = IS_XV ? W1X_IMG : W1_IMG;      // bytes of one second-Linear image
   const uint32_t bars = sbase + SM_BAR;
   auto bar = [&](int i) { return bars + 8u * (uint32_t)i; };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_BAR + 8 * NBAR);
-  const int n_my = (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1;     // tiles of this CTA: blockIdx.x + k * gridDim.x
-  // node of slot `slot` of this CTA's kk-th tile (clamped to the list: surplus slots of the last tile redo the last node)
-  auto tile_node = [&](int kk, int slot) { return node_of(p, 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + slot, n_list); };
-  // row of the w buffer: the node id (X2H: [N, 32, 16]) or the list position (H2X: compact [n_list, 32, 16])
-  auto w_row = [&](int kk, int slot, int i) {
-    const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + slot;
-    return p.w_compact ? (n < n_list ? n : n_list - 1) : i;
-  };
 
+  // ---- prologue: nothing here reads what the previous kernel of the stream produces (weights are constants), so with a
+  // programmatic dependent launch it overlaps that kernel's tail; pdl_wait() below is the dependency
+  pdl_launch_dependents();
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
@@ -188,6 +181,9 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
     }
     for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 32); mbar_init(bar(B_PJFREE + c), 2); }
     fence_mbar_init();
+    mbar_expect_tx(bar(B_WFULL), 2 * W1B + 2 * WG_IMG);          // resident weight images: two bulk (TMA) copies
+    bulk_g2s(sbase + SM_W1, W.w1, 2 * W1B, bar(B_WFULL));
+    bulk_g2s(sbase + SM_WG, W.wg, 2 * WG_IMG, bar(B_WFULL));
   }
   {   // LayerNorm affine (pre-multiplied by the activation scale) and the value bias
     float* s_ln = reinterpret_cast<float*>(smem + SM_LN);
@@ -196,12 +192,26 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
     else if (tid < 384) s_b1[tid - 256] = (IS_V || (IS_XV && tid - 256 < CBG_HEADS)) ? W.b1[tid - 256] : 0.f;
     else if (tid < 384 + 24) reinterpret_cast<float*>(smem + SM_RBF)[tid - 384] = W.rbf[tid - 384];
   }
+  pdl_wait();
+  const int n_list = list_len(p);
+  const int n_tiles = (n_list + 3) >> 2;
+  const bool has_work = (int)blockIdx.x < n_tiles;
+  const int n_my = has_work ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;     // tiles of this CTA: blockIdx.x + k * gridDim.x
+  // node of slot `slot` of this CTA's kk-th tile (clamped to the list: surplus slots of the last tile redo the last node)
+  auto tile_node = [&](int kk, int slot) { return node_of(p, 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + slot, n_list); };
+  // row of the w buffer: the node id (X2H: [N, 32, 16]) or the list position (H2X: compact [n_list, 32, 16])
+  auto w_row = [&](int kk, int slot, int i) {
+    const int n = 4 * ((int)blockIdx.x + kk * (int)gridDim.x) + slot;
+    return p.w_compact ? (n < n_list ? n : n_list - 1) : i;
+  };
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= 4 && warp < 12) {
+  if (!has_work) {
+    if (tid == 32) mbar_wait(bar(B_WFULL), 0u);      // (device-side list shorter than the grid) the bulk copies must land before the CTA exits
+  } else if (warp >= 4 && warp < 12) {
     // ===================================== S1 (tile k) =================================================================
     // thread = (edge row, column half hf).  S1: pre = TMEM + Pj -> LayerNorm -> ReLU -> (hi, lo) f16 -> TMEM.  The
     // first Linear is centred over the feature axis by the packer, so pre has zero mean and LayerNorm needs only the
@@ -607,11 +617,7 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   } else if (warp == 16) {
     // ===================================== MMA issuer ============================================================
     if (lane == 0) {
-      constexpr uint32_t W1B = IS_XV ? W1X_IMG : W1_IMG;      // bytes of one second-Linear image
       constexpr uint32_t IDESC2 = IS_XV ? IDESC16 : IDESC128;
-      mbar_expect_tx(bar(B_WFULL), 2 * W1B + 2 * WG_IMG);
-      bulk_g2s(sbase + SM_W1, W.w1, 2 * W1B, bar(B_WFULL));
-      bulk_g2s(sbase + SM_WG, W.wg, 2 * WG_IMG, bar(B_WFULL));
       mbar_wait(bar(B_WFULL), 0u);
       // Descriptors are tile-invariant: build the four bases once; a K step of 16 f16 (two core matrices, 256 bytes)
       // adds 16 to the 14-bit start-address field, so every MMA below costs one integer add and the issue itself
@@ -730,9 +736,9 @@ int g_tc_trace_tiles = 0;
 
 template <int MODE>
 void launch_tc(int ring, int grid, cudaStream_t st, const EdgeArgs& a, const TcWeights& w) {
-  if (ring == 4) x2h_tc_kernel<MODE, 4><<<grid, 544, sm_total(MODE, 4), st>>>(a, w);
-  else if (ring == 5 || MODE == MODE_V) x2h_tc_kernel<MODE, 5><<<grid, 544, sm_total(MODE, 5), st>>>(a, w);
-  else x2h_tc_kernel<MODE, (MODE == MODE_V ? 5 : 6)><<<grid, 544, sm_total(MODE, MODE == MODE_V ? 5 : 6), st>>>(a, w);
+  if (ring == 4) cbg_launch_pdl(x2h_tc_kernel<MODE, 4>, dim3(grid), dim3(544), sm_total(MODE, 4), st, a, w);
+  else if (ring == 5 || MODE == MODE_V) cbg_launch_pdl(x2h_tc_kernel<MODE, 5>, dim3(grid), dim3(544), sm_total(MODE, 5), st, a, w);
+  else cbg_launch_pdl(x2h_tc_kernel<MODE, (MODE == MODE_V ? 5 : 6)>, dim3(grid), dim3(544), sm_total(MODE, MODE == MODE_V ? 5 : 6), st, a, w);
 }
 
 int tc_init() {

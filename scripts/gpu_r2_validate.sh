@@ -14,13 +14,18 @@ try:
     print({k:round(v['ms_per_step'],3) for k,v in (d.get('kernels') or {}).items() if v['ms_per_step']>0.03})
 except Exception as e: print('parse fail', e); print(open('gpurun_out/bench_full.json').read()[-800:])
 PY
+timeout 300 python scripts/trace_x2h_tc.py > gpurun_out/trace_x2h_tc.txt 2>&1; echo "x2h trace rc=$?"; tail -13 gpurun_out/trace_x2h_tc.txt | cut -c1-160
 timeout 200 python scripts/trace_node_gemm.py > gpurun_out/trace_node_gemm.txt 2>&1; echo "trace rc=$?"; tail -15 gpurun_out/trace_node_gemm.txt | cut -c1-200
 CMD="python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --profile-steps 0"
 CBG_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 200 --csv \
     --log-file gpurun_out/launches_r02.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
-for K in x2h_tc_kernel node_gemm_f16_kernel h2x_kernel; do
-  CBG_GRAPH=0 timeout 500 ncu --set full --clock-control none --import-source on -k regex:$K -s 8 -c 2 \
+for w in c1 c3 c5; do
+  timeout 300 python bench.py --workload $w --steps 20 --warmup 5 --no-cpu-baseline --e2e-steps 100 > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+  echo "$w: $(cut -c1-160 gpurun_out/bench_$w.json | tail -1)"
+done
+for K in x2h_tc_kernel node_gemm_f16_kernel; do
+  CBG_GRAPH=0 timeout 500 ncu --set full --clock-control none --import-source on -k regex:$K -s 8 -c 4 \
       -f -o gpurun_out/prof_r02_$K $CMD > gpurun_out/ncu_r02_$K.log 2>&1
   echo "$K exit $?"
 done

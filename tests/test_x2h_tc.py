@@ -139,3 +139,18 @@ def test_h2x_tcgen05_matches_simt(gen_mode, edge_impl_reset):
         assert torch.equal(a[~gen], x[~gen])
         assert rel_err(a, b) < 1e-5, (s, rel_err(a, b))
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), s
+
+
+def test_tcgen05_repeated_runs_are_bit_identical(edge_impl_reset):
+    """The Pj ring, the Pi columns and the TMEM buffers are handed between warps through mbarriers only (cp.async +
+    mbarrier arrive; no bar.sync a race detector could see): a lost hand-over would show up as run-to-run differences.
+    Config-2-sized forward (every CTA loops ~35 times), 8 repeats, outputs must be bit-identical."""
+    model, sd = make_model(10, device=dev(), num_layers=3)
+    batch = synthetic.make_batch([300] * 64, [24] * 64, seed=2024)
+    x, h, bidx, lig, gen = composed_inputs(sd, batch)
+    args = [t.to(dev()) for t in (x, h, bidx, lig, gen)]
+    first = [t.clone() for t in model.denoiser(*args)]
+    for _ in range(7):
+        again = model.denoiser(*args)
+        for a, b in zip(first, again):
+            assert torch.equal(a, b)
