@@ -69,8 +69,13 @@ struct Sched {
   }
   __device__ __forceinline__ int kind(int g) const { return has_q ? (g == 0 ? 1 : (g == n_gemm - 1 ? 2 : 0)) : 0; }
   // plane relative to the launch's first plane (bias / out index); q second Linear: -1
+  // The plain planes are visited in an order rotated by the CTA index: every CTA streams the same weight images from L2,
+  // and without the rotation all of them pull the same lines at the same moment.
   __device__ __forceinline__ int rel(const NodeGemmArgs& p, int g) const {
-    return has_q ? (g == 0 ? p.n_planes - 1 : (g == n_gemm - 1 ? -1 : g - 1)) : g;
+    if (has_q && g == 0) return p.n_planes - 1;
+    if (has_q && g == n_gemm - 1) return -1;
+    const int idx = has_q ? g - 1 : g;
+    return n_norm > 1 ? (idx + (int)(blockIdx.x % (unsigned)n_norm)) % n_norm : idx;
   }
 };
 // weight image of GEMM g: NKC chunks x (hi | lo) x [128 n][64 k] f16; image 5 = q second Linear

@@ -119,7 +119,7 @@ __host__ __device__ constexpr uint32_t sm_bar(int mode) { return SM_QBUF + (mode
 __host__ __device__ constexpr uint32_t sm_pj(int mode) { return (sm_bar(mode) + 8u * NBAR + 16u + 127u) & ~127u; }
 __host__ __device__ constexpr uint32_t sm_total(int mode, int nch) { return sm_pj(mode) + (uint32_t)nch * PJ_CHUNK; }
 static_assert(sm_total(0, 6) <= 232448 && sm_total(1, 5) <= 232448 && sm_total(2, 6) <= 232448, "shared memory budget");
-enum { B_WFULL = 0, B_GREADY, B_UNUSED, B_ACC1 /*2*/ = 3, B_AREADY /*2*/ = 5, B_ACC2 /*2*/ = 7, B_ACC2FREE /*2*/ = 9,
+enum { B_WFULL = 0 /* Wg images */, B_GREADY, B_W1FULL /* W1 images */, B_ACC1 /*2*/ = 3, B_AREADY /*2*/ = 5, B_ACC2 /*2*/ = 7, B_ACC2FREE /*2*/ = 9,
        B_PJFULL = 11, B_PJFREE = 11 + NCH_MAX, B_PIREADY /*2*/ = 11 + 2 * NCH_MAX };
 // TMEM columns
 constexpr uint32_t TM_BUF = 0;           // 2 x 128: pre (fp32) -> a_hi (64 cols) | a_lo (64 cols)
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
+    mbar_init(bar(B_W1FULL), 1);
     mbar_init(bar(B_GREADY), 4);
     mbar_init(bar(B_PIREADY), 4);
     mbar_init(bar(B_PIREADY + 1), 4);
@@ -181,9 +182,22 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
     }
     for (int c = 0; c < NCH; ++c) { mbar_init(bar(B_PJFULL + c), 32); mbar_init(bar(B_PJFREE + c), 2); }
     fence_mbar_init();
-    mbar_expect_tx(bar(B_WFULL), 2 * W1B + 2 * WG_IMG);          // resident weight images: two bulk (TMA) copies
-    bulk_g2s(sbase + SM_W1, W.w1, 2 * W1B, bar(B_WFULL));
-    bulk_g2s(sbase + SM_WG, W.wg, 2 * WG_IMG, bar(B_WFULL));
+    // Resident weight images by bulk (TMA) copies.  Wg first on its own barrier: MMA1 of the first tile needs only Wg,
+    // W1 is not read before MMA2 (a tile's S1 later).  Every CTA of the grid reads the same 112 KB at the same moment, so
+    // each image goes in four pieces whose order is rotated by the CTA index: at any time the CTAs pull different L2 lines.
+    mbar_expect_tx(bar(B_WFULL), 2 * WG_IMG);
+    mbar_expect_tx(bar(B_W1FULL), 2 * W1B);
+    const uint32_t rot = blockIdx.x & 3u;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+      const uint32_t pc = (i + rot) & 3u, nb = (2 * WG_IMG) / 4;
+      bulk_g2s(sbase + SM_WG + pc * nb, reinterpret_cast<const uint8_t*>(W.wg) + pc * nb, nb, bar(B_WFULL));
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+      const uint32_t pc = (i + rot) & 3u, nb = (2 * W1B) / 4;
+      bulk_g2s(sbase + SM_W1 + pc * nb, reinterpret_cast<const uint8_t*>(W.w1) + pc * nb, nb, bar(B_W1FULL));
+    }
   }
   {   // LayerNorm affine (pre-multiplied by the activation scale) and the value bias
     float* s_ln = reinterpret_cast<float*>(smem + SM_LN);
@@ -210,7 +224,7 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   const uint32_t tmem = *tmem_slot;
 
   if (!has_work) {
-    if (tid == 32) mbar_wait(bar(B_WFULL), 0u);      // (device-side list shorter than the grid) the bulk copies must land before the CTA exits
+    if (tid == 32) { mbar_wait(bar(B_WFULL), 0u); mbar_wait(bar(B_W1FULL), 0u); }      // (device-side list shorter than the grid) the bulk copies must land before the CTA exits
   } else if (warp >= 4 && warp < 12) {
     // ===================================== S1 (tile k) =================================================================
     // thread = (edge row, column half hf).  S1: pre = TMEM + Pj -> LayerNorm -> ReLU -> (hi, lo) f16 -> TMEM.  The
@@ -634,6 +648,7 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
         // one N = 128 accumulator: an MMA costs ~64 cycles whether N is 64 or 128 (measured: two N = 64 halves took 3.0K
         // cycles per tile, twice the N = 128 figure), so the output is not split
         if (kk > 0) { mbar_wait(bar(B_ACC2FREE), (uint32_t)((kk - 1) & 1)); tc_fence_after(); }
+        else mbar_wait(bar(B_W1FULL), 0u);                      // first use of the W1 images
         const uint32_t d = tmem + TM_OUT;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)     // small terms first
