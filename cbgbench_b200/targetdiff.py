@@ -51,8 +51,12 @@ class PLContextEmbedderB200(nn.Module):
         emb_dim = cfg_get(cfg, 'emb_dim', 128)
         self.emb_dim = emb_dim
         if cfg_get(cfg, 'time', None) is not None or cfg_get(cfg, 'vec', None) is not None:
-            raise NotImplementedError('time / vec embeddings are not used by any shipped CBGBench config '
-                                      'and are not implemented on the B200 path')
+            # Not only unused by every shipped config: the reference's own time path cannot run.  PLContextEmbedder passes
+            # t as [N, 1] (context_emb.py:184-185) into SinusoidalPosEmb, whose x[:, None] (common.py:146) makes the
+            # embedding [N, 1, 128]; "h_lig + t_emb_lig" (context_emb.py:224) then broadcasts h to [N, N, 128] and
+            # compose_context raises (common.py:209).  Verified against the live reference.
+            raise NotImplementedError('time / vec embeddings are not used by any shipped CBGBench config (the reference\'s '
+                                      'own time-embedding path raises a shape error) and are not implemented on the B200 path')
         atom = cfg_get(cfg, 'atom', None)
         res = cfg_get(cfg, 'residue', None)
         if atom is None or res is None or cfg_get(atom, 'type') != 'linear' or cfg_get(res, 'type') != 'linear':
