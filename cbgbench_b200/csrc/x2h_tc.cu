@@ -40,6 +40,7 @@
 // replacing the fp32 SIMT h2x_kernel (edge.cu), whose 4 GFLOP per launch ran at ~65 % of the fp32 pipe.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "cbg_kernels.cuh"
 #include "cbg_tc.cuh"
 
@@ -167,6 +168,9 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   // ---- prologue: nothing here reads what the previous kernel of the stream produces (weights are constants), so with a
   // programmatic dependent launch it overlaps that kernel's tail; pdl_wait() below is the dependency
   pdl_launch_dependents();
+  // debugging: CTA 0 stamps kernel entry / end of prologue / exit into the row behind the per-tile rows of the trace buffer
+#define TC_STAMP_CTA(ev) do { if (p.trace != nullptr && blockIdx.x == 0 && tid == 0) p.trace[p.trace_tiles * 16 + (ev)] = clock64(); } while (0)
+  TC_STAMP_CTA(0);
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TM_COLS);
   if (tid == 32) {
     mbar_init(bar(B_WFULL), 1);
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  TC_STAMP_CTA(1);
 
   if (!has_work) {
     if (tid == 32) { mbar_wait(bar(B_WFULL), 0u); mbar_wait(bar(B_W1FULL), 0u); }      // (device-side list shorter than the grid) the bulk copies must land before the CTA exits
@@ -683,6 +688,7 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
   }
   tc_fence_before();
   __syncthreads();
+  TC_STAMP_CTA(2);
   if (warp == 0) tmem_dealloc(tmem, TM_COLS);
 }
 

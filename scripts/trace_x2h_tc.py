@@ -33,15 +33,21 @@ Cc[T].copy_(state['c_lig'])
 model.run_steps(state, [999, 998, 997], X, Cc)
 torch.cuda.synchronize()
 NT = 40
-buf = torch.zeros((NT, 16), dtype=torch.int64, device=dev)
+buf = torch.zeros((NT + 1, 16), dtype=torch.int64, device=dev)      # row NT: kernel entry / end of prologue / exit of CTA 0
 _lib.check(L.cbg_debug_x2h_trace(buf.data_ptr(), NT))
 model.run_steps(state, [996], X, Cc)          # one-shot hook: the first (layer 0) attention-weight launch of this step
 torch.cuda.synchronize()
 _lib.check(L.cbg_debug_x2h_trace(None, 0))
 t = buf.cpu().numpy()
-n = int((t[:, 0] > 0).sum())
+n = int((t[:NT, 0] > 0).sum())
 base = t[0, 10] if t[0, 10] > 0 else t[:n].min()
 print('tiles recorded', n)
+cta = t[NT]
+if cta[0] > 0:
+    last = t[n - 1]
+    print(f'CTA 0: entry -> end of prologue {cta[1] - cta[0]} clks; prologue -> first MMA1 issued {t[0, 11] - cta[1]}; '
+          f'entry -> S1 of tile 0 starts {t[0, 0] - cta[0]}; last S1 done -> exit {cta[2] - last[4]}; '
+          f'last EPI done -> exit {cta[2] - last[9]}; whole kernel {cta[2] - cta[0]} clks for {n} tiles')
 names = ['S1st', 'Gblt', 'preLd', 'pairB', 'S1dn', 'S1st1', 'S1dn1', 'EPIh0', 'EPIh1', 'EPIdn', 'GPrdy', 'MMA1i', 'Ardy', 'MMA2i', 'PRst', 'PRdn']
 print('tile ' + ' '.join(f'{x:>7s}' for x in names))
 for k in range(min(n, 16)):
