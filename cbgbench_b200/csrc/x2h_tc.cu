@@ -442,50 +442,54 @@ __global__ void __launch_bounds__(544, 1) x2h_tc_kernel(EdgeArgs p, TcWeights W)
         const float ax = warp_sum_x(sacc * hv[0]), ay = warp_sum_x(sacc * hv[1]), az = warp_sum_x(sacc * hv[2]);
         if (live && lane == 0) st4(p.dx + 4 * (size_t)n, make_float4(ax * (1.f / 16.f), ay * (1.f / 16.f), az * (1.f / 16.f), 0.f));
       } else {
+        // Four rounds of 32 columns (features 32 p .. 32 p + 31).  This warp is the critical one of the aggregation kernel
+        // (TMEM load -> scale -> transpose -> reduce -> store, four dependent rounds per tile), so the TMEM load of round
+        // p + 1 is issued as soon as round p's registers have gone to shared memory and flies during the reduction.
+        mbar_wait(bar(B_ACC2), (uint32_t)(k & 1));
+        tc_fence_after();
+        if (warp == 0) TC_STAMP(k, 7);
+        uint32_t r[32];
+        tmem_ld32_nowait(t_lane + TM_OUT, r);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h == 0) { mbar_wait(bar(B_ACC2), (uint32_t)(k & 1)); tc_fence_after(); }
-          if (warp == 0) TC_STAMP(k, 7 + h);
-#pragma unroll
-          for (int qq = 0; qq < 2; ++qq) {           // 32 columns at a time: features 64h + 32qq + (0..31)
-            uint32_t r[32];
-            tmem_ld32_nowait(t_lane + TM_OUT + 64u * h + 32u * qq, r);
-            tmem_wait_ld();
-            if (h == 1 && qq == 1) {      // last piece of the accumulator row is in registers
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar(B_ACC2FREE));
-            }
-            // (v + b1v) * w -> this lane's row of the transpose buffer (stride 36 words: 16-byte stores conflict free),
-            // then lane l sums column l over the node's 32 edges (fixed order: deterministic)
-            float* vrow = s_vr + lane * 36;
-#pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              const float4 b1 = *reinterpret_cast<const float4*>(s_b1 + 64 * h + 32 * qq + 4 * c4);
-              const float wh = wv[8 * h + 4 * qq + (c4 >> 1)];
-              float4 o;
-              o.x = fmaf(__uint_as_float(r[4 * c4 + 0]), kInvOut, b1.x) * wh;
-              o.y = fmaf(__uint_as_float(r[4 * c4 + 1]), kInvOut, b1.y) * wh;
-              o.z = fmaf(__uint_as_float(r[4 * c4 + 2]), kInvOut, b1.z) * wh;
-              o.w = fmaf(__uint_as_float(r[4 * c4 + 3]), kInvOut, b1.w) * wh;
-              *reinterpret_cast<float4*>(vrow + 4 * c4) = o;
-            }
+        for (int pp = 0; pp < 4; ++pp) {
+          const int h = pp >> 1, qq = pp & 1;
+          tmem_wait_ld();
+          if (pp == 3) {      // last piece of the accumulator row is in registers
+            tc_fence_before();
             __syncwarp();
-            float val[1];
-            {
-              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-              for (int e = 0; e < 32; e += 4) {
-                s0 += s_vr[(e + 0) * 36 + lane];
-                s1 += s_vr[(e + 1) * 36 + lane];
-                s2 += s_vr[(e + 2) * 36 + lane];
-                s3 += s_vr[(e + 3) * 36 + lane];
-              }
-              val[0] = (s0 + s1) + (s2 + s3);
-            }
-            __syncwarp();
-            if (live) p.h[(size_t)i * CBG_H + 64 * h + 32 * qq + lane] = hv[2 * h + qq] + val[0];
+            if (lane == 0) mbar_arrive(bar(B_ACC2FREE));
           }
+          if (warp == 0 && pp == 2) TC_STAMP(k, 8);
+          // (v + b1v) * w -> this lane's row of the transpose buffer (stride 36 words: 16-byte stores conflict free),
+          // then lane l sums column l over the node's 32 edges (fixed order: deterministic)
+          float* vrow = s_vr + lane * 36;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const float4 b1 = *reinterpret_cast<const float4*>(s_b1 + 64 * h + 32 * qq + 4 * c4);
+            const float wh = wv[8 * h + 4 * qq + (c4 >> 1)];
+            float4 o;
+            o.x = fmaf(__uint_as_float(r[4 * c4 + 0]), kInvOut, b1.x) * wh;
+            o.y = fmaf(__uint_as_float(r[4 * c4 + 1]), kInvOut, b1.y) * wh;
+            o.z = fmaf(__uint_as_float(r[4 * c4 + 2]), kInvOut, b1.z) * wh;
+            o.w = fmaf(__uint_as_float(r[4 * c4 + 3]), kInvOut, b1.w) * wh;
+            *reinterpret_cast<float4*>(vrow + 4 * c4) = o;
+          }
+          if (pp < 3) tmem_ld32_nowait(t_lane + TM_OUT + 32u * (uint32_t)(pp + 1), r);
+          __syncwarp();
+          float val;
+          {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              s0 += s_vr[(e + 0) * 36 + lane];
+              s1 += s_vr[(e + 1) * 36 + lane];
+              s2 += s_vr[(e + 2) * 36 + lane];
+              s3 += s_vr[(e + 3) * 36 + lane];
+            }
+            val = (s0 + s1) + (s2 + s3);
+          }
+          __syncwarp();
+          if (live) p.h[(size_t)i * CBG_H + 32 * pp + lane] = hv[pp] + val;
         }
       }
       if (warp == 0) TC_STAMP(k, 9);

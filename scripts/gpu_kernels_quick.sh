@@ -1,5 +1,5 @@
 #!/bin/bash
-# H2X tc + node GEMM coalesced epilogue: kernel tests, parity suite (without the full-size file), bench, traces
+# edge-kernel iteration loop: kernel tests, parity suite (without the full-size file), bench, traces
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_x2h_tc.py tests/test_gpu_parity.py tests/test_f2_samplers.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_h2x.log 2>&1; echo "tests rc=$?"; tail -8 gpurun_out/pytest_h2x.log | cut -c1-300
 timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline > gpurun_out/bench_q.log 2>&1; echo "bench rc=$?"

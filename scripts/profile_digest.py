@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Turn the artefacts of scripts/gpu_final_profile.sh (gpurun_out/) into the tracked evidence under profiles/:
+"""Turn the artefacts of scripts/gpu_r2_validate.sh (gpurun_out/) into the tracked evidence under profiles/:
 ncu summaries per kernel, the launch-share table of one bench step and profiles/ncu_traffic.json (DRAM bytes per launch
 of the dominant kernels, read by bench.py for roofline.traffic).   python scripts/profile_digest.py <tag>"""
 import collections
