@@ -796,10 +796,12 @@ int cbg_launch_x2h_tc(const EdgeArgs& a, cudaStream_t st) {
   const int grid = tiles < g_tc_sms ? tiles : g_tc_sms;
   EdgeArgs ak = a;
   ak.w_compact = 0;
-  ak.trace = g_tc_trace; ak.trace_tiles = g_tc_trace_tiles;          // debugging hook: one-shot, the next k kernel launch only
-  g_tc_trace = nullptr;
   EdgeArgs av = a;
   av.w_compact = 0;
+  // debugging hook: one-shot, the next attention-weight launch (max_tiles > 0) or aggregation launch (max_tiles < 0) only
+  if (g_tc_trace_tiles >= 0) { ak.trace = g_tc_trace; ak.trace_tiles = g_tc_trace_tiles; }
+  else { av.trace = g_tc_trace; av.trace_tiles = -g_tc_trace_tiles; }
+  g_tc_trace = nullptr;
   const float* L = a.layer;
   const TcWeights wk{L + kOffKW1, L + kOffKWg, L + kOffKLn, nullptr, L + kOffRbf};
   const TcWeights wv{L + kOffVW1, L + kOffVWg, L + kOffVLn, L + kOffVB1, L + kOffRbf};

@@ -61,8 +61,9 @@ int32_t cbg_set_edge_impl(int32_t impl, int32_t warps);
  * d[128][128] (fp32) = a[128][32] * b[128][32]^T with f16 row-major device inputs; a_from_smem = 0 feeds A from
  * tensor memory (tcgen05.st, two K-consecutive f16 per column), 1 from shared memory (canonical K-major layout). */
 int32_t cbg_selftest_umma_f16(const void* a, const void* b, float* d, int32_t a_from_smem, void* stream);
-/* Debugging: later launches of the tcgen05 attention-weight kernel stamp the pipeline events of CTA 0 (SM clock) into
- * buf_dev[max_tiles][16] (int64, device memory); NULL turns it off.  Process-wide. */
+/* Debugging: the next launch of the tcgen05 attention-weight kernel (max_tiles > 0) or aggregation kernel (max_tiles < 0,
+ * |max_tiles| rows) stamps the pipeline events of CTA 0 (SM clock) into buf_dev[|max_tiles| + 1][16] (int64, device memory;
+ * the last row takes kernel entry / end of prologue / exit); NULL turns it off.  Process-wide, one-shot. */
 int32_t cbg_debug_x2h_trace(int64_t* buf_dev, int32_t max_tiles);
 /* debug: %globaltimer stamps (ns) of CTA 0 of every following f16 node-GEMM launch into buf_dev[32] (NULL = off):
  * [0] start, [1] A tile staged, [2+g] accumulator g complete, [10+g] epilogue of g done, [20] end */

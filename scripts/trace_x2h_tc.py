@@ -34,14 +34,15 @@ model.run_steps(state, [999, 998, 997], X, Cc)
 torch.cuda.synchronize()
 NT = 40
 buf = torch.zeros((NT + 1, 16), dtype=torch.int64, device=dev)      # row NT: kernel entry / end of prologue / exit of CTA 0
-_lib.check(L.cbg_debug_x2h_trace(buf.data_ptr(), NT))
+WHICH = -1 if (len(sys.argv) > 1 and sys.argv[1] == 'v') else 1        # 'v': the aggregation kernel
+_lib.check(L.cbg_debug_x2h_trace(buf.data_ptr(), WHICH * NT))
 model.run_steps(state, [996], X, Cc)          # one-shot hook: the first (layer 0) attention-weight launch of this step
 torch.cuda.synchronize()
 _lib.check(L.cbg_debug_x2h_trace(None, 0))
 t = buf.cpu().numpy()
 n = int((t[:NT, 0] > 0).sum())
 base = t[0, 10] if t[0, 10] > 0 else t[:n].min()
-print('tiles recorded', n)
+print('kernel:', 'aggregation (MODE_V)' if WHICH < 0 else 'attention weights (MODE_K)', '- tiles recorded', n)
 cta = t[NT]
 if cta[0] > 0:
     last = t[n - 1]
