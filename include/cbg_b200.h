@@ -51,8 +51,8 @@ const char* cbg_profile_family_name(int32_t i);
 int32_t cbg_profile_enable(int32_t on);
 int32_t cbg_profile_collect(double* ms_per_family, int64_t* launches_per_family);
 
-/* TESTING hook (process-wide, not thread-safe; production code never calls it): implementation of the two fused X2H
- * edge kernels.  impl 6 (default): tcgen05 kernels (csrc/x2h_tc.cu: A operands in tensor memory, f16 hi/lo split);
+/* TESTING hook (process-wide, not thread-safe; production code never calls it): implementation of the fused X2H / H2X
+ * edge kernels.  impl 6 (default): the tcgen05 tile kernel (csrc/x2h_tc.cu: A operands in tensor memory, f16 hi/lo split);
  * impl 0: the fp32 SIMT kernels (csrc/edge.cu), kept as an independent implementation for the parity tests - the only
  * consumer of the optional R-cache.  warps = CTA size of the SIMT kernels (8, 12, 16; 0 keeps the current value).
  * Also env CBG_EDGE_IMPL / CBG_EDGE_WARPS.  Needs a current CUDA device. */
