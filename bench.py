@@ -336,11 +336,13 @@ def run_b200(args):
             rows_src = sum(cnt[l] for l in range(n_layers)) / n_layers          # rows whose Pj plane a launch may gather
         else:
             rows_src = rows
-        traffic = None
+        traffic, ncu_info = None, None
         tpath = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')      # dram bytes/launch from the last ncu --set full capture
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = (json.load(f).get(dom + '_tc') or {}).get('dram_bytes_per_launch')
+                rec = json.load(f).get(dom + '_tc') or {}
+            traffic = rec.get('dram_bytes_per_launch')
+            ncu_info = rec.get('ncu')
         # The fused X2H kernels (csrc/x2h_tc.cu) are TENSOR-bound, not HBM-bound: per 128-edge tile
         # they issue 17 + 48 tcgen05 MMAs, nothing of size [E, 128] crosses HBM.
         #   executed tensor FLOPs per tile = 17 x (128 x 128 x 16 x 2) + 48 x (128 x 64 x 16 x 2); the (hi, lo) f16 split
@@ -366,7 +368,11 @@ def run_b200(args):
                     'hbm': {'algorithmic_bytes_per_launch': alg_bytes, 'achieved_gbs': hbm, 'peak_gbs': peaks['hbm_gbs'],
                             'frac': hbm / peaks['hbm_gbs'],
                             'note': "the north-star's 60 % HBM target assumed per-edge k/v tensors crossing HBM (9.9 GB/step); they are "
-                                    'never materialised, the kernel moves ~4 KB per node and is bounded by the tensor pipe'}}
+                                    'never materialised, the kernel moves ~4 KB per node and is bounded on the compute side'},
+                    # what shares the SM with the tensor pipe: LSU wavefronts of the last ncu capture of
+                    # this kernel (unpruned launch, 5184 tiles) and the B-operand bytes the 41 MMAs of a tile read from shared memory
+                    'shared_memory': {'ncu_capture': ncu_info, 'mma_b_operand_bytes_per_tile': 41 * 128 * 16 * 2,
+                                      'note': 'static evidence from profiles/ncu_traffic.json (ncu --set full), not measured in this run'}}
 
     # ---- end to end through the public API: host batch -> model.sample() -> host trajectory -------
     e2e = None

@@ -32,7 +32,13 @@ def dram_bytes(rep):
     for vals in rows[2:]:
         m = dict(zip(hdr, vals))
         tot = sum(float(m[k].replace(',', '')) * scale.get(units[k], 1) for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
-        res.append((m['Kernel Name'], int(tot), float(m['gpu__time_duration.sum'].replace(',', ''))))
+        num = lambda k: float(m[k].replace(',', '')) if k in m and m[k] else None
+        extra = {'lsu_shared_wavefronts': num('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum'),
+                 'tensor_pipe_active_pct': num('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'),
+                 'issue_active_pct': num('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+                 'sm_cycles_elapsed_max': num('sm__cycles_elapsed.max'), 'grid': num('launch__grid_size'),
+                 'registers_per_thread': num('launch__registers_per_thread')}
+        res.append((m['Kernel Name'], int(tot), float(m['gpu__time_duration.sum'].replace(',', '')), extra))
     return res
 
 
@@ -51,8 +57,8 @@ def main():
         with open(os.path.join(PROF, f'{rnd}_ncu_{kernel}_{tag}.txt'), 'w') as f:
             f.write(txt.replace(OUT + os.sep, 'gpurun_out/'))
         if kernel == 'x2h_tc_kernel':       # launch 0 = attention weights (mode 0), launch 1 = aggregation (mode 1)
-            for (name, nbytes, us), fam in zip(dram_bytes(rep), ('x2h_k_tc', 'x2h_v_tc')):
-                traffic[fam] = {'dram_bytes_per_launch': nbytes, 'duration_us': us, 'kernel': name}
+            for (name, nbytes, us, extra), fam in zip(dram_bytes(rep), ('x2h_k_tc', 'x2h_v_tc')):
+                traffic[fam] = {'dram_bytes_per_launch': nbytes, 'duration_us': us, 'kernel': name, 'ncu': extra}
     if len(traffic) > 1:
         with open(os.path.join(PROF, 'ncu_traffic.json'), 'w') as f:
             json.dump(traffic, f, indent=1)
